@@ -1,0 +1,70 @@
+// Library-level entry points: version, error reporting, device query, GEMM dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace {
+thread_local char g_err[512] = {0};
+}
+
+void csts_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int csts_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    csts_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 4;
+  }
+  return 0;
+}
+
+int csts_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+extern "C" {
+
+int csts_version(void) { return 100; }
+
+// copies the calling thread's last error message; returns its length
+int csts_last_error(char* buf, int len) {
+  if (!buf || len <= 0) return (int)strlen(g_err);
+  strncpy(buf, g_err, (size_t)len - 1);
+  buf[len - 1] = 0;
+  return (int)strlen(buf);
+}
+
+// 0 when the current device is sm_100 (B200); non-zero with a message otherwise.  No other
+// architecture is supported and there is no fallback.
+int csts_check_device(void) {
+  int dev = 0, major = 0, minor = 0;
+  CSTS_CUDA(cudaGetDevice(&dev));
+  CSTS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CSTS_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  CSTS_REQUIRE(major == 10, "libcsts_b200 is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+  return 0;
+}
+
+int csts_gemm(const csts_gemm_args* a, void* stream) {
+  CSTS_REQUIRE(a != nullptr, "gemm: null argument block");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->backend == 1) return csts_gemm_mma_launch(*a, st);
+  if (a->backend == 2) return csts_gemm_tc_launch(*a, st);
+  if (csts_gemm_tc_supported(*a)) return csts_gemm_tc_launch(*a, st);
+  return csts_gemm_mma_launch(*a, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,462 @@
+// Token-grid kernels: depthwise 3x3x3 conv / transposed conv over the (T,H,W) token grid with a fused
+// LayerNorm(head_dim) epilogue, its weight gradient, the MaxPool3d and trilinear skip paths.
+// They read and write the token-major layouts the GEMMs produce ((B, N, 3, heads, d) qkv slices,
+// (B, heads, L, d) pooled tensors, (B, N, C) residual streams) directly through element strides, so
+// the reference's permute+contiguous copies (attention.py:31,37) never happen.
+#include "common.cuh"
+#include "grid_ops.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Gather-form depthwise conv.
+//   regular   : out[o] = sum_tap w[tap] * in[o*s + tap - 1]
+//   transposed: out[o] = sum_tap w[tap] * in[(o + 1 - tap) / s]     (when divisible and in range)
+// One warp per output position; lane owns channels [4*lane, 4*lane+4) and, for d = 192, also
+// [128 + 4*lane, ...).  Weights live in shared memory as [tap][d].
+// ------------------------------------------------------------------------------------------------
+template <int D, bool TRANSPOSED, bool NORM>
+__global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p) {
+  constexpr int NJ = (D + 127) / 128;
+  __shared__ float s_w[27 * D];
+  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
+    int tap = i / D, c = i - tap * D;
+    s_w[i] = p.w[c * 27 + tap];               // parameter layout (d,1,3,3,3) -> [tap][c]
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int Lo = p.To * p.Ho * p.Wo;
+  const int64_t total = (int64_t)p.B * p.heads * Lo;
+  const bf16* in = reinterpret_cast<const bf16*>(p.in);
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  bf16* pre = reinterpret_cast<bf16*>(p.pre);
+
+  for (int64_t idx = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); idx < total; idx += (int64_t)gridDim.x * wpb) {
+    int o = (int)(idx % Lo);
+    int bh = (int)(idx / Lo);
+    int hd = bh % p.heads, b = bh / p.heads;
+    int wo = o % p.Wo, ho = (o / p.Wo) % p.Ho, to = o / (p.Wo * p.Ho);
+    const bf16* in_bh = in + b * p.in_sB + hd * p.in_sH;
+    float acc[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      int ti;
+      if (TRANSPOSED) { int num = to + 1 - kt; if (num < 0 || num % p.st) continue; ti = num / p.st; }
+      else ti = to * p.st + kt - 1;
+      if (ti < 0 || ti >= p.Ti) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        int hi;
+        if (TRANSPOSED) { int num = ho + 1 - kh; if (num < 0 || num % p.sh) continue; hi = num / p.sh; }
+        else hi = ho * p.sh + kh - 1;
+        if (hi < 0 || hi >= p.Hi) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          int wi;
+          if (TRANSPOSED) { int num = wo + 1 - kw; if (num < 0 || num % p.sw) continue; wi = num / p.sw; }
+          else wi = wo * p.sw + kw - 1;
+          if (wi < 0 || wi >= p.Wi) continue;
+          const bf16* src = in_bh + (int64_t)((ti * p.Hi + hi) * p.Wi + wi) * p.in_sP;
+          const float* wt = s_w + ((kt * 3 + kh) * 3 + kw) * D;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            int c = 4 * lane + 128 * j;
+            if (c < D) {
+              float v[4], w4[4];
+              ld4(src + c, v);
+              ld4(wt + c, w4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(v[i], w4[i], acc[j][i]);
+            }
+          }
+        }
+      }
+    }
+    bf16* dst = out + b * p.out_sB + hd * p.out_sH + (int64_t)o * p.out_sP;
+    if (!NORM) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int c = 4 * lane + 128 * j;
+        if (c < D) st4(dst + c, acc[j]);
+      }
+    } else {
+      // the raw conv result is rounded to bf16 first (it is what backward re-reads), and the
+      // statistics are taken from the rounded values so forward and backward agree exactly
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int c = 4 * lane + 128 * j;
+        if (c < D) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { acc[j][i] = __bfloat162float(__float2bfloat16_rn(acc[j][i])); s += acc[j][i]; }
+        }
+      }
+      const float mean = warp_sum(s) * (1.f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int c = 4 * lane + 128 * j;
+        if (c < D) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { float dlt = acc[j][i] - mean; q += dlt * dlt; }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + p.eps);
+      if (lane == 0) { p.mean[idx] = mean; p.rstd[idx] = rstd; }
+      bf16* pdst = pre + idx * D;                 // pre is dense (B, heads, Lo, d)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        int c = 4 * lane + 128 * j;
+        if (c < D) {
+          float g[4], be[4], y[4];
+          ld4(p.gamma + c, g);
+          ld4(p.beta + c, be);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = (acc[j][i] - mean) * rstd * g[i] + be[i];
+          st4(pdst + c, acc[j]);
+          st4(dst + c, y);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise weight gradient:  dw[c][tap] += sum_{b,head,o} small[o][c] * big[o*s + tap - 1][c]
+// (conv: small = d(conv out), big = conv in;  transposed conv: small = conv in, big = d(out)).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(csts_wgrad_args p) {
+  constexpr int NJ = (D + 127) / 128;
+  __shared__ float s_dw[27 * D];
+  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int Ls = p.Ts * p.Hs * p.Ws;
+  const int64_t total = (int64_t)p.B * p.heads * Ls;
+  const bf16* small = reinterpret_cast<const bf16*>(p.small);
+  const bf16* big = reinterpret_cast<const bf16*>(p.big);
+  float acc[NJ][27][4];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int t = 0; t < 27; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][t][i] = 0.f;
+
+  for (int64_t idx = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); idx < total; idx += (int64_t)gridDim.x * wpb) {
+    int o = (int)(idx % Ls);
+    int bh = (int)(idx / Ls);
+    int hd = bh % p.heads, b = bh / p.heads;
+    int wo = o % p.Ws, ho = (o / p.Ws) % p.Hs, to = o / (p.Ws * p.Hs);
+    const bf16* sp = small + b * p.small_sB + hd * p.small_sH + (int64_t)o * p.small_sP;
+    const bf16* big_bh = big + b * p.big_sB + hd * p.big_sH;
+    float sv[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int c = 4 * lane + 128 * j;
+      if (c < D) ld4(sp + c, sv[j]);
+    }
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      int ti = to * p.st + kt - 1;
+      if (ti < 0 || ti >= p.Tb) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        int hi = ho * p.sh + kh - 1;
+        if (hi < 0 || hi >= p.Hb) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          int wi = wo * p.sw + kw - 1;
+          if (wi < 0 || wi >= p.Wb) continue;
+          const bf16* bp = big_bh + (int64_t)((ti * p.Hb + hi) * p.Wb + wi) * p.big_sP;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            int c = 4 * lane + 128 * j;
+            if (c < D) {
+              float v[4];
+              ld4(bp + c, v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[j][(kt * 3 + kh) * 3 + kw][i] = fmaf(v[i], sv[j][i], acc[j][(kt * 3 + kh) * 3 + kw][i]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int c = 4 * lane + 128 * j;
+    if (c < D) {
+#pragma unroll
+      for (int t = 0; t < 27; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[t * D + c + i], acc[j][t][i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
+    int tap = i / D, c = i - tap * D;
+    atomicAdd(p.dw + c * 27 + tap, s_dw[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool3d k(1,3,3) s(1,2,2) p(0,1,1) on a token-major f32 stream (B, T*H*W, C).
+// ref: attention.py:225-236 (pool_skip).  `arg` records the winning tap (0..8) per output element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ arg,
+                                                          int B, int T, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const int64_t total = (int64_t)B * T * Ho * Wo * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    int64_t pos = i / C4;
+    int wo = (int)(pos % Wo), ho = (int)((pos / Wo) % Ho);
+    int64_t bt = pos / ((int64_t)Wo * Ho);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int hi = ho * 2 + kh - 1;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int wi = wo * 2 + kw - 1;
+        if (wi < 0 || wi >= W) continue;
+        float v[4];
+        ld4(x + ((bt * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (v[k] > best[k]) { best[k] = v[k]; bi[k] = kh * 3 + kw; }
+      }
+    }
+    st4(y + pos * C + c, best);
+    if (arg) *reinterpret_cast<uchar4*>(arg + pos * C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+// dx[i] = sum over the (<= 4) windows containing i of dy[o] * [arg[o] == tap(i, o)]
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                                          float* __restrict__ dx, int B, int T, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const int64_t total = (int64_t)B * T * H * W * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    int64_t pos = i / C4;
+    int wi = (int)(pos % W), hi = (int)((pos / W) % H);
+    int64_t bt = pos / ((int64_t)W * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int num = hi + 1 - kh;
+      if (num < 0 || (num & 1)) continue;
+      int ho = num >> 1;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int numw = wi + 1 - kw;
+        if (numw < 0 || (numw & 1)) continue;
+        int wo = numw >> 1;
+        if (wo >= Wo) continue;
+        int64_t op = ((bt * Ho + ho) * Wo + wo) * C + c;
+        uchar4 a = *reinterpret_cast<const uchar4*>(arg + op);
+        float v[4];
+        ld4(dy + op, v);
+        int tap = kh * 3 + kw;
+        if (a.x == tap) acc[0] += v[0];
+        if (a.y == tap) acc[1] += v[1];
+        if (a.z == tap) acc[2] += v[2];
+        if (a.w == tap) acc[3] += v[3];
+      }
+    }
+    st4(dx + pos * C + c, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Trilinear up-sampling (align_corners=False) by integer factors (ft, fh, fw) on a token-major f32
+// stream.  ref: attention.py:463-467 (nn.Upsample) and custom_multimodal_builder.py:479.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_coef(int o, int f, int n_in, int& i0, int& i1, float& lam) {
+  if (f == 1) { i0 = i1 = o; lam = 0.f; return; }
+  float src = ((float)o + 0.5f) / (float)f - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+  lam = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int H, int W,
+                                                           int C, int ft, int fh, int fw) {
+  const int To = T * ft, Ho = H * fh, Wo = W * fw, C4 = C / 4;
+  const int64_t total = (int64_t)B * To * Ho * Wo * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    int64_t pos = i / C4;
+    int wo = (int)(pos % Wo), ho = (int)((pos / Wo) % Ho), to = (int)((pos / ((int64_t)Wo * Ho)) % To);
+    int64_t b = pos / ((int64_t)Wo * Ho * To);
+    int t0, t1, h0, h1, w0, w1;
+    float lt, lh, lw;
+    lin_coef(to, ft, T, t0, t1, lt);
+    lin_coef(ho, fh, H, h0, h1, lh);
+    lin_coef(wo, fw, W, w0, w1, lw);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      float ct = a ? lt : 1.f - lt;
+      if (ct == 0.f) continue;
+      int ti = a ? t1 : t0;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        float ch = bb ? lh : 1.f - lh;
+        if (ch == 0.f) continue;
+        int hi = bb ? h1 : h0;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float cw = cc ? lw : 1.f - lw;
+          if (cw == 0.f) continue;
+          int wi = cc ? w1 : w0;
+          float v[4];
+          ld4(x + (((b * T + ti) * H + hi) * W + wi) * C + c, v);
+          float wgt = ct * ch * cw;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+        }
+      }
+    }
+    st4(y + pos * C + c, acc);
+  }
+}
+// gather form of the adjoint: each input position sums the outputs that interpolate from it
+__device__ __forceinline__ float lin_adj(int i, int o, int f, int n_in) {
+  int i0, i1; float lam;
+  lin_coef(o, f, n_in, i0, i1, lam);
+  float w = 0.f;
+  if (i0 == i) w += 1.f - lam;
+  if (i1 == i) w += lam;
+  return w;
+}
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int T, int H, int W,
+                                                           int C, int ft, int fh, int fw, int accumulate) {
+  const int To = T * ft, Ho = H * fh, Wo = W * fw, C4 = C / 4;
+  const int64_t total = (int64_t)B * T * H * W * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    int64_t pos = i / C4;
+    int wi = (int)(pos % W), hi = (int)((pos / W) % H), ti = (int)((pos / ((int64_t)W * H)) % T);
+    int64_t b = pos / ((int64_t)W * H * T);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int tlo = ft == 1 ? ti : max(ti * ft - ft, 0), thi = ft == 1 ? ti : min(ti * ft + 2 * ft - 1, To - 1);
+    int hlo = fh == 1 ? hi : max(hi * fh - fh, 0), hhi = fh == 1 ? hi : min(hi * fh + 2 * fh - 1, Ho - 1);
+    int wlo = fw == 1 ? wi : max(wi * fw - fw, 0), whi = fw == 1 ? wi : min(wi * fw + 2 * fw - 1, Wo - 1);
+    for (int to = tlo; to <= thi; ++to) {
+      float ct = lin_adj(ti, to, ft, T);
+      if (ct == 0.f) continue;
+      for (int ho = hlo; ho <= hhi; ++ho) {
+        float ch = lin_adj(hi, ho, fh, H);
+        if (ch == 0.f) continue;
+        for (int wo = wlo; wo <= whi; ++wo) {
+          float cw = lin_adj(wi, wo, fw, W);
+          if (cw == 0.f) continue;
+          float v[4];
+          ld4(dy + (((b * To + to) * Ho + ho) * Wo + wo) * C + c, v);
+          float wgt = ct * ch * cw;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+        }
+      }
+    }
+    float* d = dx + pos * C + c;
+    if (accumulate) {
+      float o[4];
+      ld4(d, o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += o[k];
+    }
+    st4(d, acc);
+  }
+}
+
+int grid_for(int64_t work_items, int per_block) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)csts_num_sms() * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <int D>
+int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
+  int64_t total = (int64_t)p.B * p.heads * p.To * p.Ho * p.Wo;
+  int grid = grid_for(total, 8);
+  bool norm = p.gamma != nullptr;
+  if (p.transposed) {
+    if (norm) dwconv_kernel<D, true, true><<<grid, 256, 0, st>>>(p);
+    else dwconv_kernel<D, true, false><<<grid, 256, 0, st>>>(p);
+  } else {
+    if (norm) dwconv_kernel<D, false, true><<<grid, 256, 0, st>>>(p);
+    else dwconv_kernel<D, false, false><<<grid, 256, 0, st>>>(p);
+  }
+  return csts_check_launch("dwconv");
+}
+
+}  // namespace
+
+extern "C" {
+
+int csts_dwconv(const csts_pool_args* p, void* stream) {
+  CSTS_REQUIRE(p->d == 96 || p->d == 192, "dwconv: head_dim %d unsupported (96 or 192)", p->d);
+  CSTS_REQUIRE(p->in_sB % 4 == 0 && p->in_sH % 4 == 0 && p->in_sP % 4 == 0 && p->out_sB % 4 == 0 && p->out_sH % 4 == 0 &&
+                   p->out_sP % 4 == 0, "dwconv: strides must be multiples of 4 elements");
+  CSTS_REQUIRE(((uintptr_t)p->in & 7) == 0 && ((uintptr_t)p->out & 7) == 0, "dwconv: in/out must be 8-byte aligned");
+  if (p->gamma) CSTS_REQUIRE(p->beta && p->pre && p->mean && p->rstd, "dwconv: norm epilogue needs beta/pre/mean/rstd");
+  if ((int64_t)p->B * p->heads * p->To * p->Ho * p->Wo == 0) return 0;
+  return p->d == 96 ? launch_dwconv<96>(*p, (cudaStream_t)stream) : launch_dwconv<192>(*p, (cudaStream_t)stream);
+}
+
+int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
+  CSTS_REQUIRE(p->d == 96 || p->d == 192, "dwconv_wgrad: head_dim %d unsupported", p->d);
+  int64_t total = (int64_t)p->B * p->heads * p->Ts * p->Hs * p->Ws;
+  if (total == 0) return 0;
+  // few, long-running blocks: every block ends with 27*d global atomics
+  int64_t blocks = (total + 255) / 256;
+  int grid = (int)(blocks < csts_num_sms() * 2 ? blocks : csts_num_sms() * 2);
+  if (p->d == 96) dwconv_wgrad_kernel<96><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  else dwconv_wgrad_kernel<192><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  return csts_check_launch("dwconv_wgrad");
+}
+
+int csts_maxpool_fwd(const float* x, float* y, void* arg, int B, int T, int H, int W, int C, void* stream) {
+  CSTS_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: C%%4, H%%2, W%%2 required");
+  int64_t total = (int64_t)B * T * (H / 2) * (W / 2) * (C / 4);
+  if (total == 0) return 0;
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, (uint8_t*)arg, B, T, H, W, C);
+  return csts_check_launch("maxpool_fwd");
+}
+int csts_maxpool_bwd(const float* dy, const void* arg, float* dx, int B, int T, int H, int W, int C, void* stream) {
+  int64_t total = (int64_t)B * T * H * W * (C / 4);
+  if (total == 0) return 0;
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, (const uint8_t*)arg, dx, B, T, H, W, C);
+  return csts_check_launch("maxpool_bwd");
+}
+int csts_upsample_fwd(const float* x, float* y, int B, int T, int H, int W, int C, int ft, int fh, int fw, void* stream) {
+  CSTS_REQUIRE(C % 4 == 0 && ft >= 1 && fh >= 1 && fw >= 1, "upsample: bad arguments");
+  int64_t total = (int64_t)B * T * ft * H * fh * W * fw * (C / 4);
+  if (total == 0) return 0;
+  upsample_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, T, H, W, C, ft, fh, fw);
+  return csts_check_launch("upsample_fwd");
+}
+int csts_upsample_bwd(const float* dy, float* dx, int B, int T, int H, int W, int C, int ft, int fh, int fw, int accumulate, void* stream) {
+  CSTS_REQUIRE(C % 4 == 0 && ft >= 1 && fh >= 1 && fw >= 1, "upsample: bad arguments");
+  int64_t total = (int64_t)B * T * H * W * (C / 4);
+  if (total == 0) return 0;
+  upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, B, T, H, W, C, ft, fh, fw, accumulate);
+  return csts_check_launch("upsample_bwd");
+}
+
+}  // extern "C"

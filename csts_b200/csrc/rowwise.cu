@@ -1,0 +1,382 @@
+// Memory-bound row-wise kernels: LayerNorm fwd/bwd, attention softmax fwd/bwd, casts, column sums,
+// elementwise residual adds.  All HBM-bound: 128-bit (f32x4) / 64-bit (bf16x4) accesses, one warp per
+// row with shuffle reductions, grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_MAXJ = 6;   // width <= 6 * 128 = 768
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma + beta            ref: nn.LayerNorm (attention.py:239,243)
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int rows, int width, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_w = 1.f / (float)width;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const TI* xr = x + (int64_t)row * width;
+    float v[LN_MAXJ][4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      int c = (lane + 32 * j) * 4;
+      if (c < width) {
+        ld4(xr + c, v[j]);
+        s += v[j][0] + v[j][1] + v[j][2] + v[j][3];
+      }
+    }
+    const float mean = warp_sum(s) * inv_w;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      int c = (lane + 32 * j) * 4;
+      if (c < width) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float d = v[j][i] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_w + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    TO* yr = y + (int64_t)row * width;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      int c = (lane + 32 * j) * 4;
+      if (c < width) {
+        float g[4], b[4], o[4];
+        ld4(gamma + c, g);
+        ld4(beta + c, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        st4(yr + c, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dx = [add +] rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
+// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy  (per-warp registers -> smem -> one atomic per
+// column per block).
+// ------------------------------------------------------------------------------------------------
+template <typename TX, typename TDY, typename TDX>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ add,
+                                                            TDX* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int rows, int width) {
+  __shared__ float s_dg[768], s_db[768];
+  for (int i = threadIdx.x; i < width; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_w = 1.f / (float)width;
+  float adg[LN_MAXJ][4], adb[LN_MAXJ][4], g[LN_MAXJ][4];
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; ++j) {
+    int c = (lane + 32 * j) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { adg[j][i] = 0.f; adb[j][i] = 0.f; g[j][i] = 0.f; }
+    if (c < width) ld4(gamma + c, g[j]);
+  }
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const float mu = mean[row], rs = rstd[row];
+    const TX* xr = x + (int64_t)row * width;
+    const TDY* dyr = dy + (int64_t)row * width;
+    float xh[LN_MAXJ][4], gd[LN_MAXJ][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      int c = (lane + 32 * j) * 4;
+      if (c < width) {
+        float xv[4], dv[4];
+        ld4(xr + c, xv);
+        ld4(dyr + c, dv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[j][i] = (xv[i] - mu) * rs;
+          adg[j][i] += dv[i] * xh[j][i];
+          adb[j][i] += dv[i];
+          gd[j][i] = dv[i] * g[j][i];
+          s1 += gd[j][i];
+          s2 += gd[j][i] * xh[j][i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_w;
+    s2 = warp_sum(s2) * inv_w;
+    TDX* dxr = dx + (int64_t)row * width;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      int c = (lane + 32 * j) * 4;
+      if (c < width) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = rs * (gd[j][i] - s1 - xh[j][i] * s2);
+        if (add) {
+          float a[4];
+          ld4(add + (int64_t)row * width + c, a);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] += a[i];
+        }
+        st4(dxr + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; ++j) {
+    int c = (lane + 32 * j) * 4;
+    if (c < width) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { atomicAdd(&s_dg[c + i], adg[j][i]); atomicAdd(&s_db[c + i], adb[j][i]); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) { atomicAdd(dgamma + i, s_dg[i]); atomicAdd(dbeta + i, s_db[i]); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention softmax over rows of S (f32, already scaled).  P is bf16 with leading dim ldp; columns
+// [n, ldp) are written as zero so that P can be a GEMM operand.  mask_hw > 0 selects the in-frame
+// block mask of SpatialAttention (ref av_attention.py:336-347): token i belongs to frame
+// i / mask_hw for i < T*mask_hw and to frame i - T*mask_hw otherwise; cross-frame logits get -1e8,
+// i.e. probability exactly 0 in fp32.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int frame_of(int i, int thw, int hw) { return i < thw ? i / hw : i - thw; }
+
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, int64_t rows, int n,
+                                                          int lds, int ldp, int nq, int mask_hw, int mask_t) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+    const float* s = S + row * lds;
+    bf16* p = P + row * ldp;
+    const int thw = mask_t * mask_hw;
+    const int fq = mask_hw > 0 ? frame_of((int)(row % nq), thw, mask_hw) : 0;
+    float mx = -INFINITY;
+    for (int c = lane; c < n; c += 32) {
+      bool ok = mask_hw <= 0 || frame_of(c, thw, mask_hw) == fq;
+      if (ok) mx = fmaxf(mx, s[c]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < n; c += 32) {
+      bool ok = mask_hw <= 0 || frame_of(c, thw, mask_hw) == fq;
+      if (ok) sum += __expf(s[c] - mx);
+    }
+    const float inv = 1.f / warp_sum(sum);
+    for (int c = lane; c < ldp; c += 32) {
+      float v = 0.f;
+      if (c < n) {
+        bool ok = mask_hw <= 0 || frame_of(c, thw, mask_hw) == fq;
+        if (ok) v = __expf(s[c] - mx) * inv;
+      }
+      p[c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// dS = scale * P o (dP - rowsum(dP o P)); dS bf16 with zeroed pad columns
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
+                                                          int64_t rows, int n, int ldp, int lddp, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+    const bf16* p = P + row * ldp;
+    const float* dp = dP + row * lddp;
+    bf16* ds = dS + row * ldp;
+    float dot = 0.f;
+    for (int c = lane; c < n; c += 32) dot += __bfloat162float(p[c]) * dp[c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < ldp; c += 32) {
+      float v = c < n ? scale * __bfloat162float(p[c]) * (dp[c] - dot) : 0.f;
+      ds[c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// casts / permutes / elementwise
+// ------------------------------------------------------------------------------------------------
+// f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns)
+__global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int cols, int ld_out) {
+  int64_t total = rows * ld_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / ld_out;
+    int c = (int)(i - r * ld_out);
+    dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+  }
+}
+__global__ void cast_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[4];
+    ld4(src + 4 * i, v);
+    st4(dst + 4 * i, v);
+  }
+}
+// src [a][b][c] -> dst [a][c][b]   (tile transpose through shared memory), TO in {float, bf16}
+template <typename TO>
+__global__ void permute_021_kernel(const float* __restrict__ src, TO* __restrict__ dst, int a, int b, int c) {
+  __shared__ float tile[32][33];
+  const int64_t base = (int64_t)blockIdx.z * b * c;
+  int b0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int bb = b0 + i, cc = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (bb < b && cc < c) ? src[base + (int64_t)bb * c + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int cc = c0 + i, bb = b0 + threadIdx.x;
+    if (cc < c && bb < b) st_f(dst + base + (int64_t)cc * b + bb, tile[threadIdx.x][i]);
+  }
+}
+
+// out = a + b (f32), vectorised
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+// out = a * (*scalar)   (device scalar; used to apply the upstream loss gradient)
+__global__ void scale_kernel(const float* __restrict__ a, const float* __restrict__ scalar, float* __restrict__ out, int64_t n) {
+  const float s = *scalar;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] * s;
+}
+
+// column sums: out[n] += sum_m X[m][n]   (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, float* __restrict__ out, int64_t M, int N, int64_t ld,
+                                                     int rows_per_block) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col >= N) return;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = r0; r < r1; ++r) {
+    float v[4];
+    ld4(X + r * ld + col, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) atomicAdd(out + col + i, acc[i]);
+}
+
+int grid_for(int64_t work_items, int per_block) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)csts_num_sms() * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+// dtype codes: 0 = f32, 1 = bf16
+int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,
+                       float* rstd, int64_t rows, int width, float eps, void* stream) {
+  CSTS_REQUIRE(width % 4 == 0 && width <= 128 * LN_MAXJ, "layernorm: width %d unsupported (multiple of 4, <= 768)", width);
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(rows, 8);
+#define LN_FWD(TI, TO) layernorm_fwd_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, (int)rows, width, eps)
+  if (x_dtype == 0 && y_dtype == 1) LN_FWD(float, bf16);
+  else if (x_dtype == 0 && y_dtype == 0) LN_FWD(float, float);
+  else if (x_dtype == 1 && y_dtype == 1) LN_FWD(bf16, bf16);
+  else if (x_dtype == 1 && y_dtype == 0) LN_FWD(bf16, float);
+  else CSTS_REQUIRE(false, "layernorm: bad dtype codes %d %d", x_dtype, y_dtype);
+#undef LN_FWD
+  return csts_check_launch("layernorm_fwd");
+}
+
+int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                       const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
+                       int width, void* stream) {
+  CSTS_REQUIRE(width % 4 == 0 && width <= 128 * LN_MAXJ, "layernorm_bwd: width %d unsupported", width);
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (rows + 63) / 64;       // >= 8 rows per warp so the column atomics amortise
+  int grid = (int)(blocks < csts_num_sms() * 4 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 4);
+#define LN_BWD(TX, TDY, TDX) \
+  layernorm_bwd_kernel<TX, TDY, TDX><<<grid, 256, 0, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
+  if (x_dtype == 0 && dy_dtype == 1 && dx_dtype == 0) LN_BWD(float, bf16, float);
+  else if (x_dtype == 1 && dy_dtype == 1 && dx_dtype == 1) LN_BWD(bf16, bf16, bf16);
+  else if (x_dtype == 0 && dy_dtype == 0 && dx_dtype == 0) LN_BWD(float, float, float);
+  else CSTS_REQUIRE(false, "layernorm_bwd: unsupported dtype combination x=%d dy=%d dx=%d", x_dtype, dy_dtype, dx_dtype);
+#undef LN_BWD
+  return csts_check_launch("layernorm_bwd");
+}
+
+int csts_softmax_fwd(const float* S, void* P, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t, void* stream) {
+  if (rows == 0) return 0;
+  CSTS_REQUIRE(ldp >= n && lds >= n, "softmax: leading dims smaller than n");
+  softmax_fwd_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(S, (bf16*)P, rows, n, lds, ldp, nq, mask_hw, mask_t);
+  return csts_check_launch("softmax_fwd");
+}
+
+int csts_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n, int ldp, int lddp, float scale, void* stream) {
+  if (rows == 0) return 0;
+  softmax_bwd_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)P, dP, (bf16*)dS, rows, n, ldp, lddp, scale);
+  return csts_check_launch("softmax_bwd");
+}
+
+int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_out, void* stream) {
+  if (rows * cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ld_out == cols && (rows * cols) % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
+    int64_t n4 = rows * cols / 4;
+    cast_vec_kernel<<<grid_for(n4, 256), 256, 0, st>>>(src, (bf16*)dst, n4);
+  } else {
+    CSTS_REQUIRE(ld_out >= cols, "cast: ld_out < cols");
+    cast_pad_kernel<<<grid_for(rows * ld_out, 256), 256, 0, st>>>(src, (bf16*)dst, rows, cols, ld_out);
+  }
+  return csts_check_launch("cast_bf16");
+}
+
+// src f32 [a][b][c] -> dst [a][c][b], dst dtype 0 f32 / 1 bf16
+int csts_permute_021(const float* src, void* dst, int dst_dtype, int a, int b, int c, void* stream) {
+  if ((int64_t)a * b * c == 0) return 0;
+  dim3 grid(ceil_div(c, 32), ceil_div(b, 32), a), block(32, 8);
+  CSTS_REQUIRE(a <= 65535 && grid.y <= 65535, "permute_021: dims too large");
+  if (dst_dtype == 0) permute_021_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (float*)dst, a, b, c);
+  else permute_021_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, a, b, c);
+  return csts_check_launch("permute_021");
+}
+
+int csts_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  CSTS_REQUIRE(n % 4 == 0, "add: n must be a multiple of 4");
+  add_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4);
+  return csts_check_launch("add_f32");
+}
+
+int csts_scale_f32(const float* a, const float* device_scalar, float* out, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  scale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, device_scalar, out, n);
+  return csts_check_launch("scale_f32");
+}
+
+// out[N] (+)= column sums of X[M][N]; out must be zeroed by the caller unless accumulating
+int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_t ld, void* stream) {
+  if (M == 0 || N == 0) return 0;
+  CSTS_REQUIRE(N % 4 == 0 && ld % 4 == 0, "colsum: N and ld must be multiples of 4");
+  int bx = ceil_div(N / 4, 64);
+  int want_y = csts_num_sms() * 4 / bx;
+  if (want_y < 1) want_y = 1;
+  int rows_per_block = (int)((M + want_y - 1) / want_y);
+  if (rows_per_block < 32) rows_per_block = 32;
+  dim3 grid(bx, ceil_div(M, rows_per_block));
+  if (x_dtype == 0) colsum_kernel<float><<<grid, 64, 0, (cudaStream_t)stream>>>((const float*)X, out, M, N, ld, rows_per_block);
+  else colsum_kernel<bf16><<<grid, 64, 0, (cudaStream_t)stream>>>((const bf16*)X, out, M, N, ld, rows_per_block);
+  return csts_check_launch("colsum");
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// Stem, fusion glue and head kernels of CSTS: patch-embed im2col, separable position embedding,
+// fusion re-weighting, token mean, and the 1x1x1 classifier fused with the trilinear stem skip.
+#include "common.cuh"
+
+namespace {
+
+int grid_for(int64_t work_items, int per_block) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)csts_num_sms() * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for PatchEmbed: Conv3d k(3,7,7) s(2,4,4) p(1,3,3)      ref: stem_helper.py:27-38
+// x f32 (B, Cin, T, H, W) -> patches bf16 [B*To*Ho*Wo, Kp], column = ((c*3 + kt)*7 + kh)*7 + kw,
+// columns >= Cin*147 are zero (Kp is the GEMM-friendly padded width).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int T, int H,
+                                                     int W, int Kp) {
+  const int To = T / 2, Ho = H / 4, Wo = W / 4;
+  const int K = Cin * 147;
+  const int64_t total = (int64_t)B * To * Ho * Wo * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int col = (int)(i % Kp);
+    int64_t tok = i / Kp;
+    float v = 0.f;
+    if (col < K) {
+      int kw = col % 7, kh = (col / 7) % 7, kt = (col / 49) % 3, c = col / 147;
+      int wo = (int)(tok % Wo), ho = (int)((tok / Wo) % Ho), to = (int)((tok / ((int64_t)Wo * Ho)) % To);
+      int64_t b = tok / ((int64_t)Wo * Ho * To);
+      int ti = to * 2 + kt - 1, hi = ho * 4 + kh - 3, wi = wo * 4 + kw - 3;
+      if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((b * Cin + c) * T + ti) * H + hi) * W + wi];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// pos[t*HW + s][c] = spatial[s][c] + temporal[t][c]       ref: custom_multimodal_builder.py:362-365
+__global__ void pos_embed_kernel(const float* __restrict__ spatial, const float* __restrict__ temporal, float* __restrict__ pos, int T,
+                                 int HW, int C) {
+  const int64_t total = (int64_t)T * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int s = (int)(r % HW), t = (int)(r / HW);
+    pos[i] = spatial[(int64_t)s * C + c] + temporal[t * C + c];
+  }
+}
+// dspatial[s][c] = sum_{b,t} dY[b][t][s][c];  dtemporal[t][c] += sum_{b,s} dY[b][t][s][c]
+__global__ void __launch_bounds__(128) pos_embed_bwd_kernel(const float* __restrict__ dY, float* __restrict__ dspatial,
+                                                            float* __restrict__ dtemporal, int B, int T, int HW, int C, int s_per_block) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  int s0 = blockIdx.x * s_per_block, s1 = min(HW, s0 + s_per_block);
+  float tacc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) tacc[t] = 0.f;
+  for (int s = s0; s < s1; ++s) {
+    float sacc = 0.f;
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t < T) {
+          float v = dY[(((int64_t)b * T + t) * HW + s) * C + c];
+          sacc += v;
+          tacc[t] += v;
+        }
+    dspatial[(int64_t)s * C + c] = sacc;
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    if (t < T) atomicAdd(dtemporal + t * C + c, tacc[t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fusion re-weighting: out[b][t][s][c] = x[b][t][s][c] * w[b][t][c]   ref: custom_multimodal_builder.py:454-461
+// w rows are addressed with a batch stride so the (B, 8, C) temporal-fusion output is used in place.
+// ------------------------------------------------------------------------------------------------
+__global__ void reweight_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int B, int T, int S,
+                                    int C, int64_t w_sB) {
+  const int C4 = C / 4;
+  const int64_t total = (int64_t)B * T * S * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    int64_t r = i / C4;
+    int t = (int)((r / S) % T);
+    int64_t b = r / ((int64_t)S * T);
+    float xv[4], wv[4];
+    ld4(x + r * C + c, xv);
+    ld4(w + b * w_sB + (int64_t)t * C + c, wv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xv[k] *= wv[k];
+    st4(out + r * C + c, xv);
+  }
+}
+// dx = dout * w ; dw[b][t][c] = sum_s dout * x        (one thread owns (b, t, 4 channels): no atomics)
+__global__ void reweight_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w,
+                                    float* __restrict__ dx, float* __restrict__ dw, int B, int T, int S, int C, int64_t w_sB) {
+  const int C4 = C / 4;
+  const int64_t total = (int64_t)B * T * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    int64_t bt = i / C4;
+    int t = (int)(bt % T);
+    int64_t b = bt / T;
+    float wv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    ld4(w + b * w_sB + (int64_t)t * C + c, wv);
+    for (int s = 0; s < S; ++s) {
+      int64_t off = (bt * S + s) * C + c;
+      float dv[4], xv[4], o[4];
+      ld4(dout + off, dv);
+      ld4(x + off, xv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { o[k] = dv[k] * wv[k]; acc[k] = fmaf(dv[k], xv[k], acc[k]); }
+      if (dx) st4(dx + off, o);
+    }
+    st4(dw + b * w_sB + (int64_t)t * C + c, acc);
+  }
+}
+
+// out[b][c] = mean_n x[b][n][c]  (bf16 out: it is the A operand of the NCE projection GEMM)
+__global__ void token_mean_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int N, int C) {
+  const int64_t total = (int64_t)B * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t b = i / C;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc += x[(b * N + n) * C + c];
+    out[i] = __float2bfloat16_rn(acc / (float)N);
+  }
+}
+// dx[b][n][c] (+)= dout[b][c] / N
+__global__ void token_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int N, int C, int accumulate) {
+  const int64_t total = (int64_t)B * N * C;
+  const float inv = 1.f / (float)N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t b = i / ((int64_t)N * C);
+    float v = dout[b * C + c] * inv;
+    dx[i] = accumulate ? dx[i] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: logits[b][to][s] = bias + sum_c w[c] * (feat[b][to][s][c] + lerp_t(stem)[b][to][s][c])
+// ref: custom_multimodal_builder.py:476-481 (F.interpolate T -> 2T trilinear, align_corners=False,
+// then Conv3d(96,1,1)).  One warp per output token.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void t_coef(int to, int Ti, int& i0, int& i1, float& lam) {
+  float src = ((float)to + 0.5f) * 0.5f - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  i1 = i0 + 1 < Ti ? i0 + 1 : Ti - 1;
+  lam = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) classifier_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ stem,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             float* __restrict__ logits, int B, int Ti, int S, int C) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int To = 2 * Ti;
+  const int64_t total = (int64_t)B * To * S;
+  for (int64_t tok = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); tok < total; tok += (int64_t)gridDim.x * wpb) {
+    int s = (int)(tok % S), to = (int)((tok / S) % To);
+    int64_t b = tok / ((int64_t)S * To);
+    int i0, i1; float lam;
+    t_coef(to, Ti, i0, i1, lam);
+    const float* f = feat + tok * C;
+    const float* a0 = stem + ((b * Ti + i0) * S + s) * C;
+    const float* a1 = stem + ((b * Ti + i1) * S + s) * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc += w[c] * (f[c] + (1.f - lam) * a0[c] + lam * a1[c]);
+    acc = warp_sum(acc);
+    if (lane == 0) logits[tok] = acc + bias[0];
+  }
+}
+// dfeat = dlogit * w ; dw += sum dlogit * val ; dbias += sum dlogit
+__global__ void __launch_bounds__(256) classifier_bwd_feat_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat,
+                                                                  const float* __restrict__ stem, const float* __restrict__ w,
+                                                                  float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ dbias,
+                                                                  int B, int Ti, int S, int C) {
+  __shared__ float s_dw[256];
+  __shared__ float s_db;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_dw[i] = 0.f;
+  if (threadIdx.x == 0) s_db = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int To = 2 * Ti;
+  const int64_t total = (int64_t)B * To * S;
+  float adw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) adw[k] = 0.f;
+  float adb = 0.f;
+  for (int64_t tok = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); tok < total; tok += (int64_t)gridDim.x * wpb) {
+    int s = (int)(tok % S), to = (int)((tok / S) % To);
+    int64_t b = tok / ((int64_t)S * To);
+    int i0, i1; float lam;
+    t_coef(to, Ti, i0, i1, lam);
+    const float g = dlogits[tok];
+    const float* f = feat + tok * C;
+    const float* a0 = stem + ((b * Ti + i0) * S + s) * C;
+    const float* a1 = stem + ((b * Ti + i1) * S + s) * C;
+    float* df = dfeat + tok * C;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = lane + 32 * k;
+      if (c < C) {
+        df[c] = g * w[c];
+        adw[k] += g * (f[c] + (1.f - lam) * a0[c] + lam * a1[c]);
+      }
+    }
+    if (lane == 0) adb += g;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = lane + 32 * k;
+    if (c < C) atomicAdd(&s_dw[c], adw[k]);
+  }
+  if (lane == 0) atomicAdd(&s_db, adb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+  if (threadIdx.x == 0) atomicAdd(dbias, s_db);
+}
+// dstem[b][ti][s][c] = w[c] * sum_{to} coef(to -> ti) * dlogit[b][to][s]
+__global__ void classifier_bwd_stem_kernel(const float* __restrict__ dlogits, const float* __restrict__ w, float* __restrict__ dstem, int B,
+                                           int Ti, int S, int C) {
+  const int To = 2 * Ti;
+  const int64_t total = (int64_t)B * Ti * S * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int s = (int)(r % S), ti = (int)((r / S) % Ti);
+    int64_t b = r / ((int64_t)S * Ti);
+    float acc = 0.f;
+    for (int to = max(2 * ti - 2, 0); to <= min(2 * ti + 3, To - 1); ++to) {
+      int i0, i1; float lam;
+      t_coef(to, Ti, i0, i1, lam);
+      float cf = 0.f;
+      if (i0 == ti) cf += 1.f - lam;
+      if (i1 == ti) cf += lam;
+      if (cf != 0.f) acc += cf * dlogits[(b * To + to) * S + s];
+    }
+    dstem[i] = acc * w[c];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int csts_im2col_patch(const float* x, void* patches, int B, int Cin, int T, int H, int W, int Kp, void* stream) {
+  CSTS_REQUIRE(T % 2 == 0 && H % 4 == 0 && W % 4 == 0 && Kp >= Cin * 147 && Kp % 8 == 0, "im2col: bad geometry");
+  int64_t total = (int64_t)B * (T / 2) * (H / 4) * (W / 4) * Kp;
+  if (total == 0) return 0;
+  im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)patches, B, Cin, T, H, W, Kp);
+  return csts_check_launch("im2col_patch");
+}
+int csts_pos_embed(const float* spatial, const float* temporal, float* pos, int T, int HW, int C, void* stream) {
+  pos_embed_kernel<<<grid_for((int64_t)T * HW * C, 256), 256, 0, (cudaStream_t)stream>>>(spatial, temporal, pos, T, HW, C);
+  return csts_check_launch("pos_embed");
+}
+// dtemporal must be zeroed by the caller; dspatial is overwritten
+int csts_pos_embed_bwd(const float* dY, float* dspatial, float* dtemporal, int B, int T, int HW, int C, void* stream) {
+  CSTS_REQUIRE(C <= 128 && T <= 8, "pos_embed_bwd: C <= 128 and T <= 8 required");
+  int s_per_block = 8;
+  pos_embed_bwd_kernel<<<ceil_div(HW, s_per_block), 128, 0, (cudaStream_t)stream>>>(dY, dspatial, dtemporal, B, T, HW, C, s_per_block);
+  return csts_check_launch("pos_embed_bwd");
+}
+int csts_reweight_fwd(const float* x, const float* w, float* out, int B, int T, int S, int C, int64_t w_sB, void* stream) {
+  CSTS_REQUIRE(C % 4 == 0 && w_sB % 4 == 0, "reweight: C and w_sB must be multiples of 4");
+  reweight_fwd_kernel<<<grid_for((int64_t)B * T * S * C / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, w, out, B, T, S, C, w_sB);
+  return csts_check_launch("reweight_fwd");
+}
+int csts_reweight_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, int B, int T, int S, int C, int64_t w_sB,
+                      void* stream) {
+  CSTS_REQUIRE(C % 4 == 0 && w_sB % 4 == 0, "reweight: C and w_sB must be multiples of 4");
+  reweight_bwd_kernel<<<grid_for((int64_t)B * T * C / 4, 64), 64, 0, (cudaStream_t)stream>>>(dout, x, w, dx, dw, B, T, S, C, w_sB);
+  return csts_check_launch("reweight_bwd");
+}
+int csts_token_mean_fwd(const float* x, void* out_bf16, int B, int N, int C, void* stream) {
+  token_mean_fwd_kernel<<<grid_for((int64_t)B * C, 64), 64, 0, (cudaStream_t)stream>>>(x, (bf16*)out_bf16, B, N, C);
+  return csts_check_launch("token_mean_fwd");
+}
+int csts_token_mean_bwd(const float* dout, float* dx, int B, int N, int C, int accumulate, void* stream) {
+  token_mean_bwd_kernel<<<grid_for((int64_t)B * N * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, N, C, accumulate);
+  return csts_check_launch("token_mean_bwd");
+}
+int csts_classifier_fwd(const float* feat, const float* stem, const float* w, const float* bias, float* logits, int B, int Ti, int S, int C,
+                        void* stream) {
+  classifier_fwd_kernel<<<grid_for((int64_t)B * 2 * Ti * S, 8), 256, 0, (cudaStream_t)stream>>>(feat, stem, w, bias, logits, B, Ti, S, C);
+  return csts_check_launch("classifier_fwd");
+}
+// dw, dbias must be zeroed by the caller
+int csts_classifier_bwd(const float* dlogits, const float* feat, const float* stem, const float* w, float* dfeat, float* dstem, float* dw,
+                        float* dbias, int B, int Ti, int S, int C, void* stream) {
+  CSTS_REQUIRE(C <= 256, "classifier_bwd: C <= 256 required");
+  int64_t toks = (int64_t)B * 2 * Ti * S;
+  int64_t blocks = (toks + 255) / 256;
+  int grid = (int)(blocks < csts_num_sms() * 2 ? blocks : csts_num_sms() * 2);
+  classifier_bwd_feat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, feat, stem, w, dfeat, dw, dbias, B, Ti, S, C);
+  int rc = csts_check_launch("classifier_bwd_feat");
+  if (rc) return rc;
+  classifier_bwd_stem_kernel<<<grid_for((int64_t)B * Ti * S * C, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, w, dstem, B, Ti, S, C);
+  return csts_check_launch("classifier_bwd_stem");
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+"""Kernel-level parity (GPU): every exported kernel of libcsts_b200.so against the plain fp32 torch
+expression of the reference lines it replaces.  Tolerances are stated per test; bf16 storage
+implies ~2^-8 relative rounding on inputs/outputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+dev = "cuda"
+
+
+def K():
+    from csts_b200 import kernels
+    return kernels
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    # M, N, K
+    (256, 96, 96), (1024, 288, 96), (384, 192, 384), (2080, 768, 768), (128, 2304, 768),
+    (300, 384, 1536), (4096, 96, 192), (512, 3072, 768), (1000, 576, 192), (128, 96, 448),
+]
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES)
+def test_gemm_linear_plain(backend, M, N, Kd):
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(M + N + Kd)
+    A = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = bf(torch.randn(N, Kd, generator=g) * 0.05).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = A.float() @ B.float().t() + bias
+    out = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, out_dtype=torch.float32, backend=backend)
+    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+    out16 = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, out_dtype=torch.bfloat16, backend=backend)
+    assert rel_err(out16, ref) < 4e-3
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+def test_gemm_epilogues(backend):
+    k = K()
+    M, N, Kd = 640, 384, 192
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = bf(torch.randn(N, Kd, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    pre = A.float() @ B.float().t() + bias
+    # GELU + saved pre-activation
+    Z = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    h = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, act=1, Z=Z, backend=backend)
+    assert rel_err(Z, pre) < 4e-3
+    assert rel_err(h, F.gelu(pre)) < 5e-3
+    # residual, f32 out
+    o = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, residual=res, out_dtype=torch.float32, backend=backend)
+    assert rel_err(o, pre + res) < 2e-5
+    # broadcast residual rows (pos-embed style)
+    o = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, residual=res[:128].contiguous(), res_mod=128, out_dtype=torch.float32, backend=backend)
+    assert rel_err(o, pre + res[:128].repeat(5, 1)) < 2e-5
+    # accumulate
+    acc = res.clone()
+    k.gemm(A, B, M=M, N=N, K=Kd, out=acc, accumulate=True, backend=backend)
+    assert rel_err(acc, res + A.float() @ B.float().t()) < 2e-5
+    # times GELU'(Z)
+    o = k.gemm(A, B, M=M, N=N, K=Kd, act=2, Z=Z, out_dtype=torch.float32, backend=backend)
+    zf = Z.float().requires_grad_(True)
+    (gz,) = torch.autograd.grad(F.gelu(zf).sum(), zf)
+    assert rel_err(o, (A.float() @ B.float().t()) * gz) < 1e-4
+
+
+@pytest.mark.parametrize("ak,bk", [(True, True), (True, False), (False, False), (False, True)])
+def test_gemm_generic_layouts_batched(ak, bk):
+    k = K()
+    b1, b2, M, N, Kd = 2, 3, 260, 96, 264
+    g = torch.Generator(device="cpu").manual_seed(11)
+    A = bf(torch.randn(b1, b2, M, Kd, generator=g)).to(dev)
+    B = bf(torch.randn(b1, b2, Kd, N, generator=g)).to(dev)
+    ref = A.float() @ B.float()
+    As = A if ak else A.transpose(-1, -2).contiguous()
+    Bs = B.transpose(-1, -2).contiguous() if bk else B
+    out = torch.empty(b1, b2, M, N, dtype=torch.float32, device=dev)
+    k.gemm(As, Bs, M=M, N=N, K=Kd, a_kmajor=ak, b_kmajor=bk, out=out, batch=(b1, b2),
+           sA=(b2 * M * Kd, M * Kd), sB=(b2 * N * Kd, N * Kd), sC=(b2 * M * N, M * N), alpha=0.5)
+    assert rel_err(out, 0.5 * ref) < 2e-5
+
+
+def test_gemm_ragged_k_and_splitk():
+    k = K()
+    M, N, Kd = 32, 768, 4096 + 8
+    g = torch.Generator(device="cpu").manual_seed(12)
+    A = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = bf(torch.randn(N, Kd, generator=g) * 0.02).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = A.float() @ B.float().t() + bias
+    out = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, out_dtype=torch.float32, split_k=16)
+    assert rel_err(out, ref) < 2e-5
+    # K not a multiple of 8 with a padded leading dimension (attention P @ V with Nk = 260)
+    P = bf(torch.rand(64, 264, generator=g)).to(dev)
+    V = bf(torch.randn(260, 96, generator=g)).to(dev)
+    o = k.gemm(P, V, M=64, N=96, K=260, lda=264, b_kmajor=False, out_dtype=torch.float32)
+    assert rel_err(o, P[:, :260].float() @ V.float()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,width", [(1000, 96), (333, 192), (260, 384), (64, 768), (7, 96)])
+def test_layernorm_fwd_bwd(rows, width):
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    x = (torch.randn(rows, width, generator=g) * 2 + 0.5).to(dev)
+    gamma = (1 + 0.1 * torch.randn(width, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(width, generator=g)).to(dev)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (width,), gr, br, 1e-6)
+    y, mean, rstd = k.layernorm_fwd(x, gamma, beta, 1e-6, out_dtype=torch.float32)
+    assert rel_err(y, yr) < 1e-5
+    y16, _, _ = k.layernorm_fwd(x, gamma, beta, 1e-6)
+    assert rel_err(y16, yr) < 4e-3
+    dy = bf(torch.randn(rows, width, generator=g)).to(dev)
+    add = torch.randn(rows, width, generator=g).to(dev)
+    yr.backward(dy.float())
+    dg = torch.zeros(width, device=dev)
+    db = torch.zeros(width, device=dev)
+    dx = k.layernorm_bwd(dy, x, mean, rstd, gamma, dg, db, add=add)
+    assert rel_err(dx - add, xr.grad) < 1e-4
+    assert rel_err(dg, gr.grad) < 1e-4
+    assert rel_err(db, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ softmax
+@pytest.mark.parametrize("n,ldp", [(64, 64), (256, 256), (260, 264), (1024, 1024), (8, 8)])
+def test_softmax_fwd_bwd(n, ldp):
+    k = K()
+    rows = 3 * n if n == 260 else 512
+    g = torch.Generator(device="cpu").manual_seed(n)
+    S = torch.full((rows, ldp), float("nan"))
+    S[:, :n] = torch.randn(rows, n, generator=g) * 3
+    S = S.to(dev)
+    mask_hw, mask_t = (64, 4) if n == 260 else (0, 0)
+    ref_in = S[:, :n].clone()
+    if mask_hw:
+        import csts_oracle as O
+        ref_in = (ref_in.reshape(3, n, n) - O.spatial_mask((4, 8, 8), dev)).reshape(rows, n)
+    Pr = ref_in.softmax(-1)
+    P = k.softmax_fwd(S, n, ldp, nq=n, mask_hw=mask_hw, mask_t=mask_t)
+    assert P.shape == (rows, ldp)
+    assert torch.all(P[:, n:] == 0)
+    assert (P[:, :n].float() - Pr).abs().max() < 4e-3
+    dP = torch.randn(rows, ldp, generator=g).to(dev)
+    dS = k.softmax_bwd(P, dP, n, 0.125)
+    Pf = P[:, :n].float()
+    ref = 0.125 * Pf * (dP[:, :n] - (dP[:, :n] * Pf).sum(-1, keepdim=True))
+    assert rel_err(dS[:, :n], ref) < 5e-3
+    assert torch.all(dS[:, n:] == 0)
+
+
+# ------------------------------------------------------------------------------------------------ dwconv (+LN)
+POOL_CASES = [
+    # B, heads, d, thw, stride, transposed
+    (2, 1, 96, (4, 16, 16), (1, 8, 8), False),
+    (2, 2, 96, (4, 16, 16), (1, 2, 2), False),
+    (1, 2, 96, (2, 8, 8), (1, 1, 1), False),
+    (2, 2, 192, (4, 8, 8), (1, 4, 4), False),
+    (2, 2, 96, (4, 4, 4), (1, 2, 2), True),
+    (1, 2, 96, (4, 8, 8), (2, 1, 1), True),
+    (1, 2, 192, (2, 4, 4), (1, 2, 2), True),
+]
+
+
+@pytest.mark.parametrize("B,heads,d,thw,stride,transposed", POOL_CASES)
+def test_dwconv_ln_fwd_bwd(B, heads, d, thw, stride, transposed):
+    import csts_oracle as O
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(d + thw[1] + stride[1])
+    N = thw[0] * thw[1] * thw[2]
+    Cn = heads * d
+    qkv = bf(torch.randn(B, N, 3, heads, d, generator=g)).to(dev)       # the layout the qkv GEMM writes
+    w = (torch.randn(d, 1, 3, 3, 3, generator=g) * 0.2).to(dev)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(d, generator=g)).to(dev)
+    which = 1
+    # oracle (fp32 torch on the same bf16-rounded input)
+    t = qkv[:, :, which].float().permute(0, 2, 1, 3).contiguous().requires_grad_(True)   # (B,h,N,d)
+    wr, gr, br = w.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr, thw_o = O.pool_tokens(t, thw, wr, stride, gr, br, transposed=transposed)
+    in_strides = (N * 3 * Cn, d, 3 * Cn)
+    y, pre, mean, rstd, thw_out = k.dwconv(qkv, in_strides, which * Cn, B, heads, d, thw, stride, w, transposed=transposed,
+                                           norm=(gamma, beta))
+    assert tuple(thw_out) == tuple(thw_o)
+    assert rel_err(y, yr) < 8e-3, rel_err(y, yr)
+    # backward: LN bwd (generic kernel on the saved pre-LN tensor), then data-grad gather + weight grad
+    dy = bf(torch.randn(yr.shape, generator=g)).to(dev)
+    yr.backward(dy.float())
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    du = k.layernorm_bwd(dy, pre, mean, rstd, gamma, dg, db, dx_dtype=torch.bfloat16)
+    assert rel_err(dg, gr.grad) < 2e-2 and rel_err(db, br.grad) < 1e-2
+    Lo = thw_out[0] * thw_out[1] * thw_out[2]
+    dense = (heads * Lo * d, Lo * d, d)
+    dqkv = torch.zeros_like(qkv)
+    k.dwconv(du, dense, 0, B, heads, d, thw_out, stride, w, transposed=not transposed,
+             out=dqkv, out_strides=in_strides, out_off=which * Cn, thw_out=thw)
+    got = dqkv[:, :, which].float().permute(0, 2, 1, 3)
+    assert rel_err(got, t.grad) < 1.5e-2, rel_err(got, t.grad)
+    assert torch.all(dqkv[:, :, 0] == 0) and torch.all(dqkv[:, :, 2] == 0)
+    dw = torch.zeros_like(w)
+    if transposed:   # small = conv input, big = d(out)
+        k.dwconv_wgrad(qkv, in_strides, which * Cn, thw, du, dense, 0, thw_out, B, heads, d, stride, dw)
+    else:            # small = d(out), big = conv input
+        k.dwconv_wgrad(du, dense, 0, thw_out, qkv, in_strides, which * Cn, thw, B, heads, d, stride, dw)
+    assert rel_err(dw, wr.grad) < 1.5e-2, rel_err(dw, wr.grad)
+
+
+# ------------------------------------------------------------------------------------------------ skip paths
+def test_maxpool_fwd_bwd():
+    k = K()
+    B, thw, Cn = 2, (2, 8, 12), 96
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(B, thw[0] * thw[1] * thw[2], Cn, generator=g).to(dev)
+    xr = x.clone().requires_grad_(True)
+    grid = xr.reshape(B, *thw, Cn).permute(0, 4, 1, 2, 3)
+    yr = F.max_pool3d(grid, (1, 3, 3), (1, 2, 2), (0, 1, 1)).permute(0, 2, 3, 4, 1).reshape(B, -1, Cn)
+    y, arg = k.maxpool_fwd(x, B, thw, Cn)
+    assert torch.equal(y, yr)
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    yr.backward(dy)
+    dx = k.maxpool_bwd(dy, arg, B, thw, Cn)
+    assert rel_err(dx, xr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("factors", [(1, 2, 2), (2, 1, 1)])
+def test_upsample_fwd_bwd(factors):
+    k = K()
+    B, thw, Cn = 2, (3, 4, 6), 96
+    g = torch.Generator(device="cpu").manual_seed(2)
+    x = torch.randn(B, thw[0] * thw[1] * thw[2], Cn, generator=g).to(dev)
+    xr = x.clone().requires_grad_(True)
+    grid = xr.reshape(B, *thw, Cn).permute(0, 4, 1, 2, 3)
+    yr = F.interpolate(grid, scale_factor=tuple(float(f) for f in factors), mode="trilinear").permute(0, 2, 3, 4, 1).reshape(B, -1, Cn)
+    y = k.upsample_fwd(x, B, thw, Cn, factors)
+    assert rel_err(y, yr) < 1e-6
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    yr.backward(dy)
+    dx = k.upsample_bwd(dy, B, thw, Cn, factors)
+    assert rel_err(dx, xr.grad) < 1e-6
+    base = torch.randn(dx.shape, generator=g).to(dev)
+    dx2 = k.upsample_bwd(dy, B, thw, Cn, factors, dx=base.clone())
+    assert rel_err(dx2, xr.grad + base) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ stem / head
+@pytest.mark.parametrize("Cin", [3, 1])
+def test_patch_embed_im2col_gemm(Cin):
+    k = K()
+    B, T, H, W = 2, 4, 32, 32
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(B, Cin, T, H, W, generator=g).to(dev)
+    w = (torch.randn(96, Cin, 3, 7, 7, generator=g) * 0.05).to(dev)
+    b = torch.randn(96, generator=g).to(dev)
+    Kp = (Cin * 147 + 7) // 8 * 8
+    patches = k.im2col_patch(x, Kp)
+    wp = k.cast_bf16(w.reshape(96, -1), ld_out=Kp)
+    sp = torch.randn(1, (H // 4) * (W // 4), 96, generator=g).to(dev)
+    tp = torch.randn(1, T // 2, 96, generator=g).to(dev)
+    pos = k.pos_embed(sp, tp)
+    import csts_oracle as O
+    assert torch.equal(pos, O.sep_pos_embed(sp, tp)[0])
+    M = patches.shape[0]
+    tok = k.gemm(patches, wp, M=M, N=96, K=Kp, bias=b, residual=pos, res_mod=pos.shape[0], out_dtype=torch.float32)
+    ref = F.conv3d(bf(x).float(), bf(w).float(), b, stride=(2, 4, 4), padding=(1, 3, 3)).flatten(2).transpose(1, 2) + pos
+    assert rel_err(tok.reshape(B, -1, 96), ref) < 2e-5
+    # position-embedding gradients
+    dY = torch.randn(B, T // 2, pos.shape[0] // (T // 2), 96, generator=g).to(dev)
+    dsp, dtm = k.pos_embed_bwd(dY, B, T // 2, dY.shape[2], 96)
+    assert rel_err(dsp[0], dY.sum((0, 1))) < 1e-5
+    assert rel_err(dtm[0], dY.sum((0, 2))) < 1e-5
+
+
+def test_permute_and_cast_and_colsum():
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(4)
+    src = torch.randn(5, 70, 33, generator=g).to(dev)
+    assert torch.equal(k.permute_021(src, 5, 70, 33, torch.float32), src.transpose(1, 2).contiguous())
+    assert torch.equal(k.permute_021(src, 5, 70, 33, torch.bfloat16), bf(src.transpose(1, 2).contiguous()))
+    v = torch.randn(1000, 96, generator=g).to(dev)
+    assert torch.equal(k.cast_bf16(v), bf(v))
+    X = bf(torch.randn(3000, 288, generator=g)).to(dev)
+    assert rel_err(k.colsum(X, 3000, 288), X.float().sum(0)) < 1e-5
+    Xf = torch.randn(777, 96, generator=g).to(dev)
+    assert rel_err(k.colsum(Xf, 777, 96), Xf.sum(0)) < 1e-5
+    a, b = torch.randn(4096, generator=g).to(dev), torch.randn(4096, generator=g).to(dev)
+    assert torch.equal(k.add_f32(a, b), a + b)
+    s = torch.tensor([0.25], device=dev)
+    assert torch.equal(k.scale_f32(a, s), a * 0.25)
+
+
+def test_reweight_and_token_mean():
+    k = K()
+    B, T, S, Cn = 2, 4, 64, 768
+    g = torch.Generator(device="cpu").manual_seed(6)
+    x = torch.randn(B, T * S, Cn, generator=g).to(dev)
+    av = torch.randn(B, 2 * T, Cn, generator=g).to(dev)
+    for off in (0, T * Cn):
+        w = av.reshape(B, -1)[:, off: off + T * Cn].reshape(B, T, 1, Cn)
+        ref = (x.reshape(B, T, S, Cn) * w).reshape(B, T * S, Cn)
+        out = k.reweight_fwd(x, av, off, 2 * T * Cn, B, T, S, Cn)
+        assert torch.equal(out, ref)
+        dout = torch.randn(out.shape, generator=g).to(dev)
+        dav = torch.zeros_like(av)
+        dx = k.reweight_bwd(dout, x, av, off, 2 * T * Cn, dav, B, T, S, Cn)
+        assert rel_err(dx, (dout.reshape(B, T, S, Cn) * w).reshape(B, T * S, Cn)) < 1e-6
+        dwr = (dout * x).reshape(B, T, S, Cn).sum(2)
+        assert rel_err(dav.reshape(B, -1)[:, off: off + T * Cn].reshape(B, T, Cn), dwr) < 1e-5
+    m = k.token_mean_fwd(x, B, T * S, Cn)
+    assert rel_err(m, x.mean(1)) < 4e-3
+    dm = torch.randn(B, Cn, generator=g).to(dev)
+    dx = k.token_mean_bwd(dm, B, T * S, Cn)
+    assert rel_err(dx, (dm / (T * S))[:, None, :].expand(B, T * S, Cn)) < 1e-6
+
+
+def test_classifier_fwd_bwd():
+    k = K()
+    B, Ti, S, Cn = 2, 4, 64, 96
+    g = torch.Generator(device="cpu").manual_seed(8)
+    feat = torch.randn(B, 2 * Ti * S, Cn, generator=g).to(dev)
+    stem = torch.randn(B, Ti * S, Cn, generator=g).to(dev)
+    w = (torch.randn(1, Cn, 1, 1, 1, generator=g) * 0.1).to(dev)
+    b = torch.randn(1, generator=g).to(dev)
+    fr, sr = feat.clone().requires_grad_(True), stem.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    f5 = fr.reshape(B, 2 * Ti, 8, 8, Cn).permute(0, 4, 1, 2, 3)
+    s5 = sr.reshape(B, Ti, 8, 8, Cn).permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(f5 + F.interpolate(s5, size=(2 * Ti, 8, 8), mode="trilinear"), wr, br)
+    logits = k.classifier_fwd(feat, stem, w, b, B, Ti, S, Cn)
+    assert rel_err(logits.reshape(-1), ref.reshape(-1)) < 1e-5
+    dl = torch.randn(ref.shape, generator=g).to(dev)
+    ref.backward(dl)
+    dfeat, dstem, dw, db = k.classifier_bwd(dl, feat, stem, w, B, Ti, S, Cn)
+    assert rel_err(dfeat, fr.grad) < 1e-5
+    assert rel_err(dstem, sr.grad) < 1e-5
+    assert rel_err(dw, wr.grad.reshape(-1)) < 1e-4
+    assert rel_err(db, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def test_kldiv_and_egonce(golden_dir):
+    import os
+    import csts_oracle as O
+    k = K()
+    rec = torch.load(os.path.join(golden_dir, "losses.pt"), weights_only=False)
+    logits = rec["logits"].to(dev).requires_grad_(True)
+    hm = rec["hm"].to(dev)
+    loss, prob, dlog = k.kldiv_frame_softmax(logits.detach(), hm, 2.0, T=8)
+    assert rel_err(prob, rec["p"].to(dev)) < 1e-5
+    assert abs(loss.item() - rec["kld"].item()) < 1e-5 * abs(rec["kld"].item()) + 1e-7
+    O.kldiv(O.frame_softmax(logits, 2.0), hm).backward()
+    assert rel_err(dlog, logits.grad) < 1e-4
+    v = rec["v"].to(dev).requires_grad_(True)
+    a = rec["a"].to(dev).requires_grad_(True)
+    sim, na, nb = k.sim_matrix_fwd(v.detach(), a.detach())
+    assert rel_err(sim, rec["sim"].to(dev)) < 1e-5
+    nce, dsim = k.egonce(sim)
+    assert abs(nce.item() - rec["nce"].item()) < 1e-4 * abs(rec["nce"].item())
+    O.egonce(O.sim_matrix(v, a)).backward()
+    dv, da = k.sim_matrix_bwd(v.detach(), a.detach(), sim, dsim, na, nb)
+    assert rel_err(dv, v.grad) < 1e-4
+    assert rel_err(da, a.grad) < 1e-4
