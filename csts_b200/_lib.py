@@ -19,14 +19,14 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("Z", C.c_void_p),
-        ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("row_scale", C.c_void_p),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64), ("ldz", C.c_int64), ("ldr", C.c_int64),
         ("sA1", C.c_int64), ("sA2", C.c_int64), ("sB1", C.c_int64), ("sB2", C.c_int64), ("sC1", C.c_int64), ("sC2", C.c_int64),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("batch1", C.c_int32), ("batch2", C.c_int32),
         ("a_kmajor", C.c_int32), ("b_kmajor", C.c_int32),
         ("c_dtype", C.c_int32), ("act", C.c_int32), ("accumulate", C.c_int32), ("res_mod", C.c_int32),
-        ("split_k", C.c_int32), ("alpha", C.c_float), ("backend", C.c_int32),
+        ("split_k", C.c_int32), ("alpha", C.c_float), ("backend", C.c_int32), ("rows_per_scale", C.c_int32),
     ]
 
 
@@ -67,7 +67,7 @@ SIGNATURES = {
     "csts_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
     "csts_softmax_fwd": [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     "csts_softmax_bwd": [_P, _P, _P, _L, _I, _I, _I, _F, _P],
-    "csts_cast_bf16": [_P, _P, _L, _I, _I, _P],
+    "csts_cast_bf16": [_P, _P, _L, _I, _I, _P, _I, _P],
     "csts_permute_021": [_P, _P, _I, _I, _I, _I, _P],
     "csts_add_f32": [_P, _P, _P, _L, _P],
     "csts_scale_f32": [_P, _P, _P, _L, _P],

@@ -12,6 +12,8 @@ typedef struct csts_gemm_args {
                          //                                  act==2 -> read (multiply by gelu'(Z))
   const float* bias;     // [N] or NULL
   const float* residual; // f32 [rows, N] (ldr) or NULL; row = m % res_mod when res_mod > 0
+  const float* row_scale;// [ceil(M / rows_per_scale)] or NULL: result row m is multiplied by
+                         // row_scale[m / rows_per_scale] before the residual is added (DropPath)
   int64_t lda, ldb, ldc, ldz, ldr;
   int64_t sA1, sA2, sB1, sB2, sC1, sC2;  // batch strides (elements): z -> (z / batch2, z % batch2)
   int32_t M, N, K;
@@ -25,6 +27,7 @@ typedef struct csts_gemm_args {
   int32_t split_k;       // > 1: partial sums combined with f32 atomics (C must be f32)
   float alpha;
   int32_t backend;       // 0 auto, 1 mma.sync, 2 tcgen05
+  int32_t rows_per_scale;
 } csts_gemm_args;
 }
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, int64_t ld, in
 }
 
 struct Epi {
-  void* C; void* Z; const float* bias; const float* residual;
+  void* C; void* Z; const float* bias; const float* residual; const float* row_scale; int rows_per_scale;
   int64_t ldc, ldz, ldr;
   int M, N, c_dtype, act, accumulate, res_mod, atomic, first_split;
   float alpha;
@@ -111,6 +111,7 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n, float v0, 
     v0 *= gelu_erf_grad(__bfloat162float(z[0]));
     if (two) v1 *= gelu_erf_grad(__bfloat162float(z[1]));
   }
+  if (e.row_scale) { float rs = e.row_scale[m / e.rows_per_scale]; v0 *= rs; v1 *= rs; }
   if (e.residual) {
     const float* r = e.residual + (int64_t)(e.res_mod > 0 ? m % e.res_mod : m) * e.ldr + n;
     v0 += r[0]; if (two) v1 += r[1];
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(THREADS) gemm_mma_kernel(csts_gemm_args p, int
   e.M = p.M; e.N = p.N; e.c_dtype = p.c_dtype; e.act = p.act; e.accumulate = p.accumulate;
   e.res_mod = p.res_mod; e.atomic = p.split_k > 1; e.first_split = (split == 0);
   e.alpha = p.alpha; e.bias = p.bias; e.residual = p.residual;
+  e.row_scale = p.row_scale; e.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1;
   e.C = p.c_dtype == 0 ? (void*)(reinterpret_cast<float*>(p.C) + coff) : (void*)(reinterpret_cast<bf16*>(p.C) + coff);
   e.Z = p.Z ? (void*)(reinterpret_cast<bf16*>(p.Z) + coff) : nullptr;
   if (nk == 0 && !(e.atomic && e.first_split)) return;
@@ -258,7 +260,7 @@ int csts_gemm_mma_launch(const csts_gemm_args& a, cudaStream_t stream) {
   CSTS_REQUIRE(((uintptr_t)a.A & 15) == 0 && ((uintptr_t)a.B & 15) == 0, "gemm: A/B must be 16-byte aligned");
   CSTS_REQUIRE((a.sA1 % 8 == 0) && (a.sA2 % 8 == 0) && (a.sB1 % 8 == 0) && (a.sB2 % 8 == 0), "gemm: batch strides must be multiples of 8");
   if (a.split_k > 1) {
-    CSTS_REQUIRE(a.c_dtype == 0 && a.act == 0, "gemm: split-K needs f32 output and no activation");
+    CSTS_REQUIRE(a.c_dtype == 0 && a.act == 0 && !a.row_scale, "gemm: split-K needs f32 output, no activation, no row scale");
     if (!a.accumulate) {
       CSTS_REQUIRE(a.batch1 * a.batch2 == 1, "gemm: split-K without accumulate supports a single batch");
       CSTS_CUDA(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, (size_t)a.N * sizeof(float), a.M, stream));

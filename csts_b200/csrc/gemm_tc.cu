@@ -111,7 +111,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 struct TcParams {
-  void* C; void* Z; const float* bias; const float* residual;
+  void* C; void* Z; const float* bias; const float* residual; const float* row_scale; int rows_per_scale;
   int64_t ldc, ldz, ldr;
   int M, N, K;
   int c_dtype, act, accumulate, res_mod;
@@ -159,6 +159,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, int m, int n, 
         v[h * 8 + 2 * i + 1] *= gelu_erf_grad(__high2float(zz[i]));
       }
     }
+  }
+  if (p.row_scale) {
+    const float rs = p.row_scale[m / p.rows_per_scale];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= rs;
   }
   if (p.residual) {
     const float4* r4 = reinterpret_cast<const float4*>(p.residual + (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr + n);
@@ -346,6 +351,7 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   if (rc) return rc;
   TcParams p;
   p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual;
+  p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
   p.ldc = a.ldc; p.ldz = a.ldz; p.ldr = a.ldr;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.c_dtype = a.c_dtype; p.act = a.act; p.accumulate = a.accumulate; p.res_mod = a.res_mod; p.alpha = a.alpha;

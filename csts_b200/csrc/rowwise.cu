@@ -206,18 +206,28 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict
 // casts / permutes / elementwise
 // ------------------------------------------------------------------------------------------------
 // f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns)
-__global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int cols, int ld_out) {
+__global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int cols, int ld_out,
+                                const float* __restrict__ row_scale, int rows_per_scale) {
   int64_t total = rows * ld_out;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / ld_out;
     int c = (int)(i - r * ld_out);
-    dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+    float v = c < cols ? src[r * cols + c] : 0.f;
+    if (row_scale) v *= row_scale[r / rows_per_scale];
+    dst[i] = __float2bfloat16_rn(v);
   }
 }
-__global__ void cast_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4) {
+// cols must be a multiple of 4 (a 4-vector never straddles rows)
+__global__ void cast_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4, int cols4,
+                                const float* __restrict__ row_scale, int rows_per_scale) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4];
     ld4(src + 4 * i, v);
+    if (row_scale) {
+      float rs = row_scale[(i / cols4) / rows_per_scale];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] *= rs;
+    }
     st4(dst + 4 * i, v);
   }
 }
@@ -328,15 +338,18 @@ int csts_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int
   return csts_check_launch("softmax_bwd");
 }
 
-int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_out, void* stream) {
+// row m of the result is multiplied by row_scale[m / rows_per_scale] when row_scale != NULL
+int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_out, const float* row_scale, int rows_per_scale,
+                   void* stream) {
   if (rows * cols == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (ld_out == cols && (rows * cols) % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
+  if (row_scale) CSTS_REQUIRE(rows_per_scale > 0, "cast: rows_per_scale must be positive");
+  if (ld_out == cols && cols % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
     int64_t n4 = rows * cols / 4;
-    cast_vec_kernel<<<grid_for(n4, 256), 256, 0, st>>>(src, (bf16*)dst, n4);
+    cast_vec_kernel<<<grid_for(n4, 256), 256, 0, st>>>(src, (bf16*)dst, n4, cols / 4, row_scale, rows_per_scale);
   } else {
     CSTS_REQUIRE(ld_out >= cols, "cast: ld_out < cols");
-    cast_pad_kernel<<<grid_for(rows * ld_out, 256), 256, 0, st>>>(src, (bf16*)dst, rows, cols, ld_out);
+    cast_pad_kernel<<<grid_for(rows * ld_out, 256), 256, 0, st>>>(src, (bf16*)dst, rows, cols, ld_out, row_scale, rows_per_scale);
   }
   return csts_check_launch("cast_bf16");
 }

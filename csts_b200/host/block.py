@@ -1,0 +1,281 @@
+"""One CSTS transformer block (encoder / decoder / spatial-fusion / temporal-fusion) as a single
+autograd node running on the libcsts_b200 kernels.
+
+Forward follows ``MultiScaleBlock.forward`` / ``MultiScaleAttention.forward``
+(attention.py:238-248, :120-162), the decoder variants (:365-392, :469-479) and the fusion blocks
+(av_attention.py:120-152, :229-250, :322-372, :450-473).  Data layout:
+
+  residual stream x            f32  (B, N, C)           token-major
+  LayerNorm outputs, qkv, MLP  bf16 (B*N, ...)          GEMM operands
+  qkv                          bf16 (B, N, 3, heads, d) exactly as the qkv GEMM writes it
+  pooled q / k / v             bf16 (B, heads, L', d)
+  attention out                bf16 (B, Lq, heads*d)    written strided by the P.V GEMM
+
+The reference's reshape/permute/contiguous copies around the pooling convs and the head
+split/merge do not exist here: the pooling and attention kernels take element strides.
+"""
+import torch
+
+from .. import kernels as K
+
+EPS_BLOCK = 1e-6     # norm1 / norm2: partial(nn.LayerNorm, eps=1e-6)  (custom_multimodal_builder.py:61)
+EPS_POOL = 1e-5      # norm_q/k/v: nn.LayerNorm default               (attention.py:206)
+
+
+def block_param_names(spec):
+    """Parameter names of one block in the reference's registration order."""
+    n = ["norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias"]
+    if spec.stride_q is not None:
+        n += [("attn.upsample_q.weight" if spec.kind == "dec" else "attn.pool_q.weight"), "attn.norm_q.weight", "attn.norm_q.bias"]
+    if spec.stride_kv is not None:
+        n += ["attn.pool_k.weight", "attn.norm_k.weight", "attn.norm_k.bias",
+              "attn.pool_v.weight", "attn.norm_v.weight", "attn.norm_v.bias"]
+    n += ["norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"]
+    if spec.dim != spec.dim_out:
+        n += ["proj.weight", "proj.bias"]
+    return n
+
+
+def _split_k(m_out, n_out, k_tokens):
+    """Split factor for weight-gradient GEMMs (few output tiles, very long K = tokens)."""
+    tiles = ((m_out + 127) // 128) * ((n_out + 127) // 128)
+    want = max(1, (2 * 148) // tiles)
+    return max(1, min(want, k_tokens // 512))
+
+
+class _Ref:
+    """A (B, heads, L, d) bf16 tensor addressed by element strides inside `buf`."""
+    __slots__ = ("buf", "off", "sB", "sH", "sP", "L", "thw")
+
+    def __init__(self, buf, off, sB, sH, sP, L, thw):
+        self.buf, self.off, self.sB, self.sH, self.sP, self.L, self.thw = buf, off, sB, sH, sP, L, thw
+
+    @property
+    def strides(self):
+        return (self.sB, self.sH, self.sP)
+
+
+def _dense_ref(t, B, h, L, d, thw):
+    return _Ref(t, 0, h * L * d, L * d, d, L, thw)
+
+
+def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False):
+    """x: f32 (B, N, C).  p: {name: f32 parameter}.  wc: WeightCache.  Returns (y, thw_q, saved, attn)."""
+    B, N, C = x.shape
+    h, d = spec.heads, spec.head_dim
+    M = B * N
+    dec = spec.kind == "dec"
+    xn1, mean1, rstd1 = K.layernorm_fwd(x, p["norm1.weight"], p["norm1.bias"], EPS_BLOCK)
+    qkv = K.gemm(xn1.view(M, C), wc.w(p["attn.qkv.weight"]), M=M, N=3 * C, K=C, bias=p["attn.qkv.bias"])
+    qs = (N * 3 * C, d, 3 * C)                       # (batch, head, position) strides inside qkv
+    sv = {}
+    # ---- q / k / v, pooled where the block says so -------------------------------------------
+    if spec.stride_q is not None:
+        wq = p["attn.upsample_q.weight" if dec else "attn.pool_q.weight"]
+        qt, q_pre, q_mean, q_rstd, thw_q = K.dwconv(qkv, qs, 0, B, h, d, thw, spec.stride_q, wq, transposed=dec,
+                                                    norm=(p["attn.norm_q.weight"], p["attn.norm_q.bias"]), eps=EPS_POOL)
+        Lq = thw_q[0] * thw_q[1] * thw_q[2]
+        q = _dense_ref(qt, B, h, Lq, d, thw_q)
+        sv["q_pool"] = (q_pre, q_mean, q_rstd)
+    else:
+        thw_q, Lq = tuple(thw), N
+        q = _Ref(qkv, 0, *qs, N, thw_q)
+    if spec.stride_kv is not None:
+        kt, k_pre, k_mean, k_rstd, thw_k = K.dwconv(qkv, qs, C, B, h, d, thw, spec.stride_kv, p["attn.pool_k.weight"],
+                                                    norm=(p["attn.norm_k.weight"], p["attn.norm_k.bias"]), eps=EPS_POOL)
+        vt, v_pre, v_mean, v_rstd, _ = K.dwconv(qkv, qs, 2 * C, B, h, d, thw, spec.stride_kv, p["attn.pool_v.weight"],
+                                                norm=(p["attn.norm_v.weight"], p["attn.norm_v.bias"]), eps=EPS_POOL)
+        Lk = thw_k[0] * thw_k[1] * thw_k[2]
+        k = _dense_ref(kt, B, h, Lk, d, thw_k)
+        v = _dense_ref(vt, B, h, Lk, d, thw_k)
+        sv["k_pool"] = (k_pre, k_mean, k_rstd)
+        sv["v_pool"] = (v_pre, v_mean, v_rstd)
+    else:
+        Lk = N
+        k = _Ref(qkv, C, *qs, N, tuple(thw))
+        v = _Ref(qkv, 2 * C, *qs, N, tuple(thw))
+    # ---- attention: S = scale * q k^T -> softmax (+ in-frame mask) -> P v ---------------------
+    ldS = (Lk + 7) // 8 * 8
+    scale = d ** -0.5
+    S = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=x.device)
+    K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=S, ldc=ldS, alpha=scale, batch=(B, h),
+           sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
+    if spec.kind == "spatial":
+        P = K.softmax_fwd(S, Lk, ldS, nq=Lq, mask_hw=thw[1] * thw[2], mask_t=thw[0])
+    else:
+        P = K.softmax_fwd(S, Lk, ldS, nq=Lq)
+    del S
+    Mq = B * Lq
+    o = torch.empty((Mq, C), dtype=torch.bfloat16, device=x.device)
+    K.gemm(P, v.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=v.sP, out=o, ldc=C, batch=(B, h),
+           sA=(h * Lq * ldS, Lq * ldS), sB=(v.sB, v.sH), sC=(Lq * C, d), b_off=v.off)
+    # ---- residual path (attention.py:240 / :471) --------------------------------------------------
+    arg = None
+    if spec.stride_q is None or spec.kind in ("spatial", "temporal"):
+        x_res = x
+    elif dec:
+        x_res = K.upsample_fwd(x, B, thw, C, spec.stride_q)
+    else:
+        assert tuple(spec.stride_q) == (1, 2, 2), "pool_skip kernel is specialised for MaxPool3d k(1,3,3) s(1,2,2)"
+        x_res, arg = K.maxpool_fwd(x, B, thw, C, want_arg=save)
+    rps = Lq if dp_scale is not None else 0
+    x1 = K.gemm(o, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, bias=p["attn.proj.bias"], residual=x_res.view(Mq, C),
+                out_dtype=torch.float32, row_scale=dp_scale, rows_per_scale=rps)
+    # ---- MLP (attention.py:243-247) -----------------------------------------------------------------
+    xn2, mean2, rstd2 = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], EPS_BLOCK)
+    hid = spec.hidden
+    Z = torch.empty((Mq, hid), dtype=torch.bfloat16, device=x.device) if save else None
+    hdn = K.gemm(xn2, wc.w(p["mlp.fc1.weight"]), M=Mq, N=hid, K=C, bias=p["mlp.fc1.bias"], act=1, Z=Z)
+    if spec.dim != spec.dim_out:
+        base = K.gemm(xn2, wc.w(p["proj.weight"]), M=Mq, N=spec.dim_out, K=C, bias=p["proj.bias"], out_dtype=torch.float32)
+    else:
+        base = x1
+    x2 = K.gemm(hdn, wc.w(p["mlp.fc2.weight"]), M=Mq, N=spec.dim_out, K=hid, bias=p["mlp.fc2.bias"], residual=base,
+                out_dtype=torch.float32, row_scale=dp_scale, rows_per_scale=rps)
+    y = x2.view(B, Lq, spec.dim_out)
+    attn = P[..., :Lk].float() if want_attn else None
+    if not save:
+        return y, thw_q, None, attn
+    sv.update(x=x, thw=tuple(thw), mean1=mean1, rstd1=rstd1, xn1=xn1, qkv=qkv, q=q, k=k, v=v, P=P, o=o, arg=arg,
+              x1=x1, mean2=mean2, rstd2=rstd2, xn2=xn2, Z=Z, hdn=hdn, dp=dp_scale, Lq=Lq, Lk=Lk, ldS=ldS, thw_q=thw_q)
+    return y, thw_q, sv, attn
+
+
+def block_backward(spec, p, wc, sv, dy):
+    """dy: f32 (B, Lq, dim_out).  Returns (dx f32 (B,N,C), {param name: grad})."""
+    x = sv["x"]
+    B, N, C = x.shape
+    h, d = spec.heads, spec.head_dim
+    dec = spec.kind == "dec"
+    Lq, Lk, ldS, thw, thw_q = sv["Lq"], sv["Lk"], sv["ldS"], sv["thw"], sv["thw_q"]
+    M, Mq, hid, Co = B * N, B * Lq, spec.hidden, spec.dim_out
+    dp = sv["dp"]
+    rps = Lq if dp is not None else 0
+    dev = x.device
+    g = {}
+
+    def zeros(n):
+        return torch.zeros(n, dtype=torch.float32, device=dev)
+
+    def wgrad(a_rows, b_rows, m_out, n_out, ktok):
+        # dW[m_out, n_out] = a_rows^T . b_rows   (both token-major: contraction over rows)
+        return K.gemm(a_rows, b_rows, M=m_out, N=n_out, K=ktok, a_kmajor=False, b_kmajor=False, lda=m_out, ldb=n_out,
+                      out_dtype=torch.float32, split_k=_split_k(m_out, n_out, ktok))
+
+    dy = dy.contiguous().view(Mq, Co)
+    g2 = K.cast_bf16(dy, row_scale=dp, rows_per_scale=rps)             # gradient entering the (drop-path scaled) MLP branch
+    # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
+    dZ = K.gemm(g2, wc.wt(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, act=2, Z=sv["Z"])
+    g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq)
+    g["mlp.fc2.bias"] = K.colsum(g2, Mq, Co)
+    dxn2 = K.gemm(dZ, wc.wt(p["mlp.fc1.weight"]), M=Mq, N=C, K=hid)
+    g["mlp.fc1.weight"] = wgrad(dZ, sv["xn2"], hid, C, Mq)
+    g["mlp.fc1.bias"] = K.colsum(dZ, Mq, hid)
+    del dZ
+    g["norm2.weight"], g["norm2.bias"] = zeros(C), zeros(C)
+    if spec.dim != spec.dim_out:
+        gp = g2 if dp is None else K.cast_bf16(dy)                       # the re-based residual is not drop-path scaled
+        K.gemm(gp, wc.wt(p["proj.weight"]), M=Mq, N=C, K=Co, out=dxn2, accumulate=True)
+        g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq)
+        g["proj.bias"] = K.colsum(dy, Mq, Co)
+        dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"])
+    else:
+        dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
+                              add=dy)
+    del dxn2, g2
+    # ---- attention output projection ------------------------------------------------------------------
+    g1 = K.cast_bf16(dx1, row_scale=dp, rows_per_scale=rps)
+    do = K.gemm(g1, wc.wt(p["attn.proj.weight"]), M=Mq, N=C, K=C)       # (B, Lq, heads, d)
+    g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq)
+    g["attn.proj.bias"] = K.colsum(g1, Mq, C)
+    del g1
+    # ---- residual path -----------------------------------------------------------------------------------
+    if spec.stride_q is None or spec.kind in ("spatial", "temporal"):
+        dx_skip = dx1.view(B, N, C)
+    elif dec:
+        dx_skip = K.upsample_bwd(dx1, B, thw, C, spec.stride_q)
+    else:
+        dx_skip = K.maxpool_bwd(dx1, sv["arg"], B, thw, C)
+    # ---- attention backward ------------------------------------------------------------------------------
+    q, k, v, P = sv["q"], sv["k"], sv["v"], sv["P"]
+    dqkv = torch.empty((M, 3 * C), dtype=torch.bfloat16, device=dev)
+    qs = (N * 3 * C, d, 3 * C)
+    pooled_q, pooled_kv = spec.stride_q is not None, spec.stride_kv is not None
+
+    def grad_target(pooled, L, slot):
+        if pooled:
+            t = torch.empty((B, h, L, d), dtype=torch.bfloat16, device=dev)
+            return t, dict(out=t, ldc=d, sC=(h * L * d, L * d), c_off=0)
+        return None, dict(out=dqkv, ldc=3 * C, sC=(qs[0], qs[1]), c_off=slot * C)
+
+    sP = (h * Lq * ldS, Lq * ldS)
+    dv_t, tgt = grad_target(pooled_kv, Lk, 2)
+    K.gemm(P, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=C, batch=(B, h), sA=sP, sB=(Lq * C, d), **tgt)
+    dP = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=dev)
+    K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP,
+           b_off=v.off)
+    dS = K.softmax_bwd(P, dP, Lk, d ** -0.5)
+    del dP
+    dq_t, tgt = grad_target(pooled_q, Lq, 0)
+    K.gemm(dS, k.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=k.sP, batch=(B, h), sA=sP, sB=(k.sB, k.sH), b_off=k.off, **tgt)
+    dk_t, tgt = grad_target(pooled_kv, Lk, 1)
+    K.gemm(dS, q.buf, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=q.sP, batch=(B, h), sA=sP, sB=(q.sB, q.sH),
+           b_off=q.off, **tgt)
+    del dS
+
+    def pool_backward(dt, key, slot, stride, wname, nname, transposed, grid_out):
+        pre, mean, rstd = sv[key]
+        L = grid_out[0] * grid_out[1] * grid_out[2]
+        g[nname + ".weight"], g[nname + ".bias"] = zeros(d), zeros(d)
+        du = K.layernorm_bwd(dt, pre, mean, rstd, p[nname + ".weight"], g[nname + ".weight"], g[nname + ".bias"],
+                             dx_dtype=torch.bfloat16)
+        dense = (h * L * d, L * d, d)
+        # data gradient: the adjoint gather of the forward conv, written straight into the qkv-gradient slice
+        K.dwconv(du, dense, 0, B, h, d, grid_out, stride, p[wname], transposed=not transposed, out=dqkv, out_strides=qs,
+                 out_off=slot * C, thw_out=thw)
+        dw = torch.zeros_like(p[wname])
+        if transposed:
+            K.dwconv_wgrad(sv["qkv"], qs, slot * C, thw, du, dense, 0, grid_out, B, h, d, stride, dw)
+        else:
+            K.dwconv_wgrad(du, dense, 0, grid_out, sv["qkv"], qs, slot * C, thw, B, h, d, stride, dw)
+        g[wname] = dw
+
+    if pooled_q:
+        pool_backward(dq_t, "q_pool", 0, spec.stride_q, "attn.upsample_q.weight" if dec else "attn.pool_q.weight", "attn.norm_q",
+                      dec, thw_q)
+    if pooled_kv:
+        pool_backward(dk_t, "k_pool", 1, spec.stride_kv, "attn.pool_k.weight", "attn.norm_k", False, k.thw)
+        pool_backward(dv_t, "v_pool", 2, spec.stride_kv, "attn.pool_v.weight", "attn.norm_v", False, v.thw)
+    # ---- qkv projection and norm1 ---------------------------------------------------------------------------
+    dxn1 = K.gemm(dqkv, wc.wt(p["attn.qkv.weight"]), M=M, N=C, K=3 * C)
+    g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M)
+    g["attn.qkv.bias"] = K.colsum(dqkv, M, 3 * C)
+    g["norm1.weight"], g["norm1.bias"] = zeros(C), zeros(C)
+    dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
+                         add=dx_skip.view(B, N, C))
+    return dx, g
+
+
+class BlockFn(torch.autograd.Function):
+    """autograd node: (x, *block parameters) -> block output.  Non-tensor context (spec, weight cache,
+    grid) travels in `meta`."""
+
+    @staticmethod
+    def forward(ctx, meta, x, *params):
+        spec, wc, thw, dp_scale, names = meta
+        p = dict(zip(names, params))
+        need = any(ctx.needs_input_grad)      # forward runs under no_grad: ask the node, not the mode
+        y, thw_q, sv, _ = block_forward(spec, p, wc, x.contiguous(), thw, dp_scale, save=need)
+        ctx.meta = meta
+        ctx.sv = sv
+        ctx.params = params
+        ctx.thw_q = thw_q
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec, wc, thw, dp_scale, names = ctx.meta
+        p = dict(zip(names, ctx.params))
+        dx, g = block_backward(spec, p, wc, ctx.sv, dy)
+        ctx.sv = None
+        return (None, dx) + tuple(g[n].view_as(p[n]) for n in names)

@@ -1,0 +1,379 @@
+"""CSTS — audio-visual gaze-forecasting network on the libcsts_b200 kernels.
+
+Drop-in for ``slowfast/models/custom_multimodal_builder.py:20-498``: same constructor argument
+(`cfg`), same ``forward(x, y, return_embed, return_spatial_attn, return_temporal_attn)`` contract,
+same module tree and parameter names/shapes/order (so reference checkpoints, the reference
+optimizer's parameter grouping and DDP work unchanged), same initialisation (identical tensors
+under the same ``torch.manual_seed``).  The ``nn.Linear`` / ``nn.Conv3d`` / ``nn.LayerNorm`` members
+are *parameter holders only*: their ``forward`` is never called — every operation runs in
+hand-written CUDA through ``csts_b200.kernels``; there is no PyTorch or CPU fallback.
+"""
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+from torch.nn.init import trunc_normal_
+
+from .. import kernels as K
+from .block import BlockFn, block_forward, block_param_names
+from .build import MODEL_REGISTRY
+from .plan import build_plan
+from .weights import WeightCache
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (module tree mirrors the reference: attention.py, av_attention.py, common.py,
+# stem_helper.py)
+# ---------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter holder: CSTS runs through csts_b200 kernels, not nn.Module.forward")
+
+
+class PatchEmbed(_Holder):
+    def __init__(self, dim_in, dim_out, kernel, stride, padding):
+        super().__init__()
+        self.proj = nn.Conv3d(dim_in, dim_out, kernel_size=tuple(kernel), stride=tuple(stride), padding=tuple(padding))
+
+
+class Mlp(_Holder):
+    def __init__(self, dim, hidden, dim_out):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim_out)
+
+
+class Attention(_Holder):
+    def __init__(self, spec, qkv_bias):
+        super().__init__()
+        dim, d = spec.dim, spec.head_dim
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        if spec.stride_q is not None:
+            if spec.kind == "dec":
+                op = tuple(0 if s == 1 else s - 1 for s in spec.stride_q)
+                self.upsample_q = nn.ConvTranspose3d(d, d, (3, 3, 3), stride=spec.stride_q, padding=(1, 1, 1), output_padding=op,
+                                                     groups=d, bias=False)
+            else:
+                self.pool_q = nn.Conv3d(d, d, (3, 3, 3), stride=spec.stride_q, padding=(1, 1, 1), groups=d, bias=False)
+            self.norm_q = nn.LayerNorm(d)
+        if spec.stride_kv is not None:
+            self.pool_k = nn.Conv3d(d, d, (3, 3, 3), stride=spec.stride_kv, padding=(1, 1, 1), groups=d, bias=False)
+            self.norm_k = nn.LayerNorm(d)
+            self.pool_v = nn.Conv3d(d, d, (3, 3, 3), stride=spec.stride_kv, padding=(1, 1, 1), groups=d, bias=False)
+            self.norm_v = nn.LayerNorm(d)
+
+
+class Block(_Holder):
+    """MultiScaleBlock / MultiScaleDecoderBlock / SpatialBlock / TemporalBlock parameter set."""
+
+    def __init__(self, spec, qkv_bias, norm_layer):
+        super().__init__()
+        self.spec = spec
+        self.dim, self.dim_out = spec.dim, spec.dim_out
+        self.norm1 = norm_layer(spec.dim)
+        self.attn = Attention(spec, qkv_bias)
+        self.norm2 = norm_layer(spec.dim)
+        self.mlp = Mlp(spec.dim, spec.hidden, spec.dim_out)
+        if spec.dim != spec.dim_out:
+            self.proj = nn.Linear(spec.dim, spec.dim_out)
+        self._names = block_param_names(spec)
+
+    def tensors(self):
+        out = []
+        for n in self._names:
+            obj = self
+            for part in n.split("."):
+                obj = getattr(obj, part)
+            out.append(obj)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd nodes of the model-level glue
+# ---------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """Conv3d k(3,7,7) s(2,4,4) p(1,3,3) as im2col + tcgen05 GEMM, bias and the separable position
+    embedding fused in the epilogue.  ref: stem_helper.py:35-38, custom_multimodal_builder.py:345,362-370."""
+
+    @staticmethod
+    def forward(ctx, wc, x, weight, bias, pos_spatial, pos_temporal):
+        B = x.shape[0]
+        kdim = weight[0].numel()
+        kp = (kdim + 7) // 8 * 8
+        patches = K.im2col_patch(x.contiguous(), kp)
+        pos = K.pos_embed(pos_spatial, pos_temporal)
+        n_tok = pos.shape[0]
+        tok = K.gemm(patches, wc.w_padded(weight, kp), M=B * n_tok, N=weight.shape[0], K=kp, bias=bias, residual=pos, res_mod=n_tok,
+                     out_dtype=torch.float32)
+        ctx.save_for_backward(patches)
+        ctx.dims = (B, n_tok, pos_temporal.shape[1], pos_spatial.shape[1], weight.shape, kp)
+        return tok.view(B, n_tok, weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dtok):
+        (patches,) = ctx.saved_tensors
+        B, n_tok, T, HW, wshape, kp = ctx.dims
+        Cn = wshape[0]
+        dtok = dtok.contiguous()
+        g = K.cast_bf16(dtok.view(B * n_tok, Cn))
+        M = B * n_tok
+        dwp = K.gemm(g, patches, M=Cn, N=kp, K=M, a_kmajor=False, b_kmajor=False, lda=Cn, ldb=kp, out_dtype=torch.float32,
+                     split_k=max(1, min(64, M // 2048)))
+        kdim = wshape[1] * wshape[2] * wshape[3] * wshape[4]
+        dw = dwp[:, :kdim].reshape(wshape)
+        db = K.colsum(dtok, M, Cn)
+        dsp, dtm = K.pos_embed_bwd(dtok, B, T, HW, Cn)
+        return None, None, dw, db, dsp, dtm
+
+
+class FramePoolFn(torch.autograd.Function):
+    """Dense Conv3d(C, C, (1,8,8)) over a (B, T*64, C) token map = skinny split-K GEMM
+    (M = B*T, K = 64*C, N = C).  ref: custom_multimodal_builder.py:227-229, :420-421, :442-445."""
+
+    @staticmethod
+    def forward(ctx, wc, tok, weight, bias):
+        B, N, Cn = tok.shape
+        T = N // 64
+        a = K.cast_bf16(tok.contiguous())
+        w = wc.frame_pool_w(weight)
+        Kd = 64 * Cn
+        out = K.gemm(a.view(B * T, Kd), w, M=B * T, N=weight.shape[0], K=Kd, bias=bias, out_dtype=torch.float32, split_k=24)
+        ctx.save_for_backward(a)
+        ctx.wc, ctx.weight = wc, weight
+        return out.view(B, T, weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        (a,) = ctx.saved_tensors
+        weight = ctx.weight
+        B, N, Cn = a.shape
+        T, O, Kd = N // 64, weight.shape[0], 64 * Cn
+        dout = dout.contiguous().view(B * T, O)
+        g = K.cast_bf16(dout)
+        w = ctx.wc.frame_pool_w(weight)
+        dtok = K.gemm(g, w, M=B * T, N=Kd, K=O, b_kmajor=False, ldb=Kd, out_dtype=torch.float32)
+        dwp = K.gemm(g, a.view(B * T, Kd), M=O, N=Kd, K=B * T, a_kmajor=False, b_kmajor=False, lda=O, ldb=Kd, out_dtype=torch.float32)
+        dw = K.permute_021(dwp, O, 64, Cn, torch.float32).view(weight.shape)      # (O, hw, c) -> (O, c, hw)
+        db = K.colsum(dout, B * T, O)
+        return None, dtok.view(B, N, Cn), dw, db
+
+
+class ReweightFn(torch.autograd.Function):
+    """x * w[:, t] broadcast over the 64 positions of frame t; `w_off` selects the visual (0) or audio
+    (T*C) half of the temporal-fusion output.  ref: custom_multimodal_builder.py:454-461."""
+
+    @staticmethod
+    def forward(ctx, x, av, w_off, T):
+        B, N, Cn = x.shape
+        x, av = x.contiguous(), av.contiguous()
+        out = K.reweight_fwd(x, av, w_off, av.shape[1] * Cn, B, T, N // T, Cn)
+        ctx.save_for_backward(x, av)
+        ctx.w_off, ctx.T = w_off, T
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, av = ctx.saved_tensors
+        B, N, Cn = x.shape
+        dav = torch.zeros_like(av)
+        dx = K.reweight_bwd(dout.contiguous(), x, av, ctx.w_off, av.shape[1] * Cn, dav, B, ctx.T, N // ctx.T, Cn)
+        return dx, dav, None, None
+
+
+class MeanProjFn(torch.autograd.Function):
+    """mean over tokens followed by Linear(768, 256).  ref: custom_multimodal_builder.py:493-496."""
+
+    @staticmethod
+    def forward(ctx, wc, x, weight, bias):
+        B, N, Cn = x.shape
+        m = K.token_mean_fwd(x.contiguous(), B, N, Cn)
+        out = K.gemm(m, wc.w(weight), M=B, N=weight.shape[0], K=Cn, bias=bias, out_dtype=torch.float32)
+        ctx.save_for_backward(m)
+        ctx.wc, ctx.weight, ctx.dims = wc, weight, (B, N, Cn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (m,) = ctx.saved_tensors
+        B, N, Cn = ctx.dims
+        O = ctx.weight.shape[0]
+        dout = dout.contiguous()
+        g = K.cast_bf16(dout)
+        dm = K.gemm(g, ctx.wc.w(ctx.weight), M=B, N=Cn, K=O, b_kmajor=False, ldb=Cn, out_dtype=torch.float32)
+        dx = K.token_mean_bwd(dm, B, N, Cn)
+        dw = K.gemm(g, m, M=O, N=Cn, K=B, a_kmajor=False, b_kmajor=False, lda=O, ldb=Cn, out_dtype=torch.float32)
+        db = K.colsum(dout, B, O)
+        return None, dx, dw, db
+
+
+class HeadFn(torch.autograd.Function):
+    """classifier(feat + trilinear_T(stem)) -> logits (B,1,2T,H,W).  ref: custom_multimodal_builder.py:476-481."""
+
+    @staticmethod
+    def forward(ctx, feat, stem, weight, bias, thw):
+        B, _, Cn = feat.shape
+        Ti, S = thw[0], thw[1] * thw[2]
+        feat, stem = feat.contiguous(), stem.contiguous()
+        logits = K.classifier_fwd(feat, stem, weight, bias, B, Ti, S, Cn)
+        ctx.save_for_backward(feat, stem, weight)
+        ctx.dims = (B, Ti, S, Cn)
+        return logits.view(B, 1, 2 * Ti, thw[1], thw[2])
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        feat, stem, weight = ctx.saved_tensors
+        B, Ti, S, Cn = ctx.dims
+        dfeat, dstem, dw, db = K.classifier_bwd(dlogits.contiguous(), feat, stem, weight, B, Ti, S, Cn)
+        return dfeat, dstem, dw.view_as(weight), db, None
+
+
+class AddFn(torch.autograd.Function):
+    """Decoder skip connection a + b on the f32 residual stream.  ref: custom_multimodal_builder.py:467-473."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        return K.add_f32(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+# ---------------------------------------------------------------------------------------------
+@MODEL_REGISTRY.register()
+class CSTS(nn.Module):
+    """Multiscale Vision Transformer with audio-visual fusion (see module docstring)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        assert cfg.DATA.TRAIN_CROP_SIZE == cfg.DATA.TEST_CROP_SIZE
+        self.cfg = cfg
+        mv = cfg.MVIT
+        assert not mv.CLS_EMBED_ON and mv.SEP_POS_EMBED and not mv.PATCH_2D and not mv.NORM_STEM, \
+            "csts_b200 implements the configuration of configs/{Ego4D,Aria}/CSTS_*.yaml"
+        assert mv.DROPOUT_RATE == 0.0 and not cfg.MODEL.ACT_CHECKPOINT
+        assert mv.NORM == "layernorm"
+        assert list(mv.PATCH_KERNEL) == [3, 7, 7] and list(mv.PATCH_STRIDE) == [2, 4, 4] and list(mv.PATCH_PADDING) == [1, 3, 3], \
+            "the patch-embed kernel is specialised for k(3,7,7) s(2,4,4) p(1,3,3)"
+        self.spatial_audio_attn = mv.SPATIAL_AUDIO_ATTN
+        if self.spatial_audio_attn:
+            raise NotImplementedError("MVIT.SPATIAL_AUDIO_ATTN=True is not part of the hot path yet (SURVEY.md §8f row 3)")
+        norm_layer = partial(nn.LayerNorm, eps=1e-6)
+        embed_dim = mv.EMBED_DIM
+        self.patch_stride = list(mv.PATCH_STRIDE)
+        size, frames = cfg.DATA.TRAIN_CROP_SIZE, cfg.DATA.NUM_FRAMES
+        self.patch_dims = [frames // self.patch_stride[0], size // self.patch_stride[1], size // self.patch_stride[2]]
+        specs = build_plan(cfg)
+        self.specs = {s.name: s for s in specs}
+        depth = mv.DEPTH
+
+        self.patch_embed = PatchEmbed(cfg.DATA.INPUT_CHANNEL_NUM[0], embed_dim, mv.PATCH_KERNEL, mv.PATCH_STRIDE, mv.PATCH_PADDING)
+        self.patch_embed_audio = PatchEmbed(1, embed_dim, mv.PATCH_KERNEL, mv.PATCH_STRIDE, mv.PATCH_PADDING)
+        hw = self.patch_dims[1] * self.patch_dims[2]
+        self.pos_embed_spatial = nn.Parameter(torch.zeros(1, hw, embed_dim))
+        self.pos_embed_temporal = nn.Parameter(torch.zeros(1, self.patch_dims[0], embed_dim))
+        self.pos_embed_spatial_audio = nn.Parameter(torch.zeros(1, hw, embed_dim))
+        self.pos_embed_temporal_audio = nn.Parameter(torch.zeros(1, self.patch_dims[0], embed_dim))
+
+        self.blocks = nn.ModuleList([Block(s, mv.QKV_BIAS, norm_layer) for s in specs[:depth]])
+        self.blocks_audio = nn.ModuleList([Block(s, mv.QKV_BIAS, norm_layer) for s in specs[depth:depth + 4]])
+        token_dim = specs[depth - 1].dim_out
+        if "nce" in cfg.MODEL.LOSS_FUNC:
+            self.vision_proj = nn.Linear(token_dim, 256)
+            self.audio_proj = nn.Linear(token_dim, 256)
+        self.vision_pool = nn.Conv3d(token_dim, token_dim, kernel_size=(1, 8, 8), stride=1)
+        self.audio_pool = nn.Conv3d(token_dim, token_dim, kernel_size=(1, 8, 8), stride=1)
+        self.audio_pool2 = nn.Conv3d(token_dim, token_dim, kernel_size=(1, 8, 8), stride=1)
+        self.temporal_fusion = Block(self.specs["temporal_fusion"], mv.QKV_BIAS, norm_layer)
+        self.spatial_fusion = Block(self.specs["spatial_fusion"], mv.QKV_BIAS, norm_layer)
+        for i in range(1, 5):
+            setattr(self, f"decode_block{i}", Block(self.specs[f"decode_block{i}"], mv.QKV_BIAS, norm_layer))
+        self.classifier = nn.Conv3d(96, 1, kernel_size=1)
+
+        trunc_normal_(self.pos_embed_spatial, std=0.02)
+        trunc_normal_(self.pos_embed_temporal, std=0.02)
+        trunc_normal_(self.pos_embed_spatial_audio, std=0.02)
+        trunc_normal_(self.pos_embed_temporal_audio, std=0.02)
+        self.apply(self._init_weights)
+        self._wc = WeightCache()
+
+    @staticmethod
+    def _init_weights(m):
+        # custom_multimodal_builder.py:318-325
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        if self.cfg.MVIT.ZERO_DECAY_POS_CLS:
+            return {"pos_embed_spatial", "pos_embed_temporal", "pos_embed_class"}
+        return {}
+
+    # -----------------------------------------------------------------------------------------
+    def _run_block(self, blk, x, thw):
+        spec = blk.spec
+        dp_scale = None
+        if self.training and spec.drop_path > 0.0:
+            # DropPath (common.py:46-59): per-sample keep mask, scaled by 1/keep_prob
+            keep = 1.0 - spec.drop_path
+            dp_scale = torch.floor(keep + torch.rand(x.shape[0], dtype=torch.float32, device=x.device)) / keep
+        meta = (spec, self._wc, tuple(thw), dp_scale, blk._names)
+        y = BlockFn.apply(meta, x, *blk.tensors())
+        return y, spec.q_grid(thw)
+
+    def forward(self, x, y, return_embed=False, return_spatial_attn=False, return_temporal_attn=False):
+        if return_spatial_attn or return_temporal_attn:
+            raise NotImplementedError("attention-map outputs are a visualisation path (SURVEY.md §8f row 3)")
+        video = x[0] if isinstance(x, (list, tuple)) else x
+        if not video.is_cuda:
+            raise RuntimeError("csts_b200.CSTS runs on CUDA (sm_100a) only; there is no CPU path")
+        video, audio = video.float(), y.float()
+        wc = self._wc
+        x = PatchEmbedFn.apply(wc, video, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
+                               self.pos_embed_spatial, self.pos_embed_temporal)
+        y = PatchEmbedFn.apply(wc, audio, self.patch_embed_audio.proj.weight, self.patch_embed_audio.proj.bias,
+                               self.pos_embed_spatial_audio, self.pos_embed_temporal_audio)
+        B = x.shape[0]
+        thw = tuple(self.patch_dims)
+        thw_a = thw
+        skips = [(x, thw)]
+        for i, blk in enumerate(self.blocks):
+            x, thw = self._run_block(blk, x, thw)
+            if i in (0, 2, 13):
+                skips.append((x, thw))
+        for blk in self.blocks_audio:
+            y, thw_a = self._run_block(blk, y, thw_a)
+        # spatial fusion (custom_multimodal_builder.py:414-432)
+        n_vis = x.shape[1]
+        y_sp = FramePoolFn.apply(wc, y, self.audio_pool.weight, self.audio_pool.bias)
+        av, _ = self._run_block(self.spatial_fusion, torch.cat([x, y_sp], dim=1), thw)
+        x_sp = av[:, :n_vis]
+        # temporal fusion (:435-451)
+        x_t = FramePoolFn.apply(wc, x, self.vision_pool.weight, self.vision_pool.bias)
+        y_t = FramePoolFn.apply(wc, y, self.audio_pool2.weight, self.audio_pool2.bias)
+        av_t, _ = self._run_block(self.temporal_fusion, torch.cat([x_t, y_t], dim=1), (2, 2, 2))
+        # re-weight (:454-461)
+        T = thw[0]
+        Cn = x.shape[2]
+        xw = ReweightFn.apply(x_sp, av_t, 0, T)
+        # decoder (:465-479)
+        f = xw
+        for i in range(4):
+            f, thw = self._run_block(getattr(self, f"decode_block{i + 1}"), f, thw)
+            if i < 3:
+                f = AddFn.apply(f, skips[3 - i][0])
+        stem, thw0 = skips[0]
+        logits = HeadFn.apply(f, stem, self.classifier.weight, self.classifier.bias, thw0)
+        if not return_embed:
+            return logits
+        yw = ReweightFn.apply(y, av_t, T * Cn, T)
+        v = MeanProjFn.apply(wc, xw, self.vision_proj.weight, self.vision_proj.bias)
+        a = MeanProjFn.apply(wc, yw, self.audio_proj.weight, self.audio_proj.bias)
+        return [logits, v, a]

@@ -1,0 +1,85 @@
+"""Data-parallel helpers of the hot path (ref slowfast/utils/distributed.py:15-110, :305-320).
+
+The only cross-sample coupling of the training step is the InfoNCE similarity matrix: every rank
+needs every rank's (B_local, 256) video and audio embeddings.  `all_gather_with_grad` performs ONE
+all-gather of the concatenated [v | a] rows (the reference issues one per tensor) and is
+differentiable: backward returns the local rank's slice of the incoming gradient.
+
+Deliberate fix: the reference stores ``ctx.rank = 0`` (distributed.py:23) so every
+rank back-propagates rank 0's slice.  Here the true rank is used, and the slice is multiplied by
+the world size so that — after DDP's mean all-reduce of parameter gradients — the result equals
+the gradient of the single-process global-batch loss (each rank evaluates the full-batch NCE loss
+but can only differentiate through its own rows).
+"""
+import torch
+import torch.distributed as dist
+
+
+def get_world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def get_rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def is_master_proc(num_gpus=8):
+    return get_rank() % num_gpus == 0 if get_world_size() > 1 else True
+
+
+class _AllGatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor):
+        world = get_world_size()
+        ctx.rows = tensor.shape[0]
+        ctx.rank = get_rank()
+        ctx.world = world
+        out = torch.empty((world * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+        dist.all_gather_into_tensor(out, tensor.contiguous())
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lo = ctx.rows * ctx.rank
+        return grad_output[lo: lo + ctx.rows] * float(ctx.world)
+
+
+def all_gather_with_grad(tensors):
+    """Differentiable all-gather (concatenation along dim 0) of a list of equally-shaped 2-D tensors."""
+    if get_world_size() == 1:
+        return list(tensors)
+    widths = [t.shape[1] for t in tensors]
+    packed = _AllGatherRows.apply(torch.cat(list(tensors), dim=1))
+    return list(torch.split(packed, widths, dim=1))
+
+
+def all_reduce(tensors, average=True):
+    """In-place sum (or mean) across ranks; returns the list (distributed.py:75-91)."""
+    world = get_world_size()
+    if world == 1:
+        return tensors
+    for t in tensors:
+        dist.all_reduce(t, async_op=False)
+    if average:
+        for t in tensors:
+            t.mul_(1.0 / world)
+    return tensors
+
+
+def all_gather(tensors):
+    """Concatenate each tensor across ranks along dim 0 (distributed.py:52-72)."""
+    world = get_world_size()
+    if world == 1:
+        return list(tensors)
+    out = []
+    for t in tensors:
+        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t.contiguous())
+        out.append(buf)
+    return out
+
+
+def init_distributed_training(cfg):
+    """distributed.py:305-320 creates one process group per machine for SyncBN; CSTS has no
+    BatchNorm, so nothing is needed beyond the default group."""
+    return None

@@ -20,7 +20,8 @@ def set_gemm_backend(code: int):
 
 def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=torch.bfloat16,
          ldc=None, bias=None, act=0, Z=None, residual=None, res_mod=0, accumulate=False, alpha=1.0, split_k=1,
-         batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None):
+         batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None,
+         row_scale=None, rows_per_scale=0):
     """C = epi(alpha * op(A) @ op(B)).  A/B are bf16 storage tensors; offsets/strides in elements."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     if lda is None:
@@ -40,6 +41,8 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
     a.Z = Z.data_ptr() if Z is not None else None
     a.bias = bias.data_ptr() if bias is not None else None
     a.residual = residual.data_ptr() if residual is not None else None
+    a.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    a.rows_per_scale = rows_per_scale
     a.lda, a.ldb, a.ldc = lda, ldb, ldc
     a.ldz = ldc
     a.ldr = N
@@ -101,13 +104,14 @@ def softmax_bwd(P, dP, n, scale):
     return dS
 
 
-def cast_bf16(src, ld_out=None):
-    """f32 (rows, cols) -> bf16 (rows, ld_out), zero padded."""
+def cast_bf16(src, ld_out=None, row_scale=None, rows_per_scale=0):
+    """f32 (rows, cols) -> bf16 (rows, ld_out), zero padded; optional per-row-group scale
+    (row m is multiplied by row_scale[m // rows_per_scale])."""
     src2 = src.reshape(-1, src.shape[-1]) if src.dim() > 1 else src.reshape(1, -1)
     rows, cols = src2.shape
     ld = cols if ld_out is None else ld_out
     dst = torch.empty((rows, ld), dtype=torch.bfloat16, device=src.device)
-    call("csts_cast_bf16", ptr(src2), ptr(dst), rows, cols, ld)
+    call("csts_cast_bf16", ptr(src2), ptr(dst), rows, cols, ld, ptr(row_scale), rows_per_scale)
     return dst if ld_out is not None else dst.reshape(src.shape)
 
 
