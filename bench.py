@@ -1,0 +1,260 @@
+#!/usr/bin/env python3
+"""CSTS hot-path benchmark (driver contract: one JSON line on rank 0).
+
+    python bench.py --gpus N --steps K --warmup W             # csts_b200 arm
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU arm (oracle port)
+
+Workload (BASELINE.json configs[1]): CSTS Ego4D training step — forward(return_embed) + frame_softmax
++ KLDiv + sim_matrix + EgoNCE (LOSS_ALPHA 0.05) + backward + grad-norm clip (1.0) + AdamW — at a
+per-GPU batch of 8 clips (8 x 256 x 256 RGB + 8 x 256 x 256 log-STFT), bf16 tensor-core operands /
+f32 accumulate and residual stream, synthetic inputs, random-init weights, MVIT.DROPPATH_RATE 0.2.
+N > 1: one process per GPU (torchrun), batch-sharded (weak scaling), NCE all-gather + DDP all-reduce.
+
+  value : clips/s with inputs already resident in HBM (CUDA-event timed, max over ranks)
+  e2e   : the same step through the public API with the batch in pinned HOST memory — H2D of video /
+          audio / labels and D2H of the loss inside the timed region
+  roofline     : the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time vs measured peak
+  cpu_baseline : the oracle (fp32 restatement of the reference) training step on the host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "train clips/s"
+BATCH_PER_GPU = 8
+WORKLOAD = "CSTS_Ego4D_Gaze_Forecast train step (kldiv+egonce, alpha 0.05), batch 8 per GPU, 8x256x256 clip + 8x256x256 log-STFT"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops_sustained"], "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_cfg(n_gpus):
+    from csts_b200.host.config import assert_and_infer_cfg, get_cfg
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(ROOT, "configs", "Ego4D", "CSTS_Ego4D_Gaze_Forecast.yaml"))
+    cfg.merge_from_list(["NUM_GPUS", n_gpus, "MODEL.LOSS_FUNC", "kldiv+egonce", "TRAIN.BATCH_SIZE", BATCH_PER_GPU * n_gpus,
+                         "TEST.BATCH_SIZE", BATCH_PER_GPU * n_gpus])
+    return assert_and_infer_cfg(cfg)
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_step_clips_per_s(batch, steps, warmup):
+    """Oracle (fp32 torch restatement of the reference, oracle/csts_oracle.py) fwd + loss + bwd on the
+    host cores: the reference's CPU path (NUM_GPUS=0).  AdamW/clip are omitted on this arm: they are
+    <1 % of a CPU step."""
+    import torch
+    import csts_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    with open(os.path.join(ROOT, "tests", "golden", "param_shapes.json")) as f:
+        shapes = json.load(f)
+    sd = O.synthetic_state(shapes, seed=0)
+    video, audio, hm = O.synthetic_batch(batch, seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, video, audio, hm, alpha=0.05)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), torch.get_num_threads(), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    cps, cores, times = cpu_train_step_clips_per_s(batch, steps, warmup=1)
+    sample = f"{steps} timed fwd+loss+bwd steps at batch {batch} (of the batch-{BATCH_PER_GPU} workload), oracle port, fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import csts_oracle as O
+    from csts_b200 import _lib, kernels as K
+    from csts_b200.host.build import build_model
+    from csts_b200.host.train_step import construct_optimizer, train_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = make_cfg(world)
+    torch.manual_seed(cfg.RNG_SEED)
+    model = build_model(cfg)
+    model.train()
+    opt = construct_optimizer(model, cfg)
+    B = BATCH_PER_GPU
+    # host batch in pinned memory (the public-API path) and a resident device copy
+    video_h, audio_h, hm_h = O.synthetic_batch(B, seed=100 + rank)
+    video_h, audio_h, hm_h = video_h.pin_memory(), audio_h.pin_memory(), hm_h.pin_memory()
+    video_d, audio_d, hm_d = video_h.to(dev), audio_h.to(dev), hm_h.to(dev)
+    h2d = video_h.numel() * 4 + audio_h.numel() * 4 + hm_h.numel() * 4
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        return train_step(cfg, model, opt, [video_d], audio_d, hm_d, lr=cfg.SOLVER.BASE_LR)
+
+    def e2e_step():
+        v = video_h.to(dev, non_blocking=True)
+        a = audio_h.to(dev, non_blocking=True)
+        h = hm_h.to(dev, non_blocking=True)
+        loss = train_step(cfg, model, opt, [v], a, h, lr=cfg.SOLVER.BASE_LR)
+        loss_h.copy_(loss.reshape(1), non_blocking=True)
+        return loss
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        evs = []
+        K.GEMM_PROFILE = [] if profile else None
+        _lib.launch_count(reset=True)
+        for _ in range(steps):
+            flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        barrier()
+        launches = _lib.launch_count()
+        prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches, prof
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches, prof = timed(resident_step, args.steps, profile=(rank == 0))
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e_step()
+    e2e_ms, _, _ = timed(e2e_step, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clips = B * world * args.steps
+    hbm_peak, tf_peak, peak_src = peaks()
+    tc = [(s.elapsed_time(e), fl) for s, e, fl, _, is_tc in prof if is_tc]
+    tc_ms, tc_flops = sum(t for t, _ in tc), sum(f for _, f in tc)
+    all_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in prof)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": clips / (total_ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}", "droppath": cfg.MVIT.DROPPATH_RATE,
+                   "l2": "192 MiB buffer rewritten before every timed step (activations per step also exceed L2)",
+                   "optimizer": "AdamW (torch fused) + clip_grad_norm_ 1.0"},
+        "e2e": {"value": clips / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "gemm_tc_kernel (tcgen05 Linear GEMMs, all shapes of the step)", "bound": "tensor",
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                     "peak_source": f"{peak_src} sustained bf16", "launches": len(tc), "kernel_ms_per_step": tc_ms / args.steps,
+                     "share_of_step": tc_ms / total_ms, "all_gemm_ms_per_step": all_ms / args.steps},
+    }
+    if args.cpu_baseline:
+        cps, cores, times = cpu_train_step_clips_per_s(2, 2, 1)
+        out["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
+                               "sample": "2 timed fwd+loss+bwd steps at batch 2 of the same workload (oracle port, fp32)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="csts_b200", choices=["csts_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus > 1:
+            args.cpu_baseline = False          # reported at N=1 only
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,8 +110,15 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.csts_launch_count.argtypes = [C.c_int]
+    lib.csts_launch_count.restype = C.c_longlong
     _lib = lib
     return lib
+
+
+def launch_count(reset=False) -> int:
+    """Kernels launched by libcsts_b200 since load / last reset."""
+    return int(load().csts_launch_count(1 if reset else 0))
 
 
 def last_error() -> str:

@@ -5,8 +5,11 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#include <atomic>
+
 namespace {
 thread_local char g_err[512] = {0};
+std::atomic<long long> g_launches{0};
 }
 
 void csts_set_error(const char* fmt, ...) {
@@ -22,6 +25,7 @@ int csts_check_launch(const char* what) {
     csts_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
     return 4;
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -38,6 +42,13 @@ int csts_num_sms() {
 extern "C" {
 
 int csts_version(void) { return 100; }
+
+// number of kernels this library has launched since load (or since the last reset)
+long long csts_launch_count(int reset) {
+  long long n = g_launches.load(std::memory_order_relaxed);
+  if (reset) g_launches.store(0, std::memory_order_relaxed);
+  return n;
+}
 
 // copies the calling thread's last error message; returns its length
 int csts_last_error(char* buf, int len) {

@@ -13,6 +13,9 @@ from ._lib import BF16, F32, GemmArgs, PoolArgs, WgradArgs, call, dt, ptr
 _FORCE_BACKEND = 0   # 0 auto, 1 mma.sync, 2 tcgen05 (tests flip this to cross-check the two GEMMs)
 
 
+GEMM_PROFILE = None   # when a list: every gemm() appends (start_event, end_event, flops, bytes, used_tcgen05)
+
+
 def set_gemm_backend(code: int):
     global _FORCE_BACKEND
     _FORCE_BACKEND = int(code)
@@ -63,6 +66,15 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
         assert bias.dtype == torch.float32
     if residual is not None:
         assert residual.dtype == torch.float32
+    if GEMM_PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = batch[0] * batch[1]
+        ev0.record()
+        call("csts_gemm", C.byref(a))
+        ev1.record()
+        tc = a.backend != 1 and a_kmajor and b_kmajor and nb == 1 and split_k <= 1 and M >= 64 and (N % 96 == 0 or N % 128 == 0)
+        GEMM_PROFILE.append((ev0, ev1, 2.0 * M * N * K * nb, nb * (2.0 * (M * K + N * K) + out.element_size() * M * N), tc))
+        return out
     call("csts_gemm", C.byref(a))
     return out
 
