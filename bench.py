@@ -132,7 +132,7 @@ def run_gpu(args):
     import csts_oracle as O
     from csts_b200 import _lib, kernels as K
     from csts_b200.host.build import build_model
-    from csts_b200.host.train_step import construct_optimizer, train_step
+    from csts_b200.host.train_step import GraphedTrainStep, construct_optimizer, train_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -146,7 +146,8 @@ def run_gpu(args):
     torch.manual_seed(cfg.RNG_SEED)
     model = build_model(cfg)
     model.train()
-    opt = construct_optimizer(model, cfg)
+    use_graph = args.graph and world == 1
+    opt = construct_optimizer(model, cfg, capturable=use_graph)
     B = BATCH_PER_GPU
     # host batch in pinned memory (the public-API path) and a resident device copy
     video_h, audio_h, hm_h = O.synthetic_batch(B, seed=100 + rank)
@@ -161,16 +162,32 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = GraphedTrainStep(cfg, model, opt, video_d, audio_d, hm_d) if use_graph else None
+    launches_per_step = None
+    if graphed is not None:
+        # launch count of one step, taken from an eager (un-captured) step: a graph replay launches the same kernels
+        _lib.launch_count(reset=True)
+        train_step(cfg, model, opt, [video_d], audio_d, hm_d)
+        launches_per_step = _lib.launch_count()
+
     def resident_step():
+        if graphed is not None:
+            return graphed(None, None, None)            # inputs already resident in the static buffers
         return train_step(cfg, model, opt, [video_d], audio_d, hm_d, lr=cfg.SOLVER.BASE_LR)
 
     def e2e_step():
-        v = video_h.to(dev, non_blocking=True)
-        a = audio_h.to(dev, non_blocking=True)
-        h = hm_h.to(dev, non_blocking=True)
-        loss = train_step(cfg, model, opt, [v], a, h, lr=cfg.SOLVER.BASE_LR)
+        if graphed is not None:
+            loss = graphed([video_h], audio_h, hm_h)     # H2D from pinned host memory, then replay
+        else:
+            v = video_h.to(dev, non_blocking=True)
+            a = audio_h.to(dev, non_blocking=True)
+            h = hm_h.to(dev, non_blocking=True)
+            loss = train_step(cfg, model, opt, [v], a, h, lr=cfg.SOLVER.BASE_LR)
         loss_h.copy_(loss.reshape(1), non_blocking=True)
         return loss
+
+    def eager_profile_step():
+        return train_step(cfg, model, opt, [video_d], audio_d, hm_d)
 
     def timed(fn, steps, profile=False):
         barrier()
@@ -198,8 +215,12 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms, launches, prof = timed(resident_step, args.steps, profile=(rank == 0))
+    total_ms, launches, prof = timed(resident_step, args.steps, profile=(rank == 0 and graphed is None))
     clocks = sampler.stop() if rank == 0 else None
+    if graphed is not None:
+        launches = launches_per_step * args.steps
+        # per-kernel CUDA-event timing needs un-captured launches: same kernels, eager, right after the timed region
+        _, _, prof = timed(eager_profile_step, args.steps, profile=(rank == 0))
     for _ in range(2):
         e2e_step()
     e2e_ms, _, _ = timed(e2e_step, args.steps)
@@ -220,7 +241,7 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}", "droppath": cfg.MVIT.DROPPATH_RATE,
                    "l2": "192 MiB buffer rewritten before every timed step (activations per step also exceed L2)",
-                   "optimizer": "AdamW (torch fused) + clip_grad_norm_ 1.0"},
+                   "optimizer": "AdamW (torch fused) + clip_grad_norm_ 1.0", "cuda_graph": graphed is not None},
         "e2e": {"value": clips / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
@@ -228,7 +249,8 @@ def run_gpu(args):
         "roofline": {"kernel": "gemm_tc_kernel (tcgen05 Linear GEMMs, all shapes of the step)", "bound": "tensor",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
                      "peak_source": f"{peak_src} sustained bf16", "launches": len(tc), "kernel_ms_per_step": tc_ms / args.steps,
-                     "share_of_step": tc_ms / total_ms, "all_gemm_ms_per_step": all_ms / args.steps},
+                     "share_of_step": tc_ms / total_ms, "all_gemm_ms_per_step": all_ms / args.steps,
+                     "timing": "CUDA events around every launch" + (" (eager replay of the same step; the timed region itself is one CUDA-graph launch per step)" if graphed is not None else "")},
     }
     if args.cpu_baseline:
         cps, cores, times = cpu_train_step_clips_per_s(2, 2, 1)
@@ -246,6 +268,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="csts_b200", choices=["csts_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

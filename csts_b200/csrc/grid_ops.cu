@@ -15,8 +15,25 @@ namespace {
 // One warp per output position; lane owns channels [4*lane, 4*lane+4) and, for d = 192, also
 // [128 + 4*lane, ...).  Weights live in shared memory as [tap][d].
 // ------------------------------------------------------------------------------------------------
+// Tap geometry for one output coordinate along one axis: which of the 3 taps are in range and the
+// input coordinate each one reads.  Strides are powers of two (1,2,4,8,16): shifts, no division.
+template <bool TRANSPOSED>
+__device__ __forceinline__ void tap_coords(int o, int shift, int n_in, int (&idx)[3], bool (&ok)[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (TRANSPOSED) {
+      int num = o + 1 - k;
+      idx[k] = num >> shift;
+      ok[k] = num >= 0 && (num & ((1 << shift) - 1)) == 0 && idx[k] < n_in;
+    } else {
+      idx[k] = (o << shift) + k - 1;
+      ok[k] = idx[k] >= 0 && idx[k] < n_in;
+    }
+  }
+}
+
 template <int D, bool TRANSPOSED, bool NORM>
-__global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p) {
+__global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, int lh, int lw) {
   constexpr int NJ = (D + 127) / 128;
   __shared__ float s_w[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
@@ -43,26 +60,22 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p) {
     for (int j = 0; j < NJ; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-
+    int ti[3], hi[3], wi[3];
+    bool vt[3], vh[3], vw[3];
+    tap_coords<TRANSPOSED>(to, lt, p.Ti, ti, vt);
+    tap_coords<TRANSPOSED>(ho, lh, p.Hi, hi, vh);
+    tap_coords<TRANSPOSED>(wo, lw, p.Wi, wi, vw);
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
-      int ti;
-      if (TRANSPOSED) { int num = to + 1 - kt; if (num < 0 || num % p.st) continue; ti = num / p.st; }
-      else ti = to * p.st + kt - 1;
-      if (ti < 0 || ti >= p.Ti) continue;
+      if (!vt[kt]) continue;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        int hi;
-        if (TRANSPOSED) { int num = ho + 1 - kh; if (num < 0 || num % p.sh) continue; hi = num / p.sh; }
-        else hi = ho * p.sh + kh - 1;
-        if (hi < 0 || hi >= p.Hi) continue;
+        if (!vh[kh]) continue;
+        const bf16* row = in_bh + (int64_t)((ti[kt] * p.Hi + hi[kh]) * p.Wi) * p.in_sP;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          int wi;
-          if (TRANSPOSED) { int num = wo + 1 - kw; if (num < 0 || num % p.sw) continue; wi = num / p.sw; }
-          else wi = wo * p.sw + kw - 1;
-          if (wi < 0 || wi >= p.Wi) continue;
-          const bf16* src = in_bh + (int64_t)((ti * p.Hi + hi) * p.Wi + wi) * p.in_sP;
+          if (!vw[kw]) continue;
+          const bf16* src = row + (int64_t)wi[kw] * p.in_sP;
           const float* wt = s_w + ((kt * 3 + kh) * 3 + kw) * D;
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
@@ -131,61 +144,52 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p) {
 // Depthwise weight gradient:  dw[c][tap] += sum_{b,head,o} small[o][c] * big[o*s + tap - 1][c]
 // (conv: small = d(conv out), big = conv in;  transposed conv: small = conv in, big = d(out)).
 // ------------------------------------------------------------------------------------------------
+// Block = 9 warps; warp w owns the taps (kt, kh) = (w / 3, w % 3) x kw in {0,1,2}, so no cross-warp
+// reduction is needed and each lane carries only 3 x 4 accumulators per channel group (high
+// occupancy, 4 positions in flight).  Every block walks a contiguous range of `small` positions.
 template <int D>
-__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(csts_wgrad_args p) {
+__global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, int lt, int lh, int lw, int pos_per_block) {
   constexpr int NJ = (D + 127) / 128;
-  __shared__ float s_dw[27 * D];
-  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) s_dw[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kt = warp / 3, kh = warp % 3;
   const int Ls = p.Ts * p.Hs * p.Ws;
   const int64_t total = (int64_t)p.B * p.heads * Ls;
   const bf16* small = reinterpret_cast<const bf16*>(p.small);
   const bf16* big = reinterpret_cast<const bf16*>(p.big);
-  float acc[NJ][27][4];
+  float acc[NJ][3][4];
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
 #pragma unroll
-    for (int t = 0; t < 27; ++t)
+    for (int t = 0; t < 3; ++t)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][t][i] = 0.f;
-
-  for (int64_t idx = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); idx < total; idx += (int64_t)gridDim.x * wpb) {
+  const int64_t beg = (int64_t)blockIdx.x * pos_per_block;
+  const int64_t end = beg + pos_per_block < total ? beg + pos_per_block : total;
+#pragma unroll 2
+  for (int64_t idx = beg; idx < end; ++idx) {
     int o = (int)(idx % Ls);
     int bh = (int)(idx / Ls);
     int hd = bh % p.heads, b = bh / p.heads;
     int wo = o % p.Ws, ho = (o / p.Ws) % p.Hs, to = o / (p.Ws * p.Hs);
+    int ti = (to << lt) + kt - 1, hi = (ho << lh) + kh - 1;
+    if (ti < 0 || ti >= p.Tb || hi < 0 || hi >= p.Hb) continue;      // warp-uniform
     const bf16* sp = small + b * p.small_sB + hd * p.small_sH + (int64_t)o * p.small_sP;
-    const bf16* big_bh = big + b * p.big_sB + hd * p.big_sH;
-    float sv[NJ][4];
+    const bf16* row = big + b * p.big_sB + hd * p.big_sH + (int64_t)((ti * p.Hb + hi) * p.Wb) * p.big_sP;
+    const int w0 = (wo << lw) - 1;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       int c = 4 * lane + 128 * j;
-      if (c < D) ld4(sp + c, sv[j]);
-    }
-#pragma unroll
-    for (int kt = 0; kt < 3; ++kt) {
-      int ti = to * p.st + kt - 1;
-      if (ti < 0 || ti >= p.Tb) continue;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        int hi = ho * p.sh + kh - 1;
-        if (hi < 0 || hi >= p.Hb) continue;
+      if (c < D) {
+        float sv[4];
+        ld4(sp + c, sv);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          int wi = wo * p.sw + kw - 1;
-          if (wi < 0 || wi >= p.Wb) continue;
-          const bf16* bp = big_bh + (int64_t)((ti * p.Hb + hi) * p.Wb + wi) * p.big_sP;
+          int wi = w0 + kw;
+          if (wi >= 0 && wi < p.Wb) {
+            float v[4];
+            ld4(row + (int64_t)wi * p.big_sP + c, v);
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            int c = 4 * lane + 128 * j;
-            if (c < D) {
-              float v[4];
-              ld4(bp + c, v);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) acc[j][(kt * 3 + kh) * 3 + kw][i] = fmaf(v[i], sv[j][i], acc[j][(kt * 3 + kh) * 3 + kw][i]);
-            }
+            for (int i = 0; i < 4; ++i) acc[j][kw][i] = fmaf(v[i], sv[i], acc[j][kw][i]);
           }
         }
       }
@@ -196,15 +200,10 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(csts_wgrad_args p) {
     int c = 4 * lane + 128 * j;
     if (c < D) {
 #pragma unroll
-      for (int t = 0; t < 27; ++t)
+      for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[t * D + c + i], acc[j][t][i]);
+        for (int i = 0; i < 4; ++i) atomicAdd(p.dw + (c + i) * 27 + (kt * 3 + kh) * 3 + kw, acc[j][kw][i]);
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
-    int tap = i / D, c = i - tap * D;
-    atomicAdd(p.dw + c * 27 + tap, s_dw[i]);
   }
 }
 
@@ -390,17 +389,25 @@ int grid_for(int64_t work_items, int per_block) {
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+int log2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
 template <int D>
 int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   int64_t total = (int64_t)p.B * p.heads * p.To * p.Ho * p.Wo;
   int grid = grid_for(total, 8);
   bool norm = p.gamma != nullptr;
+  int lt = log2_exact(p.st), lh = log2_exact(p.sh), lw = log2_exact(p.sw);
+  CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv: strides must be powers of two (%d,%d,%d)", p.st, p.sh, p.sw);
   if (p.transposed) {
-    if (norm) dwconv_kernel<D, true, true><<<grid, 256, 0, st>>>(p);
-    else dwconv_kernel<D, true, false><<<grid, 256, 0, st>>>(p);
+    if (norm) dwconv_kernel<D, true, true><<<grid, 256, 0, st>>>(p, lt, lh, lw);
+    else dwconv_kernel<D, true, false><<<grid, 256, 0, st>>>(p, lt, lh, lw);
   } else {
-    if (norm) dwconv_kernel<D, false, true><<<grid, 256, 0, st>>>(p);
-    else dwconv_kernel<D, false, false><<<grid, 256, 0, st>>>(p);
+    if (norm) dwconv_kernel<D, false, true><<<grid, 256, 0, st>>>(p, lt, lh, lw);
+    else dwconv_kernel<D, false, false><<<grid, 256, 0, st>>>(p, lt, lh, lw);
   }
   return csts_check_launch("dwconv");
 }
@@ -423,11 +430,14 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   CSTS_REQUIRE(p->d == 96 || p->d == 192, "dwconv_wgrad: head_dim %d unsupported", p->d);
   int64_t total = (int64_t)p->B * p->heads * p->Ts * p->Hs * p->Ws;
   if (total == 0) return 0;
-  // few, long-running blocks: every block ends with 27*d global atomics
-  int64_t blocks = (total + 255) / 256;
-  int grid = (int)(blocks < csts_num_sms() * 2 ? blocks : csts_num_sms() * 2);
-  if (p->d == 96) dwconv_wgrad_kernel<96><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
-  else dwconv_wgrad_kernel<192><<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+  int lt = log2_exact(p->st), lh = log2_exact(p->sh), lw = log2_exact(p->sw);
+  CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv_wgrad: strides must be powers of two");
+  // every block ends with 27*d global atomics: cap the grid at 2 blocks per SM, >= 32 positions each
+  int64_t want = (total + 31) / 32;
+  int grid = (int)(want < csts_num_sms() * 2 ? want : csts_num_sms() * 2);
+  int pos_per_block = (int)((total + grid - 1) / grid);
+  if (p->d == 96) dwconv_wgrad_kernel<96><<<grid, 288, 0, (cudaStream_t)stream>>>(*p, lt, lh, lw, pos_per_block);
+  else dwconv_wgrad_kernel<192><<<grid, 288, 0, (cudaStream_t)stream>>>(*p, lt, lh, lw, pos_per_block);
   return csts_check_launch("dwconv_wgrad");
 }
 

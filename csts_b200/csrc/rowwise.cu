@@ -261,23 +261,37 @@ __global__ void scale_kernel(const float* __restrict__ a, const float* __restric
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] * s;
 }
 
-// column sums: out[n] += sum_m X[m][n]   (bias gradients)
+// column sums: out[n] += sum_m X[m][n]   (bias gradients).  Block = 32 column-quads x 8 row phases.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, float* __restrict__ out, int64_t M, int N, int64_t ld,
                                                      int rows_per_block) {
-  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (col >= N) return;
+  __shared__ float red[8][128];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 4;
   int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t r = r0; r < r1; ++r) {
-    float v[4];
-    ld4(X + r * ld + col, v);
+  if (col < N) {
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v[4];
+      ld4(X + r * ld + col, v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] += v[i];
+      for (int i = 0; i < 4; ++i) acc[i] += v[i];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) atomicAdd(out + col + i, acc[i]);
+  for (int i = 0; i < 4; ++i) red[ty][tx * 4 + i] = acc[i];
+  __syncthreads();
+  if (ty == 0 && col < N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][tx * 4 + i];
+      atomicAdd(out + col + i, t);
+    }
+  }
 }
 
 int grid_for(int64_t work_items, int per_block) {
@@ -313,8 +327,8 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
   CSTS_REQUIRE(width % 4 == 0 && width <= 128 * LN_MAXJ, "layernorm_bwd: width %d unsupported", width);
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = (rows + 63) / 64;       // >= 8 rows per warp so the column atomics amortise
-  int grid = (int)(blocks < csts_num_sms() * 4 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 4);
+  int64_t blocks = (rows + 31) / 32;       // >= 4 rows per warp so the column atomics amortise
+  int grid = (int)(blocks < csts_num_sms() * 8 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 8);
 #define LN_BWD(TX, TDY, TDX) \
   layernorm_bwd_kernel<TX, TDY, TDX><<<grid, 256, 0, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
   if (x_dtype == 0 && dy_dtype == 1 && dx_dtype == 0) LN_BWD(float, bf16, float);
@@ -381,14 +395,14 @@ int csts_scale_f32(const float* a, const float* device_scalar, float* out, int64
 int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_t ld, void* stream) {
   if (M == 0 || N == 0) return 0;
   CSTS_REQUIRE(N % 4 == 0 && ld % 4 == 0, "colsum: N and ld must be multiples of 4");
-  int bx = ceil_div(N / 4, 64);
+  int bx = ceil_div(N, 128);
   int want_y = csts_num_sms() * 4 / bx;
   if (want_y < 1) want_y = 1;
   int rows_per_block = (int)((M + want_y - 1) / want_y);
-  if (rows_per_block < 32) rows_per_block = 32;
+  if (rows_per_block < 64) rows_per_block = 64;
   dim3 grid(bx, ceil_div(M, rows_per_block));
-  if (x_dtype == 0) colsum_kernel<float><<<grid, 64, 0, (cudaStream_t)stream>>>((const float*)X, out, M, N, ld, rows_per_block);
-  else colsum_kernel<bf16><<<grid, 64, 0, (cudaStream_t)stream>>>((const bf16*)X, out, M, N, ld, rows_per_block);
+  if (x_dtype == 0) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, out, M, N, ld, rows_per_block);
+  else colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)X, out, M, N, ld, rows_per_block);
   return csts_check_launch("colsum");
 }
 

@@ -154,8 +154,16 @@ def block_backward(spec, p, wc, sv, dy):
     dev = x.device
     g = {}
 
+    # one memset for every accumulate-into gradient buffer of the block (norm affine, biases, pool kernels)
+    n_pool = 3 if spec.stride_q is not None and spec.stride_kv is not None else (2 if spec.stride_kv is not None else
+                                                                               (1 if spec.stride_q is not None else 0))
+    zbuf = torch.zeros(4 * C + 3 * C + C + hid + 2 * Co + n_pool * 29 * d + 64, dtype=torch.float32, device=dev)
+    zoff = [0]
+
     def zeros(n):
-        return torch.zeros(n, dtype=torch.float32, device=dev)
+        lo = zoff[0]
+        zoff[0] = lo + (n + 3) // 4 * 4          # keep 16-byte alignment for the vectorised kernels
+        return zbuf[lo: lo + n]
 
     def wgrad(a_rows, b_rows, m_out, n_out, ktok):
         # dW[m_out, n_out] = a_rows^T . b_rows   (both token-major: contraction over rows)
@@ -167,17 +175,17 @@ def block_backward(spec, p, wc, sv, dy):
     # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
     dZ = K.gemm(g2, wc.wt(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, act=2, Z=sv["Z"])
     g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq)
-    g["mlp.fc2.bias"] = K.colsum(g2, Mq, Co)
+    g["mlp.fc2.bias"] = K.colsum(g2, Mq, Co, out=zeros(Co))
     dxn2 = K.gemm(dZ, wc.wt(p["mlp.fc1.weight"]), M=Mq, N=C, K=hid)
     g["mlp.fc1.weight"] = wgrad(dZ, sv["xn2"], hid, C, Mq)
-    g["mlp.fc1.bias"] = K.colsum(dZ, Mq, hid)
+    g["mlp.fc1.bias"] = K.colsum(dZ, Mq, hid, out=zeros(hid))
     del dZ
     g["norm2.weight"], g["norm2.bias"] = zeros(C), zeros(C)
     if spec.dim != spec.dim_out:
         gp = g2 if dp is None else K.cast_bf16(dy)                       # the re-based residual is not drop-path scaled
         K.gemm(gp, wc.wt(p["proj.weight"]), M=Mq, N=C, K=Co, out=dxn2, accumulate=True)
         g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq)
-        g["proj.bias"] = K.colsum(dy, Mq, Co)
+        g["proj.bias"] = K.colsum(dy, Mq, Co, out=zeros(Co))
         dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"])
     else:
         dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
@@ -187,7 +195,7 @@ def block_backward(spec, p, wc, sv, dy):
     g1 = K.cast_bf16(dx1, row_scale=dp, rows_per_scale=rps)
     do = K.gemm(g1, wc.wt(p["attn.proj.weight"]), M=Mq, N=C, K=C)       # (B, Lq, heads, d)
     g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq)
-    g["attn.proj.bias"] = K.colsum(g1, Mq, C)
+    g["attn.proj.bias"] = K.colsum(g1, Mq, C, out=zeros(C))
     del g1
     # ---- residual path -----------------------------------------------------------------------------------
     if spec.stride_q is None or spec.kind in ("spatial", "temporal"):
@@ -233,7 +241,7 @@ def block_backward(spec, p, wc, sv, dy):
         # data gradient: the adjoint gather of the forward conv, written straight into the qkv-gradient slice
         K.dwconv(du, dense, 0, B, h, d, grid_out, stride, p[wname], transposed=not transposed, out=dqkv, out_strides=qs,
                  out_off=slot * C, thw_out=thw)
-        dw = torch.zeros_like(p[wname])
+        dw = zeros(27 * d).view_as(p[wname])
         if transposed:
             K.dwconv_wgrad(sv["qkv"], qs, slot * C, thw, du, dense, 0, grid_out, B, h, d, stride, dw)
         else:
@@ -249,7 +257,7 @@ def block_backward(spec, p, wc, sv, dy):
     # ---- qkv projection and norm1 ---------------------------------------------------------------------------
     dxn1 = K.gemm(dqkv, wc.wt(p["attn.qkv.weight"]), M=M, N=C, K=3 * C)
     g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M)
-    g["attn.qkv.bias"] = K.colsum(dqkv, M, 3 * C)
+    g["attn.qkv.bias"] = K.colsum(dqkv, M, 3 * C, out=zeros(3 * C))
     g["norm1.weight"], g["norm1.bias"] = zeros(C), zeros(C)
     dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
                          add=dx_skip.view(B, N, C))

@@ -10,7 +10,7 @@ from . import losses
 from .utils import frame_softmax, sim_matrix
 
 
-def construct_optimizer(model, cfg):
+def construct_optimizer(model, cfg, capturable=False):
     """Parameter grouping of slowfast/models/optimizer.py:11-108 for the AdamW case: weight decay on
     matrices / conv kernels / position embeddings, zero weight decay on 1-D parameters and biases
     (SOLVER.ZERO_WD_1D_PARAM) and on model.no_weight_decay()."""
@@ -31,7 +31,10 @@ def construct_optimizer(model, cfg):
                           {"params": no_decay, "weight_decay": 0.0}) if g["params"]]
     if cfg.SOLVER.OPTIMIZING_METHOD != "adamw":
         raise NotImplementedError("the CSTS configs train with AdamW")
-    return torch.optim.AdamW(groups, lr=cfg.SOLVER.BASE_LR, eps=1e-08, weight_decay=cfg.SOLVER.WEIGHT_DECAY, fused=True)
+    lr = cfg.SOLVER.BASE_LR
+    if capturable:      # CUDA-graph replay: the learning rate must live on the device
+        lr = torch.tensor(float(lr), dtype=torch.float32, device=decay[0].device)
+    return torch.optim.AdamW(groups, lr=lr, eps=1e-08, weight_decay=cfg.SOLVER.WEIGHT_DECAY, fused=True, capturable=capturable)
 
 
 def compute_loss(cfg, model, inputs, audio_frames, labels_hm):
@@ -57,7 +60,10 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None):
     """Forward, loss, backward, clip, optimizer step.  Returns the (device) loss tensor; no host sync."""
     if lr is not None:
         for group in optimizer.param_groups:
-            group["lr"] = lr
+            if torch.is_tensor(group["lr"]):
+                group["lr"].fill_(lr)
+            else:
+                group["lr"] = lr
     loss, _, _, _ = compute_loss(cfg, model, inputs, audio_frames, labels_hm)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
@@ -65,3 +71,49 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None):
         torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM, foreach=True)
     optimizer.step()
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """The whole training step (weight casts, forward, loss, backward, clip, AdamW) captured once into
+    a CUDA graph and replayed: ~1100 kernel launches per step cost one graph launch on the host.
+
+    All shapes of the path are static (fixed clip geometry, fixed batch), which is what makes the
+    capture legal.  Inputs are copied into static device buffers before each replay, so the caller
+    keeps passing ordinary (host or device) tensors.  The optimizer must be constructed with
+    ``construct_optimizer(model, cfg, capturable=True)``.
+    """
+
+    def __init__(self, cfg, model, optimizer, video, audio, labels_hm, warmup=3):
+        inner = model.module if hasattr(model, "module") else model
+        dev = next(inner.parameters()).device
+        self.cfg, self.model, self.optimizer = cfg, model, optimizer
+        self.video = torch.empty(video.shape, dtype=torch.float32, device=dev)
+        self.audio = torch.empty(audio.shape, dtype=torch.float32, device=dev)
+        self.labels = torch.empty(labels_hm.shape, dtype=torch.float32, device=dev)
+        self._load(video, audio, labels_hm)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):              # eager warm-up: lazy inits (func attributes, optimizer state, NCCL)
+                train_step(cfg, model, optimizer, [self.video], self.audio, self.labels)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        inner._wc.clear()                        # the bf16 weight casts must be part of the captured step
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = train_step(cfg, model, optimizer, [self.video], self.audio, self.labels)
+
+    def _load(self, video, audio, labels_hm):
+        self.video.copy_(video[0] if isinstance(video, (list, tuple)) else video, non_blocking=True)
+        self.audio.copy_(audio, non_blocking=True)
+        self.labels.copy_(labels_hm, non_blocking=True)
+
+    def __call__(self, inputs, audio_frames, labels_hm, lr=None):
+        if lr is not None:
+            for group in self.optimizer.param_groups:
+                group["lr"].fill_(lr)
+        if inputs is not None:
+            self._load(inputs, audio_frames, labels_hm)
+        self.graph.replay()
+        return self.loss
