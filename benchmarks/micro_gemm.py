@@ -16,40 +16,52 @@ SHAPES = [  # (M tokens at B=8, K, N)
 ]
 
 
-def timeit(fn, flush, iters=10):
-    for _ in range(3):
+def timeit(make_launch, sets, reps=4):
+    """GPU time per launch with no host overhead and a cold L2: `sets` operand sets (together larger than
+    L2) are cycled, the whole sequence is captured into a CUDA graph and replayed between two events."""
+    launches = [make_launch(i) for i in range(sets)]
+    for fn in launches:
         fn()
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        fn()
-        e.record()
-        torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e))
-    ts.sort()
-    return ts[len(ts) // 2]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            for fn in launches:
+                fn()
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / (reps * sets)
 
 
 def main():
     dev = "cuda"
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     rows = []
     for M, Kd, N in SHAPES:
-        A = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
-        B = (torch.randn(N, Kd, device=dev) * 0.05).to(torch.bfloat16)
-        bias = torch.randn(N, device=dev)
-        out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
-        t_tc = timeit(lambda: K.gemm(A, B, M=M, N=N, K=Kd, bias=bias, out=out, backend=2), flush)
-        t_mma = timeit(lambda: K.gemm(A, B, M=M, N=N, K=Kd, bias=bias, out=out, backend=1), flush)
-        t_lib = timeit(lambda: torch.addmm(bias.to(torch.bfloat16), A, B.t(), out=out), flush)
-        flops = 2.0 * M * N * Kd
         byts = 2.0 * (M * Kd + N * Kd + M * N)
-        rows.append(dict(M=M, K=Kd, N=N, tc_ms=t_tc, mma_ms=t_mma, cublas_ms=t_lib, tc_tflops=flops / t_tc / 1e9,
-                         tc_gbs=byts / t_tc / 1e6, cublas_tflops=flops / t_lib / 1e9))
-        print(json.dumps(rows[-1]))
+        sets = max(2, int(300e6 // byts) + 1)
+        As = [torch.randn(M, Kd, device=dev).to(torch.bfloat16) for _ in range(sets)]
+        Bs = [(torch.randn(N, Kd, device=dev) * 0.05).to(torch.bfloat16) for _ in range(sets)]
+        outs = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(sets)]
+        bias = torch.randn(N, device=dev)
+        bias16 = bias.to(torch.bfloat16)
+        t_tc = timeit(lambda i: (lambda: K.gemm(As[i], Bs[i], M=M, N=N, K=Kd, bias=bias, out=outs[i], backend=2)), sets)
+        t_mma = timeit(lambda i: (lambda: K.gemm(As[i], Bs[i], M=M, N=N, K=Kd, bias=bias, out=outs[i], backend=1)), sets)
+        t_lib = timeit(lambda i: (lambda: torch.addmm(bias16, As[i], Bs[i].t(), out=outs[i])), sets)
+        # weight-gradient layout: dW[N, Kd] = dY[M, N]^T . X[M, Kd] (contraction over the M tokens)
+        dW = torch.empty(N, Kd, dtype=torch.float32, device=dev)
+        split = max(1, min(296 // (((N + 127) // 128) * ((Kd + 127) // 128)), M // 512))
+        t_wg = timeit(lambda i: (lambda: K.gemm(outs[i], As[i], M=N, N=Kd, K=M, a_kmajor=False, b_kmajor=False, out=dW, split_k=split,
+                                                 backend=2)), sets)
+        flops = 2.0 * M * N * Kd
+        rows.append(dict(M=M, K=Kd, N=N, tc_us=1e3 * t_tc, mma_us=1e3 * t_mma, cublas_us=1e3 * t_lib, wgrad_tc_us=1e3 * t_wg,
+                         tc_tflops=flops / t_tc / 1e9, tc_gbs=byts / t_tc / 1e6, cublas_tflops=flops / t_lib / 1e9,
+                         wgrad_tflops=flops / t_wg / 1e9, hbm_floor_us=byts / 6.5558e6, tensor_floor_us=flops / 1402e6))
+        print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in rows[-1].items()}), flush=True)
     return rows
 
 

