@@ -110,6 +110,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.csts_gemm_backend.argtypes = [C.POINTER(GemmArgs)]
+    lib.csts_gemm_backend.restype = C.c_int
     lib.csts_launch_count.argtypes = [C.c_int]
     lib.csts_launch_count.restype = C.c_longlong
     _lib = lib

@@ -69,6 +69,13 @@ int csts_check_device(void) {
   return 0;
 }
 
+// which kernel csts_gemm would run for this problem: 2 = tcgen05, 1 = mma.sync
+int csts_gemm_backend(const csts_gemm_args* a) {
+  if (a->backend == 1) return 1;
+  if (a->backend == 2) return 2;
+  return csts_gemm_tc_supported(*a) ? 2 : 1;
+}
+
 int csts_gemm(const csts_gemm_args* a, void* stream) {
   CSTS_REQUIRE(a != nullptr, "gemm: null argument block");
   cudaStream_t st = (cudaStream_t)stream;

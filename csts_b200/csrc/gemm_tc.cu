@@ -19,6 +19,8 @@
 // K / M / N tails are handled by TMA out-of-bounds zero fill and row/column predicates.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm.h"
 
@@ -56,10 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+// operands are described as rank-4 tensors (inner, rows, batch2, batch1); unbatched problems use 1 x 1
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -129,9 +132,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_
 struct TcParams {
   void* C; void* Z; const float* bias; const float* residual; const float* row_scale;
   int64_t ldc, ldz, ldr;
+  int64_t sC1, sC2;                 // batch strides of C (elements)
   int M, N, K;
   int c_dtype, act, accumulate, res_mod, rows_per_scale;
   int splits, kblocks_per_split;
+  int batch, batch2;                // batch = batch1 * batch2; z -> (z / batch2, z % batch2)
   float alpha;
 };
 
@@ -215,13 +220,13 @@ __device__ __forceinline__ void pack_slice(unsigned char* stage, int lane, int h
 
 // bf16 output, one unit = 64 columns (two TMEM slices -> one full 128-byte staging row per lane)
 template <int EPI>
-__device__ __forceinline__ void epilogue_unit_bf16(const TcParams& p, unsigned char* stage, const float* sbias, int m0, int n0,
-                                                   int cols_in_tile, int lane, uint32_t taddr, float rs) {
+__device__ __forceinline__ void epilogue_unit_bf16(const TcParams& p, int64_t coff, unsigned char* stage, const float* sbias, int m0,
+                                                   int n0, int cols_in_tile, int lane, uint32_t taddr, float rs) {
   const int rows_valid = min(32, p.M - m0);
   const int cols_valid = min(min(64, cols_in_tile), p.N - n0);
   const bool two = cols_valid > 32;
   const bool use_bias = p.bias != nullptr;
-  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.C) + (int64_t)m0 * p.ldc + n0);
+  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.C) + coff + (int64_t)m0 * p.ldc + n0);
   unsigned char* zg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.Z) + (int64_t)m0 * p.ldz + n0);
   float v0[32], v1[32];
   load_slice(p, taddr, sbias, use_bias, v0);
@@ -276,11 +281,11 @@ __device__ __forceinline__ void epilogue_unit_bf16(const TcParams& p, unsigned c
 
 // f32 output, one unit = 32 columns (128-byte staging rows)
 template <int EPI>
-__device__ __forceinline__ void epilogue_unit_f32(const TcParams& p, unsigned char* stage, const float* sbias, int m0, int n0,
-                                                  int cols_in_tile, int lane, uint32_t taddr, float rs, bool first_split) {
+__device__ __forceinline__ void epilogue_unit_f32(const TcParams& p, int64_t coff, unsigned char* stage, const float* sbias, int m0,
+                                                  int n0, int cols_in_tile, int lane, uint32_t taddr, float rs, bool first_split) {
   const int rows_valid = min(32, p.M - m0);
   const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
-  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(p.C) + (int64_t)m0 * p.ldc + n0);
+  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(p.C) + coff + (int64_t)m0 * p.ldc + n0);
   // issue the residual / old-C tile read first: its latency overlaps the TMEM load
   const bool has_res = p.residual != nullptr && first_split;
   const bool has_acc = EPI == EPI_F32 && p.accumulate;
@@ -344,7 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int num_items = tiles_m * tiles_n * p.splits;
+  const int num_items = tiles_m * tiles_n * p.splits * p.batch;
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -362,11 +367,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   // work item -> (tile_m, tile_n, split); consecutive items walk M first so that the B (weight)
   // tile stays hot in L2 across neighbouring CTAs
-  auto decode = [&](int item, int& tm, int& tn, int& kb0, int& kb1) {
+  auto decode = [&](int item, int& tm, int& tn, int& z, int& kb0, int& kb1) {
     int split = item % p.splits;
     int t = item / p.splits;
     tm = t % tiles_m;
-    tn = t / tiles_m;
+    t /= tiles_m;
+    tn = t % tiles_n;
+    z = t / tiles_n;
     kb0 = split * p.kblocks_per_split;
     kb1 = min(kblocks, kb0 + p.kblocks_per_split);
     return split;
@@ -377,8 +384,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tm, tn, kb0, kb1;
-        decode(item, tm, tn, kb0, kb1);
+        int tm, tn, z, kb0, kb1;
+        decode(item, tm, tn, z, kb0, kb1);
+        const int z1 = z / p.batch2, z2 = z % p.batch2;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           mbar_expect_tx(full0 + 8 * stage, C::A_BYTES + (B_MN ? C::B_BOXES * 8192 : BN * BK * 2));
@@ -386,15 +394,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t bar = full0 + 8 * stage;
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmap_a, bar, tm * BM + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tma_load_4d(a_dst + j * 8192, &tmap_a, bar, tm * BM + j * 64, kb * BK, z2, z1);
           } else {
-            tma_load_2d(a_dst, &tmap_a, bar, kb * BK, tm * BM);
+            tma_load_4d(a_dst, &tmap_a, bar, kb * BK, tm * BM, z2, z1);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < C::B_BOXES; ++j) tma_load_2d(b_dst + j * 8192, &tmap_b, bar, tn * BN + j * 64, kb * BK);
+            for (int j = 0; j < C::B_BOXES; ++j) tma_load_4d(b_dst + j * 8192, &tmap_b, bar, tn * BN + j * 64, kb * BK, z2, z1);
           } else {
-            tma_load_2d(b_dst, &tmap_b, bar, kb * BK, tn * BN);
+            tma_load_4d(b_dst, &tmap_b, bar, kb * BK, tn * BN, z2, z1);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -407,8 +415,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tm, tn, kb0, kb1;
-        decode(item, tm, tn, kb0, kb1);
+        int tm, tn, z, kb0, kb1;
+        decode(item, tm, tn, z, kb0, kb1);
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -441,8 +449,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int UNIT = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 32 : 64;
     int as = 0; uint32_t aphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int tm, tn, kb0, kb1;
-      const int split = decode(item, tm, tn, kb0, kb1);
+      int tm, tn, z, kb0, kb1;
+      const int split = decode(item, tm, tn, z, kb0, kb1);
+      const int64_t coff = (int64_t)(z / p.batch2) * p.sC1 + (int64_t)(z % p.batch2) * p.sC2;
       const int m0 = tm * BM + quad * 32;
       // bias slice of this tile -> the warp's shared-memory copy (latency hidden behind the accumulator wait)
       if (p.bias) {
@@ -460,8 +469,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c = half * UNIT; c < BN; c += 2 * UNIT) {
         const int n0 = tn * BN + c;
         if (!live || n0 >= p.N) continue;
-        if (UNIT == 64) epilogue_unit_bf16<EPI>(p, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs);
-        else epilogue_unit_f32<EPI>(p, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs, split == 0);
+        if (UNIT == 64) epilogue_unit_bf16<EPI>(p, coff, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs);
+        else epilogue_unit_f32<EPI>(p, coff, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs, split == 0);
       }
       tc_fence_before();
       __syncwarp();
@@ -494,18 +503,22 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor with row pitch ld elements; box = [box_rows, 64 cols], 128B swizzle
-int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// bf16 [batch1][batch2][rows][cols] tensor, row pitch ld, batch strides s1 / s2 (elements);
+// box = [1, 1, box_rows, 64 cols], 128B swizzle, out-of-bounds elements read as zero
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
+              int64_t s1, int64_t s2) {
   EncodeTiledFn fn = get_encode_fn();
   CSTS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch2, (cuuint64_t)batch1};
+  // a dimension of extent 1 still needs a legal (16-byte multiple) stride
+  cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch2 > 1 ? s2 * 2 : ld * 2), (cuuint64_t)(batch1 > 1 ? s1 * 2 : ld * 2)};
+  cuuint32_t box[4] = {64u, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CSTS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld ld=%ld", (int)r, (long)rows, (long)cols, (long)ld);
+  CSTS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld ld=%ld batch=%dx%d strides %ld %ld", (int)r,
+               (long)rows, (long)cols, (long)ld, batch1, batch2, (long)s1, (long)s2);
   return 0;
 }
 
@@ -520,14 +533,17 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   CUtensorMap ta, tb;
   // K-major operand X[mn][k]: tensor [mn rows, K cols], box [tile rows, 64 k].
   // MN-major operand X[k][mn]: tensor [K rows, mn cols], box [64 k rows, 64 mn].
-  int rc = A_MN ? make_tmap(&ta, a.A, a.K, a.M, a.lda, BK) : make_tmap(&ta, a.A, a.M, a.K, a.lda, BM);
+  int rc = A_MN ? make_tmap(&ta, a.A, a.K, a.M, a.lda, BK, a.batch1, a.batch2, a.sA1, a.sA2)
+                : make_tmap(&ta, a.A, a.M, a.K, a.lda, BM, a.batch1, a.batch2, a.sA1, a.sA2);
   if (rc) return rc;
-  rc = B_MN ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK) : make_tmap(&tb, a.B, a.N, a.K, a.ldb, BN);
+  rc = B_MN ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK, a.batch1, a.batch2, a.sB1, a.sB2)
+            : make_tmap(&tb, a.B, a.N, a.K, a.ldb, BN, a.batch1, a.batch2, a.sB1, a.sB2);
   if (rc) return rc;
   TcParams p;
   p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual;
   p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
   p.ldc = a.ldc; p.ldz = a.ldz; p.ldr = a.ldr;
+  p.sC1 = a.sC1; p.sC2 = a.sC2; p.batch = a.batch1 * a.batch2; p.batch2 = a.batch2;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.c_dtype = a.c_dtype; p.act = a.act; p.accumulate = a.accumulate; p.res_mod = a.res_mod; p.alpha = a.alpha;
   const int kblocks = ceil_div(a.K, BK);
@@ -535,31 +551,36 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   if (splits > kblocks) splits = kblocks;
   p.kblocks_per_split = ceil_div(kblocks, splits);
   p.splits = ceil_div(kblocks, p.kblocks_per_split);
-  if (p.splits > 1 && !a.accumulate)
+  if (p.splits > 1 && !a.accumulate) {
+    CSTS_REQUIRE(p.batch == 1, "gemm_tc: split-K without accumulate supports a single batch");
     CSTS_CUDA(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, (size_t)a.N * sizeof(float), a.M, stream));
-  int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits;
+  }
+  int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits * p.batch;
   int grid = items < csts_num_sms() ? items : csts_num_sms();
   gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   return csts_check_launch("gemm_tc_kernel");
 }
 
-int pick_bn(int M, int N, int splits) {
-  // widest tile that wastes no columns while still giving every SM work; fewer, fatter tiles otherwise
+int pick_bn(int M, int N, int work_mult) {
+  // least padded columns first; among equals the widest tile that still gives every SM work, else
+  // the narrowest (most CTAs)
   const int cands[4] = {256, 192, 128, 96};
   int sms = csts_num_sms();
+  int best_pad = 1 << 30;
+  for (int i = 0; i < 4; ++i) best_pad = std::min(best_pad, ceil_div(N, cands[i]) * cands[i]);
   for (int i = 0; i < 4; ++i) {
     int bn = cands[i];
-    if (N % bn) continue;
-    if (ceil_div(M, BM) * (N / bn) * splits >= sms) return bn;
+    if (ceil_div(N, bn) * bn != best_pad) continue;
+    if ((long)ceil_div(M, BM) * (best_pad / bn) * work_mult >= sms) return bn;
   }
   for (int i = 3; i >= 0; --i)
-    if (N % cands[i] == 0) return cands[i];
-  return 0;
+    if (ceil_div(N, cands[i]) * cands[i] == best_pad) return cands[i];
+  return 96;
 }
 
 template <bool A_MN, bool B_MN, int EPI>
 int dispatch(const csts_gemm_args& a, cudaStream_t stream) {
-  switch (pick_bn(a.M, a.N, a.split_k > 1 ? a.split_k : 1)) {
+  switch (pick_bn(a.M, a.N, (a.split_k > 1 ? a.split_k : 1) * a.batch1 * a.batch2)) {
     case 256: return launch<256, A_MN, B_MN, EPI>(a, stream);
     case 192: return launch<192, A_MN, B_MN, EPI>(a, stream);
     case 128: return launch<128, A_MN, B_MN, EPI>(a, stream);
@@ -579,23 +600,21 @@ int effective_splits(const csts_gemm_args& a) {
 }  // namespace
 
 bool csts_gemm_tc_supported(const csts_gemm_args& a) {
-  if (a.a_kmajor != a.b_kmajor) return false;          // mixed majorness: generic kernel
-  if (a.batch1 * a.batch2 != 1) return false;
-  if (a.N % 96 != 0 && a.N % 128 != 0) return false;
+  if (!a.a_kmajor && a.b_kmajor) return false;         // (MN-major A, K-major B) never occurs on the path
+  const int nb = a.batch1 * a.batch2;
   if (a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
-  if (a.a_kmajor && a.K % 8 != 0) return false;
-  if (!a.a_kmajor && (a.M % 8 != 0)) return false;
   if (((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
-  // coalesced epilogue: 16-byte aligned rows
-  int cbytes = a.c_dtype == 0 ? 4 : 2;
-  if (((uintptr_t)a.C & 15) || (a.ldc * cbytes) % 16) return false;
-  if (a.Z && (((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
-  if (a.residual && (((uintptr_t)a.residual & 15) || (a.ldr * 4) % 16)) return false;
+  if (nb > 1 && ((a.sA1 | a.sA2 | a.sB1 | a.sB2) % 8 != 0)) return false;
+  const int cbytes = a.c_dtype == 0 ? 4 : 2;
+  // coalesced epilogue: 16-byte aligned rows, whole 16-byte chunks
+  if (((uintptr_t)a.C & 15) || (a.ldc * cbytes) % 16 || ((int64_t)a.N * cbytes) % 16) return false;
+  if (nb > 1 && (((a.sC1 | a.sC2) * cbytes) % 16 != 0)) return false;
+  if (a.Z && (nb > 1 || ((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
+  if (a.residual && (nb > 1 || ((uintptr_t)a.residual & 15) || (a.ldr * 4) % 16)) return false;
   if (a.res_mod > 0 && a.res_mod % 32 != 0) return false;
-  if (a.bias && ((uintptr_t)a.bias & 15)) return false;
+  if (a.bias && (((uintptr_t)a.bias & 15) || a.N % 4 != 0)) return false;
   if (a.split_k > 1 && (a.c_dtype != 0 || a.act != 0 || a.row_scale)) return false;
   if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with bf16 outputs only
-  if (!a.a_kmajor && a.c_dtype != 0) return false;     // weight gradients are f32
   if (a.act != 0 && (a.accumulate || a.residual)) return false;
   if (a.c_dtype != 0 && a.residual) return false;
   if (a.M < 64) return false;                          // skinny problems: the generic kernel with split-K
@@ -606,7 +625,14 @@ int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
   CSTS_REQUIRE(csts_gemm_tc_supported(a), "gemm_tc: unsupported problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   if (a.act == 2) CSTS_REQUIRE(a.Z != nullptr, "gemm: act==2 needs Z");
   const bool atomic = effective_splits(a) > 1;
-  if (!a.a_kmajor) return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);
+  if (!a.a_kmajor) {                                    // (MN, MN): weight gradients, dV / dK of attention
+    if (a.c_dtype == 1) return dispatch<true, true, EPI_BF16>(a, stream);
+    return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);
+  }
+  if (!a.b_kmajor) {                                    // (K, MN): P.V and dS.K of attention
+    CSTS_REQUIRE(a.act == 0 && !atomic, "gemm_tc: (K-major, MN-major) products have plain epilogues");
+    return a.c_dtype == 1 ? dispatch<false, true, EPI_BF16>(a, stream) : dispatch<false, true, EPI_F32>(a, stream);
+  }
   if (a.c_dtype == 0) return atomic ? dispatch<false, false, EPI_F32_ATOMIC>(a, stream) : dispatch<false, false, EPI_F32>(a, stream);
   if (a.act == 1) return dispatch<false, false, EPI_BF16_GELU>(a, stream);
   if (a.act == 2) return dispatch<false, false, EPI_BF16_DGELU>(a, stream);

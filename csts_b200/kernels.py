@@ -72,7 +72,7 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
         ev0.record()
         call("csts_gemm", C.byref(a))
         ev1.record()
-        tc = a.backend != 1 and a_kmajor and b_kmajor and nb == 1 and split_k <= 1 and M >= 64 and (N % 96 == 0 or N % 128 == 0)
+        tc = _lib.load().csts_gemm_backend(C.byref(a)) == 2
         GEMM_PROFILE.append((ev0, ev1, 2.0 * M * N * K * nb, nb * (2.0 * (M * K + N * K) + out.element_size() * M * N), tc))
         return out
     call("csts_gemm", C.byref(a))

@@ -85,9 +85,12 @@ def test_gemm_epilogues(backend):
     assert rel_err(o, (A.float() @ B.float().t()) * gz) < (1e-4 if backend == 1 else 4e-3)
 
 
+@pytest.mark.parametrize("backend", [1, 2])
 @pytest.mark.parametrize("ak,bk", [(True, True), (True, False), (False, False), (False, True)])
-def test_gemm_generic_layouts_batched(ak, bk):
+def test_gemm_generic_layouts_batched(ak, bk, backend):
     k = K()
+    if backend == 2 and (not ak) and bk:
+        pytest.skip("(MN-major A, K-major B) does not occur on the path; generic kernel only")
     b1, b2, M, N, Kd = 2, 3, 260, 96, 264
     Mp = 264                                   # M-major storage needs a leading dim that is a multiple of 8
     g = torch.Generator(device="cpu").manual_seed(11)
@@ -103,8 +106,50 @@ def test_gemm_generic_layouts_batched(ak, bk):
     Bs = B.transpose(-1, -2).contiguous() if bk else B
     out = torch.empty(b1, b2, M, N, dtype=torch.float32, device=dev)
     k.gemm(As, Bs, M=M, N=N, K=Kd, a_kmajor=ak, b_kmajor=bk, lda=lda, out=out, batch=(b1, b2),
-           sA=sA, sB=(b2 * N * Kd, N * Kd), sC=(b2 * M * N, M * N), alpha=0.5)
+           sA=sA, sB=(b2 * N * Kd, N * Kd), sC=(b2 * M * N, M * N), alpha=0.5, backend=backend)
     assert rel_err(out, 0.5 * ref) < 2e-5
+    out16 = torch.empty(b1, b2, M, N, dtype=torch.bfloat16, device=dev)
+    k.gemm(As, Bs, M=M, N=N, K=Kd, a_kmajor=ak, b_kmajor=bk, lda=lda, out=out16, batch=(b1, b2),
+           sA=sA, sB=(b2 * N * Kd, N * Kd), sC=(b2 * M * N, M * N), backend=backend)
+    assert rel_err(out16, ref) < 4e-3
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("Lq,Lk,heads", [(256, 64, 2), (512, 256, 2), (260, 260, 8), (128, 1024, 2)])
+def test_gemm_attention_shapes(backend, Lq, Lk, heads):
+    """The six attention products on strided (B, N, 3, heads, d) / (B, heads, L, ld) operands."""
+    k = K()
+    B, d = 2, 96
+    Cn = heads * d
+    g = torch.Generator(device="cpu").manual_seed(Lq + Lk)
+    qkv = bf(torch.randn(B, Lq, 3, heads, d, generator=g)).to(dev)                   # q strided inside qkv
+    kk = bf(torch.randn(B, heads, Lk, d, generator=g)).to(dev)
+    vv = bf(torch.randn(B, heads, Lk, d, generator=g)).to(dev)
+    ldS = (Lk + 7) // 8 * 8
+    q = qkv[:, :, 0].permute(0, 2, 1, 3).float()
+    S = torch.empty(B, heads, Lq, ldS, dtype=torch.float32, device=dev)
+    k.gemm(qkv, kk, M=Lq, N=Lk, K=d, lda=3 * Cn, ldb=d, out=S, ldc=ldS, alpha=0.25, batch=(B, heads),
+           sA=(Lq * 3 * Cn, d), sB=(heads * Lk * d, Lk * d), sC=(heads * Lq * ldS, Lq * ldS), backend=backend)
+    Sref = 0.25 * q @ kk.float().transpose(-1, -2)
+    assert rel_err(S[..., :Lk], Sref) < 2e-5
+    P = torch.zeros(B, heads, Lq, ldS, dtype=torch.bfloat16, device=dev)
+    P[..., :Lk] = bf(Sref.softmax(-1))
+    o = torch.empty(B, Lq, Cn, dtype=torch.bfloat16, device=dev)
+    k.gemm(P, vv, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=d, out=o, ldc=Cn, batch=(B, heads),
+           sA=(heads * Lq * ldS, Lq * ldS), sB=(heads * Lk * d, Lk * d), sC=(Lq * Cn, d), backend=backend)
+    oref = (P[..., :Lk].float() @ vv.float()).permute(0, 2, 1, 3).reshape(B, Lq, Cn)
+    assert rel_err(o, oref) < 4e-3
+    do = bf(torch.randn(B, Lq, Cn, generator=g)).to(dev)
+    dv = torch.empty(B, heads, Lk, d, dtype=torch.bfloat16, device=dev)
+    k.gemm(P, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=Cn, out=dv, ldc=d, batch=(B, heads),
+           sA=(heads * Lq * ldS, Lq * ldS), sB=(Lq * Cn, d), sC=(heads * Lk * d, Lk * d), backend=backend)
+    do4 = do.float().reshape(B, Lq, heads, d).permute(0, 2, 1, 3)
+    assert rel_err(dv, P[..., :Lk].float().transpose(-1, -2) @ do4) < 4e-3
+    dq = torch.zeros(B, Lq, 3, heads, d, dtype=torch.bfloat16, device=dev)              # dQ written into the qkv-gradient slice
+    k.gemm(P, kk, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=d, out=dq, ldc=3 * Cn, batch=(B, heads),
+           sA=(heads * Lq * ldS, Lq * ldS), sB=(heads * Lk * d, Lk * d), sC=(Lq * 3 * Cn, d), backend=backend)
+    assert rel_err(dq[:, :, 0].permute(0, 2, 1, 3), P[..., :Lk].float() @ kk.float()) < 4e-3
+    assert torch.all(dq[:, :, 1:] == 0)
 
 
 @pytest.mark.parametrize("backend", [1, 2])

