@@ -49,11 +49,21 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
   bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* pre = reinterpret_cast<bf16*>(p.pre);
 
-  for (int64_t idx = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); idx < total; idx += (int64_t)gridDim.x * wpb) {
+  // each warp walks a contiguous range of output positions: coordinates are decoded once and then
+  // advanced incrementally (no per-position division)
+  const int64_t nwarps = (int64_t)gridDim.x * wpb;
+  const int64_t per_warp = (total + nwarps - 1) / nwarps;
+  int64_t idx = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * per_warp;
+  const int64_t idx_end = idx + per_warp < total ? idx + per_warp : total;
+  int wo = 0, ho = 0, to = 0, hd = 0, b = 0;
+  if (idx < idx_end) {
     int o = (int)(idx % Lo);
     int bh = (int)(idx / Lo);
-    int hd = bh % p.heads, b = bh / p.heads;
-    int wo = o % p.Wo, ho = (o / p.Wo) % p.Ho, to = o / (p.Wo * p.Ho);
+    hd = bh % p.heads; b = bh / p.heads;
+    wo = o % p.Wo; ho = (o / p.Wo) % p.Ho; to = o / (p.Wo * p.Ho);
+  }
+  for (; idx < idx_end; ++idx) {
+    const int o = (to * p.Ho + ho) * p.Wo + wo;
     const bf16* in_bh = in + b * p.in_sB + hd * p.in_sH;
     float acc[NJ][4];
 #pragma unroll
@@ -137,6 +147,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
         }
       }
     }
+    if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; if (++to == p.To) { to = 0; if (++hd == p.heads) { hd = 0; ++b; } } } }
   }
 }
 
@@ -165,12 +176,22 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
       for (int i = 0; i < 4; ++i) acc[j][t][i] = 0.f;
   const int64_t beg = (int64_t)blockIdx.x * pos_per_block;
   const int64_t end = beg + pos_per_block < total ? beg + pos_per_block : total;
+  int wo = 0, ho = 0, to = 0, hd = 0, b = 0;
+  if (beg < end) {
+    int o = (int)(beg % Ls);
+    int bh = (int)(beg / Ls);
+    hd = bh % p.heads; b = bh / p.heads;
+    wo = o % p.Ws; ho = (o / p.Ws) % p.Hs; to = o / (p.Ws * p.Hs);
+  }
+  // coordinates advance incrementally; `adv` runs at the top of every iteration but the first
+  bool first = true;
 #pragma unroll 2
   for (int64_t idx = beg; idx < end; ++idx) {
-    int o = (int)(idx % Ls);
-    int bh = (int)(idx / Ls);
-    int hd = bh % p.heads, b = bh / p.heads;
-    int wo = o % p.Ws, ho = (o / p.Ws) % p.Hs, to = o / (p.Ws * p.Hs);
+    if (!first) {
+      if (++wo == p.Ws) { wo = 0; if (++ho == p.Hs) { ho = 0; if (++to == p.Ts) { to = 0; if (++hd == p.heads) { hd = 0; ++b; } } } }
+    }
+    first = false;
+    const int o = (to * p.Hs + ho) * p.Ws + wo;
     int ti = (to << lt) + kt - 1, hi = (ho << lh) + kh - 1;
     if (ti < 0 || ti >= p.Tb || hi < 0 || hi >= p.Hb) continue;      // warp-uniform
     const bf16* sp = small + b * p.small_sB + hd * p.small_sH + (int64_t)o * p.small_sP;

@@ -5,12 +5,12 @@
 
 namespace {
 
-constexpr int LN_MAXJ = 6;   // width <= 6 * 128 = 768
+constexpr int LN_MAX_WIDTH = 768;   // up to 6 column groups of 128 per warp
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm forward: y = (x - mean) * rstd * gamma + beta            ref: nn.LayerNorm (attention.py:239,243)
 // ------------------------------------------------------------------------------------------------
-template <typename TI, typename TO>
+template <typename TI, typename TO, int LN_MAXJ>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI* __restrict
 // dgamma += sum_rows dy*xhat, dbeta += sum_rows dy  (per-warp registers -> smem -> one atomic per
 // column per block).
 // ------------------------------------------------------------------------------------------------
-template <typename TX, typename TDY, typename TDX>
+template <typename TX, typename TDY, typename TDX, int LN_MAXJ>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ add,
@@ -307,35 +307,51 @@ extern "C" {
 // dtype codes: 0 = f32, 1 = bf16
 int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,
                        float* rstd, int64_t rows, int width, float eps, void* stream) {
-  CSTS_REQUIRE(width % 4 == 0 && width <= 128 * LN_MAXJ, "layernorm: width %d unsupported (multiple of 4, <= 768)", width);
+  CSTS_REQUIRE(width % 4 == 0 && width <= LN_MAX_WIDTH, "layernorm: width %d unsupported (multiple of 4, <= 768)", width);
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(rows, 8);
-#define LN_FWD(TI, TO) layernorm_fwd_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, (int)rows, width, eps)
+#define LN_FWD_J(TI, TO, J) layernorm_fwd_kernel<TI, TO, J><<<grid, 256, 0, st>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, (int)rows, width, eps)
+#define LN_FWD(TI, TO)                                   \
+  do {                                                   \
+    if (width <= 128) LN_FWD_J(TI, TO, 1);               \
+    else if (width <= 256) LN_FWD_J(TI, TO, 2);          \
+    else if (width <= 384) LN_FWD_J(TI, TO, 3);          \
+    else LN_FWD_J(TI, TO, 6);                            \
+  } while (0)
   if (x_dtype == 0 && y_dtype == 1) LN_FWD(float, bf16);
   else if (x_dtype == 0 && y_dtype == 0) LN_FWD(float, float);
   else if (x_dtype == 1 && y_dtype == 1) LN_FWD(bf16, bf16);
   else if (x_dtype == 1 && y_dtype == 0) LN_FWD(bf16, float);
   else CSTS_REQUIRE(false, "layernorm: bad dtype codes %d %d", x_dtype, y_dtype);
 #undef LN_FWD
+#undef LN_FWD_J
   return csts_check_launch("layernorm_fwd");
 }
 
 int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                        const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
                        int width, void* stream) {
-  CSTS_REQUIRE(width % 4 == 0 && width <= 128 * LN_MAXJ, "layernorm_bwd: width %d unsupported", width);
+  CSTS_REQUIRE(width % 4 == 0 && width <= LN_MAX_WIDTH, "layernorm_bwd: width %d unsupported", width);
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int64_t blocks = (rows + 31) / 32;       // >= 4 rows per warp so the column atomics amortise
   int grid = (int)(blocks < csts_num_sms() * 8 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 8);
-#define LN_BWD(TX, TDY, TDX) \
-  layernorm_bwd_kernel<TX, TDY, TDX><<<grid, 256, 0, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
+#define LN_BWD_J(TX, TDY, TDX, J) \
+  layernorm_bwd_kernel<TX, TDY, TDX, J><<<grid, 256, 0, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
+#define LN_BWD(TX, TDY, TDX)                             \
+  do {                                                   \
+    if (width <= 128) LN_BWD_J(TX, TDY, TDX, 1);         \
+    else if (width <= 256) LN_BWD_J(TX, TDY, TDX, 2);    \
+    else if (width <= 384) LN_BWD_J(TX, TDY, TDX, 3);    \
+    else LN_BWD_J(TX, TDY, TDX, 6);                      \
+  } while (0)
   if (x_dtype == 0 && dy_dtype == 1 && dx_dtype == 0) LN_BWD(float, bf16, float);
   else if (x_dtype == 1 && dy_dtype == 1 && dx_dtype == 1) LN_BWD(bf16, bf16, bf16);
   else if (x_dtype == 0 && dy_dtype == 0 && dx_dtype == 0) LN_BWD(float, float, float);
   else CSTS_REQUIRE(false, "layernorm_bwd: unsupported dtype combination x=%d dy=%d dx=%d", x_dtype, dy_dtype, dx_dtype);
 #undef LN_BWD
+#undef LN_BWD_J
   return csts_check_launch("layernorm_bwd");
 }
 
