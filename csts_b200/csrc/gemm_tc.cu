@@ -27,11 +27,10 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 12;                         // three per TMEM lane quadrant
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int SMEM_BUDGET = 160 * 1024;
+constexpr int SMEM_BUDGET = 168 * 1024;
 constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;   // one 32-row x 128-byte tile per epilogue warp
-constexpr int BIAS_BYTES = NUM_EPI_WARPS * 256 * 4;       // per-warp copy of the tile's bias slice
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -146,19 +145,29 @@ template <int BN> struct Cfg {
   static constexpr int B_BYTES = B_BOXES * 64 * BK * 2;          // >= BN * BK * 2, multiple of 8 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;   // >= 2 accumulators, power of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int NACC = (512 / BN) >= 4 ? 4 : 2;            // accumulator stages in TMEM
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---- epilogue helpers: a warp moves a 32-row x 128-byte tile between global memory (coalesced: 8 lanes
 // cover one 128-byte row segment, 4 rows per instruction) and its swizzled staging tile, in which
 // lane r then owns row r (16-byte chunk j of row r lives at chunk j ^ (r & 7): conflict-free both ways).
-__device__ __forceinline__ uint4* stage_ptr(unsigned char* stage, int row, int chunk) {
-  return reinterpret_cast<uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+// Staging is addressed in the shared window explicitly (ld/st.shared), never through generic pointers.
+__device__ __forceinline__ uint32_t stage_addr(uint32_t stage, int row, int chunk) {
+  return stage + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 // global -> staging.  `gbase` points at (row 0, first byte) of the 32 x 128 B window; rows beyond
 // `rows_valid` and bytes beyond `bytes_valid` are skipped.  All 8 loads are issued before the stores.
-__device__ __forceinline__ void stage_load(unsigned char* stage, const unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
+__device__ __forceinline__ void stage_load(uint32_t stage, const unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
                                            int bytes_valid, int lane) {
   const int chunk = lane & 7;
   const bool col_ok = chunk * 16 < bytes_valid;
@@ -167,19 +176,19 @@ __device__ __forceinline__ void stage_load(unsigned char* stage, const unsigned 
   for (int i = 0; i < 8; ++i) {
     int row = 4 * i + (lane >> 3);
     v[i] = make_uint4(0, 0, 0, 0);
-    if (col_ok && row < rows_valid) v[i] = *reinterpret_cast<const uint4*>(gbase + row * pitch_bytes + chunk * 16);
+    if (col_ok && row < rows_valid) v[i] = __ldg(reinterpret_cast<const uint4*>(gbase + row * pitch_bytes + chunk * 16));
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) *stage_ptr(stage, 4 * i + (lane >> 3), chunk) = v[i];
+  for (int i = 0; i < 8; ++i) sts128(stage_addr(stage, 4 * i + (lane >> 3), chunk), v[i]);
 }
 template <bool ATOMIC>
-__device__ __forceinline__ void stage_store(unsigned char* stage, unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
-                                            int bytes_valid, int lane) {
+__device__ __forceinline__ void stage_store(uint32_t stage, unsigned char* gbase, int64_t pitch_bytes, int rows_valid, int bytes_valid,
+                                            int lane) {
   const int chunk = lane & 7;
   const bool col_ok = chunk * 16 < bytes_valid;
   uint4 v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = *stage_ptr(stage, 4 * i + (lane >> 3), chunk);
+  for (int i = 0; i < 8; ++i) v[i] = lds128(stage_addr(stage, 4 * i + (lane >> 3), chunk));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int row = 4 * i + (lane >> 3);
@@ -196,137 +205,117 @@ __device__ __forceinline__ void stage_store(unsigned char* stage, unsigned char*
 
 enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32_ATOMIC = 4 };
 
-// alpha * acc + bias for one 32-column slice (bias read from the warp's shared-memory copy)
-__device__ __forceinline__ void load_slice(const TcParams& p, uint32_t taddr, const float* sbias, bool use_bias, float (&v)[32]) {
+// One 32-column slice of the accumulator rows owned by this warp -> epilogue math -> global memory.
+// m0 = first row of the warp's 32-row band, n0 = first column, `stage` = the warp's staging tile.
+template <int EPI>
+__device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, uint32_t stage, int m0, int n0, int cols_in_tile,
+                                               int lane, uint32_t taddr, float rs, bool first_split) {
+  constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
+  constexpr int ESZ = F32 ? 4 : 2;
+  const int rows_valid = min(32, p.M - m0);
+  const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
+  unsigned char* cg = reinterpret_cast<unsigned char*>(p.C) + (coff + (int64_t)m0 * p.ldc + n0) * ESZ;
+  unsigned char* zg = reinterpret_cast<unsigned char*>(p.Z) + ((int64_t)m0 * p.ldz + n0) * 2;
+  // global reads first: their latency overlaps the TMEM load
+  float4 bv[8];
+  const bool use_bias = p.bias != nullptr && first_split;
+  if (use_bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bv[i] = (4 * i < cols_valid) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i) : make_float4(0, 0, 0, 0);
+  }
+  const bool has_res = F32 && p.residual != nullptr && first_split;
+  const bool has_acc = (EPI == EPI_F32 || EPI == EPI_BF16) && p.accumulate;
+  if (EPI == EPI_BF16_DGELU) stage_load(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
+  else if (has_res) {
+    int rrow = p.res_mod > 0 ? m0 % p.res_mod : m0;
+    stage_load(stage, reinterpret_cast<const unsigned char*>(p.residual + (int64_t)rrow * p.ldr + n0), p.ldr * 4, rows_valid,
+               cols_valid * 4, lane);
+  } else if (has_acc) stage_load(stage, cg, p.ldc * ESZ, rows_valid, cols_valid * ESZ, lane);
   uint32_t r[32];
   tmem_ld32(taddr, r);
   tmem_ld_wait();
+  float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
   if (use_bias) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float4 b = *reinterpret_cast<const float4*>(sbias + i);
-      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-    }
+    for (int i = 0; i < 8; ++i) { v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w; }
   }
-}
-__device__ __forceinline__ void pack_slice(unsigned char* stage, int lane, int half, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *stage_ptr(stage, lane, half * 4 + j) = make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
-                                                       pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7]));
-}
-
-// bf16 output, one unit = 64 columns (two TMEM slices -> one full 128-byte staging row per lane)
-template <int EPI>
-__device__ __forceinline__ void epilogue_unit_bf16(const TcParams& p, int64_t coff, unsigned char* stage, const float* sbias, int m0,
-                                                   int n0, int cols_in_tile, int lane, uint32_t taddr, float rs) {
-  const int rows_valid = min(32, p.M - m0);
-  const int cols_valid = min(min(64, cols_in_tile), p.N - n0);
-  const bool two = cols_valid > 32;
-  const bool use_bias = p.bias != nullptr;
-  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.C) + coff + (int64_t)m0 * p.ldc + n0);
-  unsigned char* zg = reinterpret_cast<unsigned char*>(reinterpret_cast<bf16*>(p.Z) + (int64_t)m0 * p.ldz + n0);
-  float v0[32], v1[32];
-  load_slice(p, taddr, sbias, use_bias, v0);
-  if (two) load_slice(p, taddr + 32, sbias + 32, use_bias, v1);
   if (EPI == EPI_BF16_GELU) {
     if (p.Z) {
-      pack_slice(stage, lane, 0, v0);
-      if (two) pack_slice(stage, lane, 1, v1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
+                                                      pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
       __syncwarp();
       stage_store<false>(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
       __syncwarp();
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v0[i] = gelu_erf(v0[i]);
-    if (two) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v1[i] = gelu_erf(v1[i]);
-    }
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
   }
-  if (EPI == EPI_BF16_DGELU || (EPI == EPI_BF16 && p.accumulate)) {
-    // read the Z tile (DGELU) or the old C tile (accumulate) through the staging buffer
-    stage_load(stage, EPI == EPI_BF16_DGELU ? zg : cg, (EPI == EPI_BF16_DGELU ? p.ldz : p.ldc) * 2, rows_valid, cols_valid * 2, lane);
+  if (EPI == EPI_BF16_DGELU) {
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint4 t0 = *stage_ptr(stage, lane, j), t1 = *stage_ptr(stage, lane, 4 + j);
-      const bf162* a0 = reinterpret_cast<const bf162*>(&t0);
-      const bf162* a1 = reinterpret_cast<const bf162*>(&t1);
+      uint4 t = lds128(stage_addr(stage, lane, j));
+      const bf162* zz = reinterpret_cast<const bf162*>(&t);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (EPI == EPI_BF16_DGELU) {
-          v0[8 * j + 2 * i] *= gelu_erf_grad(__low2float(a0[i])); v0[8 * j + 2 * i + 1] *= gelu_erf_grad(__high2float(a0[i]));
-          v1[8 * j + 2 * i] *= gelu_erf_grad(__low2float(a1[i])); v1[8 * j + 2 * i + 1] *= gelu_erf_grad(__high2float(a1[i]));
-        } else {
-          v0[8 * j + 2 * i] += __low2float(a0[i]); v0[8 * j + 2 * i + 1] += __high2float(a0[i]);
-          v1[8 * j + 2 * i] += __low2float(a1[i]); v1[8 * j + 2 * i + 1] += __high2float(a1[i]);
-        }
+        v[8 * j + 2 * i] *= gelu_erf_grad(__low2float(zz[i]));
+        v[8 * j + 2 * i + 1] *= gelu_erf_grad(__high2float(zz[i]));
       }
     }
     __syncwarp();
   }
   if (p.row_scale) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { v0[i] *= rs; v1[i] *= rs; }
-  }
-  pack_slice(stage, lane, 0, v0);
-  if (two) pack_slice(stage, lane, 1, v1);
-  __syncwarp();
-  stage_store<false>(stage, cg, p.ldc * 2, rows_valid, cols_valid * 2, lane);
-  __syncwarp();
-}
-
-// f32 output, one unit = 32 columns (128-byte staging rows)
-template <int EPI>
-__device__ __forceinline__ void epilogue_unit_f32(const TcParams& p, int64_t coff, unsigned char* stage, const float* sbias, int m0,
-                                                  int n0, int cols_in_tile, int lane, uint32_t taddr, float rs, bool first_split) {
-  const int rows_valid = min(32, p.M - m0);
-  const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
-  unsigned char* cg = reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(p.C) + coff + (int64_t)m0 * p.ldc + n0);
-  // issue the residual / old-C tile read first: its latency overlaps the TMEM load
-  const bool has_res = p.residual != nullptr && first_split;
-  const bool has_acc = EPI == EPI_F32 && p.accumulate;
-  if (has_res) {
-    int rrow = p.res_mod > 0 ? m0 % p.res_mod : m0;
-    stage_load(stage, reinterpret_cast<const unsigned char*>(p.residual + (int64_t)rrow * p.ldr + n0), p.ldr * 4, rows_valid,
-               cols_valid * 4, lane);
-  }
-  float v[32];
-  load_slice(p, taddr, sbias, p.bias != nullptr && first_split, v);
-  if (p.row_scale) {
-#pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= rs;
   }
-  if (has_res) {
+  if (has_res || (F32 && has_acc)) {
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      uint4 t = *stage_ptr(stage, lane, j);
+      uint4 t = lds128(stage_addr(stage, lane, j));
       v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y);
       v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
     }
     __syncwarp();
-  }
-  if (has_acc) {
-    stage_load(stage, cg, p.ldc * 4, rows_valid, cols_valid * 4, lane);
+    if (has_res && has_acc) {                      // residual and accumulate together: second pass for the old C
+      stage_load(stage, cg, p.ldc * 4, rows_valid, cols_valid * 4, lane);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 t = lds128(stage_addr(stage, lane, j));
+        v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y);
+        v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
+      }
+      __syncwarp();
+    }
+  } else if (!F32 && has_acc) {
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 t = *stage_ptr(stage, lane, j);
-      v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y);
-      v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
+    for (int j = 0; j < 4; ++j) {
+      uint4 t = lds128(stage_addr(stage, lane, j));
+      const bf162* oo = reinterpret_cast<const bf162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[8 * j + 2 * i] += __low2float(oo[i]); v[8 * j + 2 * i + 1] += __high2float(oo[i]); }
     }
     __syncwarp();
   }
+  if (F32) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *stage_ptr(stage, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                                            __float_as_uint(v[4 * j + 3]));
+    for (int j = 0; j < 8; ++j)
+      sts128(stage_addr(stage, lane, j), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                    __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+  }
   __syncwarp();
-  stage_store<EPI == EPI_F32_ATOMIC>(stage, cg, p.ldc * 4, rows_valid, cols_valid * 4, lane);
+  stage_store<EPI == EPI_F32_ATOMIC>(stage, cg, p.ldc * ESZ, rows_valid, cols_valid * ESZ, lane);
   __syncwarp();
 }
 
@@ -340,12 +329,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::STAGES * C::A_BYTES;
   unsigned char* sStage = smem + C::STAGES * C::STAGE_BYTES;
-  float* sBias = reinterpret_cast<float*>(sStage + STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES + BIAS_BYTES);
-  // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES);
+  // bars: full[STAGES], empty[STAGES], tmem_full[NACC], tmem_empty[NACC]
   uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
-  uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 8 * C::NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2 * C::NACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -356,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, NUM_EPI_WARPS); }
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
@@ -437,45 +425,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull0 + 8 * as);                // accumulator complete
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (++as == C::NACC) { as = 0; aphase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9): two warps per TMEM lane quadrant =====================
+    // ===================== epilogue (warps 2..13): three warps per TMEM lane quadrant =====================
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;                // which of the quadrant's two warps
-    unsigned char* stage_buf = sStage + (warp - 2) * (32 * 128);
-    float* bias_buf = sBias + (warp - 2) * 256;
-    constexpr int UNIT = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 32 : 64;
+    const int sub = (warp - 2) >> 2;                 // which of the quadrant's three warps
+    const uint32_t stage_buf = smem_u32(sStage) + (warp - 2) * (32 * 128);
     int as = 0; uint32_t aphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tm, tn, z, kb0, kb1;
       const int split = decode(item, tm, tn, z, kb0, kb1);
       const int64_t coff = (int64_t)(z / p.batch2) * p.sC1 + (int64_t)(z % p.batch2) * p.sC2;
       const int m0 = tm * BM + quad * 32;
-      // bias slice of this tile -> the warp's shared-memory copy (latency hidden behind the accumulator wait)
-      if (p.bias) {
-#pragma unroll
-        for (int c = lane; c < BN; c += 32) bias_buf[c] = (tn * BN + c < p.N) ? p.bias[tn * BN + c] : 0.f;
-      }
       float rs = 1.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + lane, p.M - 1) / p.rows_per_scale];
-      __syncwarp();
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
       const bool live = m0 < p.M && kb1 > kb0;       // rows beyond M / an empty k-range contribute nothing
 #pragma unroll 1
-      for (int c = half * UNIT; c < BN; c += 2 * UNIT) {
+      for (int c = sub * 32; c < BN; c += (NUM_EPI_WARPS / 4) * 32) {
         const int n0 = tn * BN + c;
         if (!live || n0 >= p.N) continue;
-        if (UNIT == 64) epilogue_unit_bf16<EPI>(p, coff, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs);
-        else epilogue_unit_f32<EPI>(p, coff, stage_buf, bias_buf + c, m0, n0, BN - c, lane, trow + c, rs, split == 0);
+        epilogue_slice<EPI>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == C::NACC) { as = 0; aphase ^= 1; }
     }
   }
 
