@@ -1,0 +1,170 @@
+/* libcsts_b200.so — C ABI of the B200 (sm_100a) kernels behind the CSTS hot path.
+ *
+ * The reference (BolinLai/CSTS) is pure Python: the "FFI" of this path is the set of
+ * torch.nn / torch.nn.functional calls made by slowfast/models/{attention,av_attention,common,
+ * stem_helper,custom_multimodal_builder,losses}.py and slowfast/utils/utils.py.  Each entry point
+ * below names the reference call site(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes and strides in ELEMENTS, `void* stream` = cudaStream_t.
+ *   - every function returns 0 on success and a non-zero code otherwise; csts_last_error() returns the
+ *     calling thread's message.  No exception crosses the ABI, there is no fallback path.
+ *   - asynchronous on `stream`, no internal synchronisation, no device allocation, no retained pointers:
+ *     the caller (PyTorch's caching allocator) owns all memory.  Re-entrant / thread-safe (backward runs
+ *     on autograd's worker thread).
+ *   - dtype codes: 0 = f32, 1 = bf16.  Residual stream / statistics / gradients of parameters are f32,
+ *     GEMM operands and saved activations are bf16.
+ *   - the library is built for sm_100a only; csts_check_device() reports anything else.
+ */
+#ifndef CSTS_B200_H
+#define CSTS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int csts_version(void);
+int csts_last_error(char* buf, int len);
+int csts_check_device(void);
+long long csts_launch_count(int reset);          /* kernels launched since load / last reset */
+
+/* ---- GEMM -------------------------------------------------------------------------------------------
+ * C[z][m][n] = epi( alpha * sum_k opA(A[z])[m][k] * opB(B[z])[n][k] )
+ * Replaces every nn.Linear (attention.py:130,159; common.py:19-31; attention.py:246; custom_multimodal_
+ * builder.py:495-496), the q@k^T / attn@v batched matmuls (attention.py:154,158; av_attention.py:137,141,
+ * 334,351), the PatchEmbed Conv3d after im2col (stem_helper.py:27-36), the dense (1,8,8) Conv3d pools
+ * (custom_multimodal_builder.py:227-229) and all of their autograd backward products.
+ * Large token-major problems run on the tcgen05/TMEM/TMA kernel, odd shapes on the mma.sync kernel. */
+typedef struct csts_gemm_args {
+  const void* A;          /* bf16 */
+  const void* B;          /* bf16 */
+  void* C;                /* f32 or bf16 (c_dtype) */
+  void* Z;                /* bf16, same shape as C (pitch ldz): act==1 -> receives the pre-activation,
+                                                                act==2 -> is read (multiply by GELU'(Z)) */
+  const float* bias;      /* [N] or NULL */
+  const float* residual;  /* f32 [rows, N] (pitch ldr) or NULL; row = m % res_mod when res_mod > 0 */
+  const float* row_scale; /* [ceil(M / rows_per_scale)] or NULL: row m is multiplied by
+                             row_scale[m / rows_per_scale] before the residual is added (DropPath, common.py:46-59) */
+  int64_t lda, ldb, ldc, ldz, ldr;
+  int64_t sA1, sA2, sB1, sB2, sC1, sC2;   /* batch strides: z -> (z / batch2, z % batch2) */
+  int32_t M, N, K;
+  int32_t batch1, batch2;
+  int32_t a_kmajor;       /* 1: A[m*lda + k]   0: A[k*lda + m] */
+  int32_t b_kmajor;       /* 1: B[n*ldb + k]   0: B[k*ldb + n] */
+  int32_t c_dtype;        /* 0 f32, 1 bf16 */
+  int32_t act;            /* 0 none, 1 exact-erf GELU (nn.GELU(), common.py:21), 2 times GELU'(Z) */
+  int32_t accumulate;     /* C += result */
+  int32_t res_mod;
+  int32_t split_k;        /* > 1: partial sums combined with f32 atomics (C must be f32) */
+  float alpha;
+  int32_t backend;        /* 0 auto, 1 mma.sync, 2 tcgen05 */
+  int32_t rows_per_scale;
+} csts_gemm_args;
+int csts_gemm(const csts_gemm_args* a, void* stream);
+int csts_gemm_backend(const csts_gemm_args* a);  /* 2 = tcgen05, 1 = mma.sync for this problem */
+
+/* ---- LayerNorm: nn.LayerNorm (attention.py:239,243 norm1/norm2 eps 1e-6; :42-43 norm_q/k/v eps 1e-5) --- */
+int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,
+                       float* rstd, int64_t rows, int width, float eps, void* stream);
+/* dx = [add +] LN'(dy); dgamma/dbeta (f32, zeroed by the caller) are accumulated into */
+int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                       const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
+                       int width, void* stream);
+
+/* ---- attention softmax: attn.softmax(dim=-1) (attention.py:155), with the in-frame mask of
+ * SpatialAttention (av_attention.py:336-348) when mask_hw > 0.  P is bf16, pad columns [n, ldp) zero. */
+int csts_softmax_fwd(const float* S, void* P, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t, void* stream);
+int csts_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n, int ldp, int lddp, float scale, void* stream);
+
+/* ---- casts / layout / elementwise ------------------------------------------------------------------- */
+int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_out, const float* row_scale, int rows_per_scale,
+                   void* stream);
+int csts_permute_021(const float* src, void* dst, int dst_dtype, int a, int b, int c, void* stream); /* [a][b][c] -> [a][c][b] */
+int csts_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);     /* decoder skips, custom_multimodal_builder.py:467-473 */
+int csts_scale_f32(const float* a, const float* device_scalar, float* out, int64_t n, void* stream);
+int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_t ld, void* stream);  /* bias gradients */
+
+/* ---- attention_pool / attention_upsample: depthwise 3x3x3 Conv3d / ConvTranspose3d over the token grid
+ * + LayerNorm(head_dim) (attention.py:11-49, :105-116; :251-292, :344-348).  Element (b, head, pos, c) of
+ * `in` lives at in + b*in_sB + head*in_sH + pos*in_sP + c: the kernels read the (B,N,3,heads,d) qkv
+ * tensor in place, so the reference's permute+contiguous copies (attention.py:31,37) do not exist. */
+typedef struct csts_pool_args {
+  const void* in;         /* bf16 */
+  void* out;              /* bf16 */
+  const float* w;         /* (d,1,3,3,3) parameter, f32 */
+  const float* gamma;     /* LayerNorm(d) weight or NULL (no norm: `out` = raw conv) */
+  const float* beta;
+  void* pre;              /* bf16 dense (B, heads, Lo, d): raw conv output kept for backward (norm only) */
+  float* mean;            /* [B*heads*Lo] (norm only) */
+  float* rstd;
+  int64_t in_sB, in_sH, in_sP;
+  int64_t out_sB, out_sH, out_sP;
+  int32_t B, heads, d;
+  int32_t Ti, Hi, Wi;     /* input grid */
+  int32_t To, Ho, Wo;     /* output grid */
+  int32_t st, sh, sw;     /* stride of the (un-transposed) convolution, powers of two */
+  int32_t transposed;     /* 0: out[o] = sum_tap w[tap] in[o*s+tap-1]; 1: out[o] = sum_tap w[tap] in[(o+1-tap)/s] */
+  float eps;
+} csts_pool_args;
+int csts_dwconv(const csts_pool_args* p, void* stream);
+
+/* dw[c][tap] += sum small[o][c] * big[o*s + tap - 1][c]   (conv: small = d(out), big = in; transposed: swapped) */
+typedef struct csts_wgrad_args {
+  const void* small;      /* bf16, grid (Ts,Hs,Ws) */
+  const void* big;        /* bf16, grid (Tb,Hb,Wb) */
+  float* dw;              /* (d,1,3,3,3) f32, accumulated into */
+  int64_t small_sB, small_sH, small_sP;
+  int64_t big_sB, big_sH, big_sP;
+  int32_t B, heads, d;
+  int32_t Ts, Hs, Ws;
+  int32_t Tb, Hb, Wb;
+  int32_t st, sh, sw;
+} csts_wgrad_args;
+int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream);
+
+/* ---- residual-path resampling on the token-major f32 stream (B, T*H*W, C) -------------------------------
+ * pool_skip = nn.MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (attention.py:225-236,240);
+ * upsample_skip = nn.Upsample(trilinear, align_corners=False) (attention.py:463-467,471). */
+int csts_maxpool_fwd(const float* x, float* y, void* argmax_u8, int B, int T, int H, int W, int C, void* stream);
+int csts_maxpool_bwd(const float* dy, const void* argmax_u8, float* dx, int B, int T, int H, int W, int C, void* stream);
+int csts_upsample_fwd(const float* x, float* y, int B, int T, int H, int W, int C, int ft, int fh, int fw, void* stream);
+int csts_upsample_bwd(const float* dy, float* dx, int B, int T, int H, int W, int C, int ft, int fh, int fw, int accumulate, void* stream);
+
+/* ---- stem / fusion glue / head --------------------------------------------------------------------- */
+/* PatchEmbed Conv3d k(3,7,7) s(2,4,4) p(1,3,3) as im2col (stem_helper.py:27-38): x f32 (B,Cin,T,H,W) ->
+ * bf16 [B*T/2*H/4*W/4, Kp], column ((c*3+kt)*7+kh)*7+kw, zero padded to Kp */
+int csts_im2col_patch(const float* x, void* patches, int B, int Cin, int T, int H, int W, int Kp, void* stream);
+/* separable position embedding (custom_multimodal_builder.py:362-370) and its gradient */
+int csts_pos_embed(const float* spatial, const float* temporal, float* pos, int T, int HW, int C, void* stream);
+int csts_pos_embed_bwd(const float* dY, float* dspatial, float* dtemporal, int B, int T, int HW, int C, void* stream);
+/* fusion re-weighting x * w[:, t] (custom_multimodal_builder.py:454-461) */
+int csts_reweight_fwd(const float* x, const float* w, float* out, int B, int T, int S, int C, int64_t w_sB, void* stream);
+int csts_reweight_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, int B, int T, int S, int C, int64_t w_sB,
+                      void* stream);
+/* x.mean(dim=1) feeding vision_proj / audio_proj (custom_multimodal_builder.py:493-496) */
+int csts_token_mean_fwd(const float* x, void* out_bf16, int B, int N, int C, void* stream);
+int csts_token_mean_bwd(const float* dout, float* dx, int B, int N, int C, int accumulate, void* stream);
+/* classifier(feat + F.interpolate(stem, T -> 2T, trilinear)) (custom_multimodal_builder.py:476-481) */
+int csts_classifier_fwd(const float* feat, const float* stem, const float* w, const float* bias, float* logits, int B, int Ti, int S, int C,
+                        void* stream);
+int csts_classifier_bwd(const float* dlogits, const float* feat, const float* stem, const float* w, float* dfeat, float* dstem, float* dw,
+                        float* dbias, int B, int Ti, int S, int C, void* stream);
+
+/* ---- losses -------------------------------------------------------------------------------------------
+ * frame_softmax (slowfast/utils/utils.py:5-12) fused with KLDiv (slowfast/models/losses.py:59-82): emits the
+ * soft-maxed heat-maps, the scalar loss and d loss / d logits in one pass over the logits. */
+int csts_kldiv_frame_softmax(const float* logits, const float* target, float* prob, float* frame_kl, float* loss, float* dlogits,
+                             int frames, int HW, int T, float temperature, void* stream);
+/* sim_matrix (slowfast/utils/utils.py:15-24) and its gradient */
+int csts_sim_matrix_fwd(const float* a, const float* b, float* sim, float* na, float* nb, int n, int D, float eps, void* stream);
+int csts_sim_matrix_bwd(const float* a, const float* b, const float* sim, const float* dsim, const float* na, const float* nb, float* da,
+                        float* db, int n, int D, void* stream);
+/* EgoNCE (slowfast/models/losses.py:157-170): loss and d loss / d sim; lse_scratch holds 2*n floats */
+int csts_egonce(const float* sim, float* loss, float* dsim, float* lse_scratch, int n, float temperature, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSTS_B200_H */
