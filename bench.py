@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]): CSTS Ego4D training step — forward(return
 + KLDiv + sim_matrix + EgoNCE (LOSS_ALPHA 0.05) + backward + grad-norm clip (1.0) + AdamW — at a
 per-GPU batch of 8 clips (8 x 256 x 256 RGB + 8 x 256 x 256 log-STFT), bf16 tensor-core operands /
 f32 accumulate and residual stream, synthetic inputs, random-init weights, MVIT.DROPPATH_RATE 0.2.
-N > 1: one process per GPU (torchrun), batch-sharded (weak scaling), NCE all-gather + DDP all-reduce.
+N > 1: one process per GPU (torchrun), batch-sharded (weak scaling), NCE all-gather + bucketed NCCL
+gradient all-reduce (captured in the step's CUDA graph; --no-graph uses the eager DDP reducer instead).
 
   value : clips/s with inputs already resident in HBM (CUDA-event timed, max over ranks)
   e2e   : the same step through the public API with the batch in pinned HOST memory — H2D of video /
@@ -146,7 +147,7 @@ def run_gpu(args):
     torch.manual_seed(cfg.RNG_SEED)
     model = build_model(cfg)
     model.train()
-    use_graph = args.graph and world == 1
+    use_graph = args.graph
     opt = construct_optimizer(model, cfg, capturable=use_graph)
     B = BATCH_PER_GPU
     # host batch in pinned memory (the public-API path) and a resident device copy
@@ -167,7 +168,7 @@ def run_gpu(args):
     if graphed is not None:
         # launch count of one step, taken from an eager (un-captured) step: a graph replay launches the same kernels
         _lib.launch_count(reset=True)
-        train_step(cfg, model, opt, [video_d], audio_d, hm_d)
+        train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync)
         launches_per_step = _lib.launch_count()
 
     def resident_step():
@@ -187,7 +188,7 @@ def run_gpu(args):
         return loss
 
     def eager_profile_step():
-        return train_step(cfg, model, opt, [video_d], audio_d, hm_d)
+        return train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync)
 
     def timed(fn, steps, profile=False):
         barrier()

@@ -79,6 +79,32 @@ def all_gather(tensors):
     return out
 
 
+def allreduce_gradients(params, bucket_bytes=256 << 20):
+    """Average the gradients of `params` across ranks with a few large NCCL all-reduces over NVLink /
+    NVSwitch (NVLS when available): gradients are packed into contiguous f32 buckets (reverse
+    registration order ~ the order backward produces them), reduced with ReduceOp.AVG, and `p.grad`
+    is re-pointed at its slice of the bucket (no copy back).  Unlike the DDP reducer this is plain
+    stream-ordered work, so the whole training step including the exchange can live in one CUDA graph."""
+    world = get_world_size()
+    if world == 1:
+        return
+    todo = [p for p in params if p.grad is not None][::-1]
+    i = 0
+    while i < len(todo):
+        bucket, size = [], 0
+        while i < len(todo) and (not bucket or size + todo[i].numel() * 4 <= bucket_bytes):
+            bucket.append(todo[i])
+            size += todo[i].numel() * 4
+            i += 1
+        flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            p.grad = flat[off: off + n].view_as(p)
+            off += n
+
+
 def init_distributed_training(cfg):
     """distributed.py:305-320 creates one process group per machine for SyncBN; CSTS has no
     BatchNorm, so nothing is needed beyond the default group."""

@@ -56,8 +56,10 @@ def compute_loss(cfg, model, inputs, audio_frames, labels_hm):
     raise NotImplementedError(f"loss {cfg.MODEL.LOSS_FUNC} is outside the CSTS hot path")
 
 
-def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None):
-    """Forward, loss, backward, clip, optimizer step.  Returns the (device) loss tensor; no host sync."""
+def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, grad_sync=None):
+    """Forward, loss, backward, [gradient exchange], clip, optimizer step.  Returns the (device) loss tensor;
+    no host sync.  With a DDP-wrapped model the exchange happens inside backward (DDP reducer); for an
+    un-wrapped replica pass grad_sync (e.g. distributed.allreduce_gradients) to average gradients here."""
     if lr is not None:
         for group in optimizer.param_groups:
             if torch.is_tensor(group["lr"]):
@@ -67,6 +69,8 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None):
     loss, _, _, _ = compute_loss(cfg, model, inputs, audio_frames, labels_hm)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
+    if grad_sync is not None:
+        grad_sync()
     if cfg.SOLVER.CLIP_GRAD_L2NORM:
         torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM, foreach=True)
     optimizer.step()
@@ -84,7 +88,12 @@ class GraphedTrainStep:
     """
 
     def __init__(self, cfg, model, optimizer, video, audio, labels_hm, warmup=3):
+        # Data parallel: the replica is stepped un-wrapped and gradients are averaged by captured NCCL
+        # all-reduces (DDP's reducer is host-driven and cannot be replayed from a graph); DDP's
+        # constructor has already broadcast rank 0's parameters.
         inner = model.module if hasattr(model, "module") else model
+        model = inner
+        self.grad_sync = (lambda: du.allreduce_gradients(list(inner.parameters()))) if du.get_world_size() > 1 else None
         dev = next(inner.parameters()).device
         self.cfg, self.model, self.optimizer = cfg, model, optimizer
         self.video = torch.empty(video.shape, dtype=torch.float32, device=dev)
@@ -95,14 +104,14 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):              # eager warm-up: lazy inits (func attributes, optimizer state, NCCL)
-                train_step(cfg, model, optimizer, [self.video], self.audio, self.labels)
+                train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         inner._wc.clear()                        # the bf16 weight casts must be part of the captured step
         optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss = train_step(cfg, model, optimizer, [self.video], self.audio, self.labels)
+            self.loss = train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync)
 
     def _load(self, video, audio, labels_hm):
         self.video.copy_(video[0] if isinstance(video, (list, tuple)) else video, non_blocking=True)
