@@ -145,9 +145,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_cfg(world)
     torch.manual_seed(cfg.RNG_SEED)
-    model = build_model(cfg)
-    model.train()
     use_graph = args.graph
+    model = build_model(cfg, ddp=not use_graph)
+    model.train()
     opt = construct_optimizer(model, cfg, capturable=use_graph)
     B = BATCH_PER_GPU
     # host batch in pinned memory (the public-API path) and a resident device copy

@@ -11,7 +11,10 @@ MODEL_REGISTRY.__doc__ = """Registry for video models: the registered object is 
 and returns a torch.nn.Module."""
 
 
-def build_model(cfg, gpu_id=None):
+def build_model(cfg, gpu_id=None, ddp=True):
+    """`ddp=False` (extension of the reference signature) returns the bare replica with rank 0's
+    parameters broadcast, for the CUDA-graph data-parallel step whose gradient exchange is a captured
+    NCCL all-reduce (train_step.GraphedTrainStep) instead of DDP's host-driven reducer."""
     from . import csts  # noqa: F401  (registers CSTS)
     if torch.cuda.is_available():
         assert cfg.NUM_GPUS <= torch.cuda.device_count(), "Cannot use more GPU devices than available"
@@ -21,6 +24,10 @@ def build_model(cfg, gpu_id=None):
     if cfg.NUM_GPUS:
         cur_device = torch.cuda.current_device() if gpu_id is None else gpu_id
         model = model.cuda(device=cur_device)
+    if cfg.NUM_GPUS > 1 and not ddp:
+        from . import distributed as du
+        du.broadcast_parameters(model)
+        return model
     if cfg.NUM_GPUS > 1:
         # Gradient all-reduce over NVLink/NVSwitch, bucketed and overlapped with backward.  Every
         # parameter receives a gradient when return_embed=True, so no unused-

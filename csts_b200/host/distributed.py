@@ -105,6 +105,15 @@ def allreduce_gradients(params, bucket_bytes=256 << 20):
             off += n
 
 
+def broadcast_parameters(model, src=0):
+    """Make every rank start from rank `src`'s parameters and buffers (what DDP's constructor does)."""
+    if get_world_size() == 1:
+        return
+    tensors = [p.data for p in model.parameters()] + [b.data for b in model.buffers()]
+    for t in tensors:
+        dist.broadcast(t, src=src)
+
+
 def init_distributed_training(cfg):
     """distributed.py:305-320 creates one process group per machine for SyncBN; CSTS has no
     BatchNorm, so nothing is needed beyond the default group."""
