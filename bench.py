@@ -225,10 +225,14 @@ def run_gpu(args):
     for _ in range(2):
         e2e_step()
     e2e_ms, _, _ = timed(e2e_step, args.steps)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    if world > 1:
+        # Tear down without destroying the NCCL communicator: destroying it while captured graphs still
+        # reference its kernels can dead-lock.  Ranks > 0 leave right after the last collective.
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank != 0:
+            sys.stdout.flush()
+            os._exit(0)
 
     clips = B * world * args.steps
     hbm_peak, tf_peak, peak_src = peaks()
@@ -258,8 +262,9 @@ def run_gpu(args):
         out["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
                                "sample": "2 timed fwd+loss+bwd steps at batch 2 of the same workload (oracle port, fp32)"}
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
