@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
     tap_coords<TRANSPOSED>(to, lt, p.Ti, ti, vt);
     tap_coords<TRANSPOSED>(ho, lh, p.Hi, hi, vh);
     tap_coords<TRANSPOSED>(wo, lw, p.Wi, wi, vw);
+    const bool any_tap = (vt[0] | vt[1] | vt[2]) & (vh[0] | vh[1] | vh[2]) & (vw[0] | vw[1] | vw[2]);
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
-      if (!vt[kt]) continue;
+      if (!any_tap || !vt[kt]) continue;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         if (!vh[kh]) continue;
@@ -155,16 +156,16 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 // Depthwise weight gradient:  dw[c][tap] += sum_{b,head,o} small[o][c] * big[o*s + tap - 1][c]
 // (conv: small = d(conv out), big = conv in;  transposed conv: small = conv in, big = d(out)).
 // ------------------------------------------------------------------------------------------------
-// Block = 9 warps; warp w owns the taps (kt, kh) = (w / 3, w % 3) x kw in {0,1,2}, so no cross-warp
-// reduction is needed and each lane carries only 3 x 4 accumulators per channel group (high
-// occupancy, 4 positions in flight).  Every block walks a contiguous range of `small` positions.
-template <int D>
-__global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, int lt, int lh, int lw, int pos_per_block) {
+// Block = 9 warps; warp w owns the tap row (kt, kh) = (w / 3, w % 3) with its 3 kw taps, so no
+// cross-warp reduction is needed and each lane carries only 3 x 4 accumulators per channel group.
+// A block walks a contiguous range of `small` ROWS (b, head, to, ho); inside a row the three kw taps
+// slide over `big` through registers: stride 1 re-uses two of three loads, stride 2 one of three.
+template <int D, int SW>
+__global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, int lt, int lh, int lw, int rows_per_block) {
   constexpr int NJ = (D + 127) / 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kt = warp / 3, kh = warp % 3;
-  const int Ls = p.Ts * p.Hs * p.Ws;
-  const int64_t total = (int64_t)p.B * p.heads * Ls;
+  const int64_t rows_total = (int64_t)p.B * p.heads * p.Ts * p.Hs;
   const bf16* small = reinterpret_cast<const bf16*>(p.small);
   const bf16* big = reinterpret_cast<const bf16*>(p.big);
   float acc[NJ][3][4];
@@ -174,47 +175,56 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
     for (int t = 0; t < 3; ++t)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][t][i] = 0.f;
-  const int64_t beg = (int64_t)blockIdx.x * pos_per_block;
-  const int64_t end = beg + pos_per_block < total ? beg + pos_per_block : total;
-  int wo = 0, ho = 0, to = 0, hd = 0, b = 0;
+  const int64_t beg = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t end = beg + rows_per_block < rows_total ? beg + rows_per_block : rows_total;
+  int ho = 0, to = 0, hd = 0, b = 0;
   if (beg < end) {
-    int o = (int)(beg % Ls);
-    int bh = (int)(beg / Ls);
-    hd = bh % p.heads; b = bh / p.heads;
-    wo = o % p.Ws; ho = (o / p.Ws) % p.Hs; to = o / (p.Ws * p.Hs);
+    int64_t r = beg;
+    ho = (int)(r % p.Hs); r /= p.Hs;
+    to = (int)(r % p.Ts); r /= p.Ts;
+    hd = (int)(r % p.heads); b = (int)(r / p.heads);
   }
-  // coordinates advance incrementally; `adv` runs at the top of every iteration but the first
-  bool first = true;
-#pragma unroll 2
-  for (int64_t idx = beg; idx < end; ++idx) {
-    if (!first) {
-      if (++wo == p.Ws) { wo = 0; if (++ho == p.Hs) { ho = 0; if (++to == p.Ts) { to = 0; if (++hd == p.heads) { hd = 0; ++b; } } } }
-    }
-    first = false;
-    const int o = (to * p.Hs + ho) * p.Ws + wo;
-    int ti = (to << lt) + kt - 1, hi = (ho << lh) + kh - 1;
-    if (ti < 0 || ti >= p.Tb || hi < 0 || hi >= p.Hb) continue;      // warp-uniform
-    const bf16* sp = small + b * p.small_sB + hd * p.small_sH + (int64_t)o * p.small_sP;
-    const bf16* row = big + b * p.big_sB + hd * p.big_sH + (int64_t)((ti * p.Hb + hi) * p.Wb) * p.big_sP;
-    const int w0 = (wo << lw) - 1;
+  for (int64_t row = beg; row < end; ++row) {
+    const int ti = (to << lt) + kt - 1, hi = (ho << lh) + kh - 1;
+    if (ti >= 0 && ti < p.Tb && hi >= 0 && hi < p.Hb) {                  // warp-uniform
+      const bf16* srow = small + b * p.small_sB + hd * p.small_sH + (int64_t)((to * p.Hs + ho) * p.Ws) * p.small_sP;
+      const bf16* brow = big + b * p.big_sB + hd * p.big_sH + (int64_t)((ti * p.Hb + hi) * p.Wb) * p.big_sP;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      int c = 4 * lane + 128 * j;
-      if (c < D) {
-        float sv[4];
-        ld4(sp + c, sv);
+      for (int j = 0; j < NJ; ++j) {
+        const int c = 4 * lane + 128 * j;
+        if (c >= D) continue;
+        auto ld_big = [&](int wi, float (&v)[4]) {
+          if (wi >= 0 && wi < p.Wb) ld4(brow + (int64_t)wi * p.big_sP + c, v);
+          else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+        };
+        float w0[4], w1[4], w2[4];           // big[wi0], big[wi0+1], big[wi0+2] with wi0 = wo*sw - 1
+        if (SW == 1) { ld_big(-1, w0); ld_big(0, w1); }
+        if (SW == 2) { ld_big(-1, w0); }
+#pragma unroll 4
+        for (int wo = 0; wo < p.Ws; ++wo) {
+          float sv[4];
+          ld4(srow + (int64_t)wo * p.small_sP + c, sv);
+          const int wi0 = (wo << lw) - 1;
+          if (SW == 1) ld_big(wi0 + 2, w2);
+          else if (SW == 2) { ld_big(wi0 + 1, w1); ld_big(wi0 + 2, w2); }
+          else { ld_big(wi0, w0); ld_big(wi0 + 1, w1); ld_big(wi0 + 2, w2); }
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          int wi = w0 + kw;
-          if (wi >= 0 && wi < p.Wb) {
-            float v[4];
-            ld4(row + (int64_t)wi * p.big_sP + c, v);
+          for (int i = 0; i < 4; ++i) {
+            acc[j][0][i] = fmaf(w0[i], sv[i], acc[j][0][i]);
+            acc[j][1][i] = fmaf(w1[i], sv[i], acc[j][1][i]);
+            acc[j][2][i] = fmaf(w2[i], sv[i], acc[j][2][i]);
+          }
+          if (SW == 1) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[j][kw][i] = fmaf(v[i], sv[i], acc[j][kw][i]);
+            for (int i = 0; i < 4; ++i) { w0[i] = w1[i]; w1[i] = w2[i]; }
+          } else if (SW == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w0[i] = w2[i];
           }
         }
       }
     }
+    if (++ho == p.Hs) { ho = 0; if (++to == p.Ts) { to = 0; if (++hd == p.heads) { hd = 0; ++b; } } }
   }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -453,12 +463,16 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   if (total == 0) return 0;
   int lt = log2_exact(p->st), lh = log2_exact(p->sh), lw = log2_exact(p->sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv_wgrad: strides must be powers of two");
-  // every block ends with 27*d global atomics: cap the grid at 2 blocks per SM, >= 32 positions each
-  int64_t want = (total + 31) / 32;
-  int grid = (int)(want < csts_num_sms() * 2 ? want : csts_num_sms() * 2);
-  int pos_per_block = (int)((total + grid - 1) / grid);
-  if (p->d == 96) dwconv_wgrad_kernel<96><<<grid, 288, 0, (cudaStream_t)stream>>>(*p, lt, lh, lw, pos_per_block);
-  else dwconv_wgrad_kernel<192><<<grid, 288, 0, (cudaStream_t)stream>>>(*p, lt, lh, lw, pos_per_block);
+  // every block ends with 27*d global atomics: cap the grid at 4 blocks per SM
+  const int64_t rows_total = (int64_t)p->B * p->heads * p->Ts * p->Hs;
+  int grid = (int)(rows_total < csts_num_sms() * 4 ? rows_total : csts_num_sms() * 4);
+  int rows_per_block = (int)((rows_total + grid - 1) / grid);
+  grid = (int)((rows_total + rows_per_block - 1) / rows_per_block);
+  cudaStream_t st = (cudaStream_t)stream;
+#define WGRAD(D_, SW_) dwconv_wgrad_kernel<D_, SW_><<<grid, 288, 0, st>>>(*p, lt, lh, lw, rows_per_block)
+  if (p->d == 96) { if (p->sw == 1) WGRAD(96, 1); else if (p->sw == 2) WGRAD(96, 2); else WGRAD(96, 0); }
+  else { if (p->sw == 1) WGRAD(192, 1); else if (p->sw == 2) WGRAD(192, 2); else WGRAD(192, 0); }
+#undef WGRAD
   return csts_check_launch("dwconv_wgrad");
 }
 

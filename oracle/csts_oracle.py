@@ -77,6 +77,101 @@ def arch_table(depth=16, embed_dim=96, num_heads=1,
 
 
 ARCH = arch_table()
+
+# --------------------------------------------------------------------------------------------
+# Optional bf16 emulation.  With EMULATE_BF16 = True the oracle inserts round-to-bf16 at exactly the
+# tensors that csts_b200 stores in bf16 (GEMM operands, saved activations and the operand
+# gradients of backward), while accumulation, the residual stream, statistics and parameter
+# gradients stay f32 — the precision contract of DESIGN.md §3.  Comparing the CUDA path with this
+# variant separates *implementation* error (must be ~1e-3) from *rounding-policy* error (what the
+# plain fp32 oracle measures).  Off by default: the oracle proper is fp32.
+# --------------------------------------------------------------------------------------------
+EMULATE_BF16 = False
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return _bf(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf(g)
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf(g)
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return _bf(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _GeluSavedBf16(torch.autograd.Function):
+    """gelu(z) in f32 whose backward evaluates gelu' at the bf16-rounded pre-activation (the saved Z)."""
+
+    @staticmethod
+    def forward(ctx, z):
+        ctx.save_for_backward(_bf(z))
+        return F.gelu(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        (zb,) = ctx.saved_tensors
+        cdf = 0.5 * (1 + torch.erf(zb * 0.7071067811865476))
+        pdf = 0.3989422804014327 * torch.exp(-0.5 * zb * zb)
+        return g * (cdf + zb * pdf)
+
+
+class _SoftmaxSavedBf16(torch.autograd.Function):
+    """softmax whose output is stored in bf16 and whose backward uses that stored value."""
+
+    @staticmethod
+    def forward(ctx, s):
+        p = _bf(s.softmax(dim=-1))
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        return p * (g - (g * p).sum(-1, keepdim=True))
+
+
+def rnd(t):      # stored in bf16, gradient stored in bf16
+    return _RoundBoth.apply(t) if EMULATE_BF16 else t
+
+
+def rnd_f(t):    # stored in bf16 (forward only)
+    return _RoundFwd.apply(t) if EMULATE_BF16 else t
+
+
+def rnd_b(t):    # gradient arriving here is cast to bf16 before it feeds the backward GEMMs
+    return _RoundBwd.apply(t) if EMULATE_BF16 else t
+
+
+def _gelu(z):
+    return _GeluSavedBf16.apply(z) if EMULATE_BF16 else F.gelu(z)
+
+
+def _softmax(s):
+    return _SoftmaxSavedBf16.apply(s) if EMULATE_BF16 else s.softmax(dim=-1)
 EPS_BLOCK = 1e-6   # norm1/norm2: partial(nn.LayerNorm, eps=1e-6), ref custom_multimodal_builder.py:61
 EPS_POOL = 1e-5    # norm_q/k/v: plain nn.LayerNorm, ref attention.py:206 (SURVEY.md App. C)
 
@@ -114,7 +209,7 @@ def pool_tokens(t, thw, w, stride, ln_w, ln_b, transposed=False):
     else:
         g = F.conv3d(g, w, None, stride=stride, padding=1, groups=d)
     t, thw = _from_grid(g, B, h)
-    t = F.layer_norm(t, (d,), ln_w, ln_b, EPS_POOL)
+    t = rnd(F.layer_norm(rnd(t), (d,), ln_w, ln_b, EPS_POOL))
     return t, thw
 
 
@@ -140,7 +235,7 @@ def attention(sd, pfx, x, thw, heads, stride_q, stride_kv, kind, want_attn=False
     """
     B, N, C = x.shape
     d = C // heads
-    qkv = F.linear(x, sd[pfx + "qkv.weight"], sd[pfx + "qkv.bias"])
+    qkv = rnd(F.linear(x, rnd_f(sd[pfx + "qkv.weight"]), sd[pfx + "qkv.bias"]))
     qkv = qkv.reshape(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
     q_thw = thw
@@ -155,12 +250,12 @@ def attention(sd, pfx, x, thw, heads, stride_q, stride_kv, kind, want_attn=False
                            sd[pfx + "norm_k.weight"], sd[pfx + "norm_k.bias"])
         v, _ = pool_tokens(v, thw, sd[pfx + "pool_v.weight"], stride_kv,
                            sd[pfx + "norm_v.weight"], sd[pfx + "norm_v.bias"])
-    s = (q @ k.transpose(-2, -1)) * (d ** -0.5)
+    s = rnd_b(q @ k.transpose(-2, -1)) * (d ** -0.5)
     if kind == "spatial":
         s = s - spatial_mask(thw, s.device)
-    p = s.softmax(dim=-1)
-    o = (p @ v).transpose(1, 2).reshape(B, q.shape[2], C)
-    o = F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])
+    p = _softmax(s)
+    o = rnd((p @ v).transpose(1, 2).reshape(B, q.shape[2], C))
+    o = rnd_b(F.linear(o, rnd_f(sd[pfx + "proj.weight"]), sd[pfx + "proj.bias"]))
     return (o, q_thw, p) if want_attn else (o, q_thw)
 
 
@@ -186,22 +281,22 @@ def block(sd, name, x, thw, want_attn=False, spec=None):
     `spec` = (kind, dim, dim_out, heads, stride_q, stride_kv) overrides the ARCH row (unit tests)."""
     kind, dim, dim_out, heads, sq, skv = spec if spec is not None else ARCH[name][1:]
     p = name + "."
-    xn = F.layer_norm(x, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], EPS_BLOCK)
+    xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], EPS_BLOCK))
     res = attention(sd, p + "attn.", xn, thw, heads, sq, skv, kind, want_attn)
     x = skip_path(x, thw, kind, sq) + res[0]
-    xn = F.layer_norm(x, (dim,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], EPS_BLOCK)
+    xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], EPS_BLOCK))
     # decoder MLP hidden is 4*dim_out (ref attention.py:444) — implied by the weight shapes
-    hid = F.gelu(F.linear(xn, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))     # exact erf
-    mlp = F.linear(hid, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    hid = rnd_f(_gelu(rnd_b(F.linear(xn, rnd_f(sd[p + "mlp.fc1.weight"]), sd[p + "mlp.fc1.bias"]))))     # exact erf
+    mlp = rnd_b(F.linear(hid, rnd_f(sd[p + "mlp.fc2.weight"]), sd[p + "mlp.fc2.bias"]))
     if dim != dim_out:
-        x = F.linear(xn, sd[p + "proj.weight"], sd[p + "proj.bias"])                  # ref :245-246
+        x = rnd_b(F.linear(xn, rnd_f(sd[p + "proj.weight"]), sd[p + "proj.bias"]))    # ref :245-246
     x = x + mlp
     return (x, res[1], res[2]) if want_attn else (x, res[1])
 
 
 def patch_embed(sd, name, x):
     """ref: stem_helper.py:35-38 — Conv3d k(3,7,7) s(2,4,4) p(1,3,3), flatten, transpose."""
-    y = F.conv3d(x, sd[name + ".proj.weight"], sd[name + ".proj.bias"], stride=(2, 4, 4), padding=(1, 3, 3))
+    y = rnd_b(F.conv3d(rnd_f(x), rnd_f(sd[name + ".proj.weight"]), sd[name + ".proj.bias"], stride=(2, 4, 4), padding=(1, 3, 3)))
     return y.flatten(2).transpose(1, 2)
 
 
@@ -215,8 +310,8 @@ def frame_pool(sd, name, tok, thw):
     """Dense Conv3d(768,768,(1,8,8)) over a (B, T*8*8, C) token map -> (B, T, C).
     ref: custom_multimodal_builder.py:227-229, :420-421."""
     B, N, C = tok.shape
-    g = tok.reshape(B, *thw, C).permute(0, 4, 1, 2, 3)
-    y = F.conv3d(g, sd[name + ".weight"], sd[name + ".bias"])
+    g = rnd_f(tok).reshape(B, *thw, C).permute(0, 4, 1, 2, 3)
+    y = rnd_b(F.conv3d(g, rnd_f(sd[name + ".weight"]), sd[name + ".bias"]))
     return y.squeeze(-1).squeeze(-1).permute(0, 2, 1)
 
 
@@ -273,8 +368,8 @@ def csts_forward(sd, video, audio, return_embed=False, return_intermediates=Fals
     logits = F.conv3d(f, sd["classifier.weight"], sd["classifier.bias"])             # ref :481
     out = [logits]
     if return_embed:                                                                  # ref :493-498
-        out.append(F.linear(xw.mean(dim=1), sd["vision_proj.weight"], sd["vision_proj.bias"]))
-        out.append(F.linear(yw.mean(dim=1), sd["audio_proj.weight"], sd["audio_proj.bias"]))
+        out.append(rnd_b(F.linear(rnd_f(xw.mean(dim=1)), rnd_f(sd["vision_proj.weight"]), sd["vision_proj.bias"])))
+        out.append(rnd_b(F.linear(rnd_f(yw.mean(dim=1)), rnd_f(sd["audio_proj.weight"]), sd["audio_proj.bias"])))
     if return_intermediates:
         return out, inter
     return out if return_embed else logits

@@ -170,6 +170,54 @@ def test_full_model_against_reference_golden(golden_dir, fixture, gain):
         assert rel_err(model.get_parameter(n).grad, g.to(dev)) <= 0.5, n
 
 
+def test_full_model_against_bf16_emulating_oracle(golden_dir):
+    """Implementation error vs rounding-policy error.  The oracle with EMULATE_BF16 rounds exactly the
+    tensors csts_b200 stores in bf16 (and nothing else); what remains between it and the CUDA path is
+    accumulation order, the transcendental implementations and a few double roundings."""
+    import csts_oracle as O
+    from csts_b200.host.build import build_model
+    shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
+    sd = O.synthetic_state(shapes, seed=0, gain=1.0)
+    model = build_model(make_cfg())
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    video, audio, hm = (t.to(dev) for t in O.synthetic_batch(2, seed=1))
+    loss, kld, nce, logits, v, a = _train_step(model, video, audio, hm, 0.05)
+    loss.backward()
+    sd_gpu = {k: t.to(dev) for k, t in sd.items()}
+    O.EMULATE_BF16 = True
+    try:
+        e_loss, _, _, e_logits, e_grads = O.loss_and_grads(sd_gpu, video, audio, hm, alpha=0.05)
+    finally:
+        O.EMULATE_BF16 = False
+    f_loss, _, _, f_logits, f_grads = O.loss_and_grads(sd_gpu, video, audio, hm, alpha=0.05)
+
+    def global_rel(ga, gb):
+        num = sum((ga[n].float() - gb[n]).pow(2).sum().item() for n in gb)
+        den = sum(gb[n].pow(2).sum().item() for n in gb)
+        return (num / den) ** 0.5
+
+    ours = {n: p.grad for n, p in model.named_parameters()}
+    per = sorted(((rel_err(ours[n], e_grads[n]), n) for n in e_grads if f_grads[n].norm() > 1e-6), reverse=True)
+    report = {
+        "logits_mean_abs_vs_emulated": (logits - e_logits).abs().mean().item(),
+        "logits_mean_abs_vs_fp32": (logits - f_logits).abs().mean().item(),
+        "emulated_vs_fp32_logits_mean_abs": (e_logits - f_logits).abs().mean().item(),
+        "grad_global_rel_vs_emulated": global_rel(ours, e_grads),
+        "grad_global_rel_vs_fp32": global_rel(ours, f_grads),
+        "emulated_vs_fp32_grad_global_rel": global_rel(e_grads, f_grads),
+        "grad_median_vs_emulated": per[len(per) // 2][0],
+        "grad_worst_vs_emulated": [(round(e, 5), n) for e, n in per[:8]],
+    }
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "parity_bf16_emulation.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps(report, indent=1))
+    # the CUDA path must sit much closer to the bf16-emulating oracle than to the fp32 one
+    assert report["grad_global_rel_vs_emulated"] <= 2e-2, report
+    assert report["logits_mean_abs_vs_emulated"] <= 1e-3, report
+
+
 def test_eval_forward_matches_train_forward_without_droppath(model_and_state):
     import csts_oracle as O
     model, sd = model_and_state
