@@ -74,12 +74,31 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return red[32];
 }
 
-// exact (erf) GELU and its derivative — nn.GELU() default, ref slowfast/models/common.py:21
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf-based GELU (nn.GELU() default, ref slowfast/models/common.py:21) and its derivative.
+// erf is evaluated with Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7 — below f32 round-off of the
+// surrounding arithmetic and far below the bf16 storage of the result): one reciprocal, one ex2 and six
+// FMAs instead of libm's branchy erff; exp(-x^2/2) is shared between erf(x/sqrt2) and the Gaussian pdf.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float y = fabsf(x) * 0.70710678118654752f;
+  const float e = __expf(-y * y);                                  // exp(-x^2/2)
+  const float t = __fdividef(1.f, fmaf(0.3275911f, y, 1.f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.f);                   // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 
 // typed element access: T in {float, bf16}
