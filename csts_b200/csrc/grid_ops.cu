@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
   const bf16* in = reinterpret_cast<const bf16*>(p.in);
   bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* pre = reinterpret_cast<bf16*>(p.pre);
+  const int sW = (int)p.in_sP, sH = p.Wi * sW, sT = p.Hi * sH;      // input strides in elements (32-bit)
 
   // each warp walks a contiguous range of output positions: coordinates are decoded once and then
   // advanced incrementally (no per-position division)
@@ -76,25 +77,30 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
     tap_coords<TRANSPOSED>(ho, lh, p.Hi, hi, vh);
     tap_coords<TRANSPOSED>(wo, lw, p.Wi, wi, vw);
     const bool any_tap = (vt[0] | vt[1] | vt[2]) & (vh[0] | vh[1] | vh[2]) & (vw[0] | vw[1] | vw[2]);
+    // 32-bit element offsets per axis (the whole (b, head) slab is < 2^31 elements, checked on the host):
+    // one add per tap instead of 64-bit multiplies
+    int ot[3], oh[3], ow[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ot[k] = ti[k] * sT; oh[k] = hi[k] * sH; ow[k] = wi[k] * sW; }
+    const bf16* pl = in_bh + 4 * lane;
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
       if (!any_tap || !vt[kt]) continue;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         if (!vh[kh]) continue;
-        const bf16* row = in_bh + (int64_t)((ti[kt] * p.Hi + hi[kh]) * p.Wi) * p.in_sP;
+        const int orow = ot[kt] + oh[kh];
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           if (!vw[kw]) continue;
-          const bf16* src = row + (int64_t)wi[kw] * p.in_sP;
-          const float* wt = s_w + ((kt * 3 + kh) * 3 + kw) * D;
+          const bf16* src = pl + (orow + ow[kw]);
+          const float* wt = s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane;
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            int c = 4 * lane + 128 * j;
-            if (c < D) {
+            if (4 * lane + 128 * j < D) {
               float v[4], w4[4];
-              ld4(src + c, v);
-              ld4(wt + c, w4);
+              ld4(src + 128 * j, v);
+              ld4(wt + 128 * j, w4);
 #pragma unroll
               for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(v[i], w4[i], acc[j][i]);
             }
@@ -193,8 +199,11 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
       for (int j = 0; j < NJ; ++j) {
         const int c = 4 * lane + 128 * j;
         if (c >= D) continue;
+        const bf16* bcol = brow + c;
+        const bf16* scol = srow + c;
+        const int bsP = (int)p.big_sP, ssP = (int)p.small_sP;
         auto ld_big = [&](int wi, float (&v)[4]) {
-          if (wi >= 0 && wi < p.Wb) ld4(brow + (int64_t)wi * p.big_sP + c, v);
+          if (wi >= 0 && wi < p.Wb) ld4(bcol + wi * bsP, v);
           else { v[0] = v[1] = v[2] = v[3] = 0.f; }
         };
         float w0[4], w1[4], w2[4];           // big[wi0], big[wi0+1], big[wi0+2] with wi0 = wo*sw - 1
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
 #pragma unroll 4
         for (int wo = 0; wo < p.Ws; ++wo) {
           float sv[4];
-          ld4(srow + (int64_t)wo * p.small_sP + c, sv);
+          ld4(scol + wo * ssP, sv);
           const int wi0 = (wo << lw) - 1;
           if (SW == 1) ld_big(wi0 + 2, w2);
           else if (SW == 2) { ld_big(wi0 + 1, w1); ld_big(wi0 + 2, w2); }
@@ -454,6 +463,7 @@ int csts_dwconv(const csts_pool_args* p, void* stream) {
   CSTS_REQUIRE(((uintptr_t)p->in & 7) == 0 && ((uintptr_t)p->out & 7) == 0, "dwconv: in/out must be 8-byte aligned");
   if (p->gamma) CSTS_REQUIRE(p->beta && p->pre && p->mean && p->rstd, "dwconv: norm epilogue needs beta/pre/mean/rstd");
   if ((int64_t)p->B * p->heads * p->To * p->Ho * p->Wo == 0) return 0;
+  CSTS_REQUIRE((int64_t)p->Ti * p->Hi * p->Wi * p->in_sP < (1LL << 31), "dwconv: one (batch, head) slab must stay below 2^31 elements");
   return p->d == 96 ? launch_dwconv<96>(*p, (cudaStream_t)stream) : launch_dwconv<192>(*p, (cudaStream_t)stream);
 }
 

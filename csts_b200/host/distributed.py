@@ -105,6 +105,73 @@ def allreduce_gradients(params, bucket_bytes=256 << 20):
             off += n
 
 
+class OverlappedGradSync:
+    """Gradient averaging overlapped with backward, as plain stream-ordered work (graph-capturable).
+
+    Parameters are split into groups in reverse registration order (~ the order backward finishes
+    them).  A post-accumulate-grad hook counts down each group; when a group is complete its
+    gradients are packed and all-reduced (NCCL, AVG) on a side stream while backward keeps running on
+    the main stream.  `finish()` joins the side stream before the clip / optimizer step.  The three
+    151 MB frame-pool kernels become ready after the decoder + fusion backward (~1/3 of the way), so
+    their exchange hides behind the encoder backward.
+    """
+
+    def __init__(self, model, group_bytes=(64 << 20, 512 << 20, 1 << 40)):
+        self.params = [p for p in model.parameters() if p.requires_grad][::-1]
+        self.groups, cur, size, gi = [], [], 0, 0
+        for p in self.params:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= group_bytes[min(gi, len(group_bytes) - 1)]:
+                self.groups.append(cur)
+                cur, size, gi = [], 0, gi + 1
+        if cur:
+            self.groups.append(cur)
+        self.group_of = {id(p): g for g, ps in enumerate(self.groups) for p in ps}
+        self.pending = [0] * len(self.groups)
+        self.stream = None
+        self.enabled = False
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def start(self):
+        """Call right before loss.backward()."""
+        if get_world_size() == 1:
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        self.pending = [len(g) for g in self.groups]
+        self.enabled = True
+
+    def _hook(self, param):
+        if not self.enabled:
+            return
+        g = self.group_of[id(param)]
+        self.pending[g] -= 1
+        if self.pending[g] == 0:
+            self._reduce(self.groups[g])
+
+    def _reduce(self, group):
+        main = torch.cuda.current_stream()
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            flat = torch.cat([p.grad.reshape(-1) for p in group])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            off = 0
+            for p in group:
+                n = p.numel()
+                p.grad = flat[off: off + n].view_as(p)
+                off += n
+
+    def finish(self):
+        """Call after loss.backward(): joins the exchange before gradients are consumed."""
+        if not self.enabled:
+            return
+        self.enabled = False
+        assert all(c == 0 for c in self.pending), "a parameter received no gradient"
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
 def broadcast_parameters(model, src=0):
     """Make every rank start from rank `src`'s parameters and buffers (what DDP's constructor does)."""
     if get_world_size() == 1:

@@ -68,9 +68,14 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, 
                 group["lr"] = lr
     loss, _, _, _ = compute_loss(cfg, model, inputs, audio_frames, labels_hm)
     optimizer.zero_grad(set_to_none=True)
-    loss.backward()
-    if grad_sync is not None:
-        grad_sync()
+    if hasattr(grad_sync, "start"):          # OverlappedGradSync: exchange runs during backward
+        grad_sync.start()
+        loss.backward()
+        grad_sync.finish()
+    else:
+        loss.backward()
+        if grad_sync is not None:
+            grad_sync()
     if cfg.SOLVER.CLIP_GRAD_L2NORM:
         torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM, foreach=True)
     optimizer.step()
@@ -93,7 +98,13 @@ class GraphedTrainStep:
         # constructor has already broadcast rank 0's parameters.
         inner = model.module if hasattr(model, "module") else model
         model = inner
-        self.grad_sync = (lambda: du.allreduce_gradients(list(inner.parameters()))) if du.get_world_size() > 1 else None
+        self.grad_sync = None
+        if du.get_world_size() > 1:
+            import os
+            if os.environ.get("CSTS_OVERLAP_ALLREDUCE", "1") == "1":
+                self.grad_sync = du.OverlappedGradSync(inner)
+            else:
+                self.grad_sync = lambda: du.allreduce_gradients(list(inner.parameters()))
         dev = next(inner.parameters()).device
         self.cfg, self.model, self.optimizer = cfg, model, optimizer
         self.video = torch.empty(video.shape, dtype=torch.float32, device=dev)
