@@ -203,7 +203,7 @@ __device__ __forceinline__ void stage_store(uint32_t stage, unsigned char* gbase
   }
 }
 
-enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32_ATOMIC = 4 };
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32_ATOMIC = 4, EPI_SOFTMAX = 5, EPI_DSOFTMAX = 6 };
 
 // One 32-column slice of the accumulator rows owned by this warp -> epilogue math -> global memory.
 // m0 = first row of the warp's 32-row band, n0 = first column, `stage` = the warp's staging tile.
@@ -319,6 +319,90 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
   __syncwarp();
 }
 
+// Fused attention-softmax epilogues for key counts that fit one tile (N = Lk <= BN <= 256): a warp owns
+// 32 complete rows (lane = row), so the row reductions need no cross-lane traffic at all.
+//   EPI_SOFTMAX : acc = q.k^T          -> C = P  = softmax(alpha * acc)                (bf16, pad columns zero)
+//   EPI_DSOFTMAX: acc = dO.v^T (= dP)  -> C = dS = alpha * P o (dP - rowsum(dP o P))   (P read from Z)
+// replacing the f32 S / dP round trips through HBM and the separate softmax kernels (attention.py:154-155).
+template <int EPI>
+__device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, uint32_t stage, int m0, int lane, uint32_t trow) {
+  const int rows_valid = min(32, p.M - m0);
+  const int ncols = p.N, nstore = (int)p.ldc;
+  unsigned char* cg = reinterpret_cast<unsigned char*>(p.C) + (coff + (int64_t)m0 * p.ldc) * 2;
+  const unsigned char* pg = reinterpret_cast<const unsigned char*>(p.Z) + (coff + (int64_t)m0 * p.ldz) * 2;
+  float m = -INFINITY, l = 0.f, dot = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 32) {
+    uint32_t r[32];
+    if (EPI == EPI_DSOFTMAX) stage_load(stage, pg + c * 2, p.ldz * 2, rows_valid, min(32, nstore - c) * 2, lane);
+    tmem_ld32(trow + c, r);
+    tmem_ld_wait();
+    if (EPI == EPI_SOFTMAX) {
+      float mloc = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = (c + i < ncols) ? __uint_as_float(r[i]) * p.alpha : -INFINITY;
+        r[i] = __float_as_uint(v);
+        mloc = fmaxf(mloc, v);
+      }
+      const float mnew = fmaxf(m, mloc);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum += __expf(__uint_as_float(r[i]) - mnew);
+      l = l * __expf(m - mnew) + sum;
+      m = mnew;
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 t = lds128(stage_addr(stage, lane, j));
+        const bf162* pp = reinterpret_cast<const bf162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int col = c + 8 * j + 2 * i;
+          if (col < ncols) dot = fmaf(__low2float(pp[i]), __uint_as_float(r[8 * j + 2 * i]), dot);
+          if (col + 1 < ncols) dot = fmaf(__high2float(pp[i]), __uint_as_float(r[8 * j + 2 * i + 1]), dot);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  const float inv = 1.f / l;
+#pragma unroll 1
+  for (int c = 0; c < nstore; c += 32) {
+    uint32_t r[32];
+    float v[32];
+    if (EPI == EPI_DSOFTMAX) stage_load(stage, pg + c * 2, p.ldz * 2, rows_valid, min(32, nstore - c) * 2, lane);
+    tmem_ld32(trow + c, r);
+    tmem_ld_wait();
+    if (EPI == EPI_SOFTMAX) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (c + i < ncols) ? __expf(__uint_as_float(r[i]) * p.alpha - m) * inv : 0.f;
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 t = lds128(stage_addr(stage, lane, j));
+        const bf162* pp = reinterpret_cast<const bf162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int col = c + 8 * j + 2 * i;
+          v[8 * j + 2 * i] = (col < ncols) ? p.alpha * __low2float(pp[i]) * (__uint_as_float(r[8 * j + 2 * i]) - dot) : 0.f;
+          v[8 * j + 2 * i + 1] = (col + 1 < ncols) ? p.alpha * __high2float(pp[i]) * (__uint_as_float(r[8 * j + 2 * i + 1]) - dot) : 0.f;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+    __syncwarp();
+    stage_store<false>(stage, cg + c * 2, p.ldc * 2, rows_valid, min(32, nstore - c) * 2, lane);
+    __syncwarp();
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
@@ -344,7 +428,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, NUM_EPI_WARPS); }
+    constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX;      // one warp per quadrant drains a tile
+    for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, ROWS ? 4 : NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
@@ -433,6 +518,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int sub = (warp - 2) >> 2;                 // which of the quadrant's three warps
     const uint32_t stage_buf = smem_u32(sStage) + (warp - 2) * (32 * 128);
+    if (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) {
+      // whole-row epilogues: the quadrant's warps take turns on successive tiles (tile seq -> warp seq % NSUB),
+      // so up to NSUB tiles per quadrant are drained concurrently and no cross-warp reduction exists
+      constexpr int NSUB = C::NACC < 3 ? C::NACC : 3;
+      int seq = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++seq) {
+        if (sub >= NSUB || seq % NSUB != sub) continue;
+        const int as = seq % C::NACC;
+        const uint32_t aphase = (uint32_t)(seq / C::NACC) & 1u;
+        int tm, tn, z, kb0, kb1;
+        decode(item, tm, tn, z, kb0, kb1);
+        const int64_t coff = (int64_t)(z / p.batch2) * p.sC1 + (int64_t)(z % p.batch2) * p.sC2;
+        const int m0 = tm * BM + quad * 32;
+        mbar_wait(tfull0 + 8 * as, aphase);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+        if (m0 < p.M) softmax_rows<EPI>(p, coff, stage_buf, m0, lane, trow);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      }
+    } else {
     int as = 0; uint32_t aphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tm, tn, z, kb0, kb1;
@@ -449,12 +556,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c = sub * 32; c < BN; c += (NUM_EPI_WARPS / 4) * 32) {
         const int n0 = tn * BN + c;
         if (!live || n0 >= p.N) continue;
-        epilogue_slice<EPI>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0);
+        epilogue_slice<(EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) ? EPI_BF16 : EPI>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs,
+                                                                                       split == 0);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       if (++as == C::NACC) { as = 0; aphase ^= 1; }
+    }
     }
   }
 
@@ -588,11 +697,18 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   // coalesced epilogue: 16-byte aligned rows, whole 16-byte chunks
   if (((uintptr_t)a.C & 15) || (a.ldc * cbytes) % 16 || ((int64_t)a.N * cbytes) % 16) return false;
   if (nb > 1 && (((a.sC1 | a.sC2) * cbytes) % 16 != 0)) return false;
-  if (a.Z && (nb > 1 || ((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
+  if (a.Z && a.act != 4 && (nb > 1 || ((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
   if (a.residual && (nb > 1 || ((uintptr_t)a.residual & 15) || (a.ldr * 4) % 16)) return false;
   if (a.res_mod > 0 && a.res_mod % 32 != 0) return false;
   if (a.bias && (((uintptr_t)a.bias & 15) || a.N % 4 != 0)) return false;
   if (a.split_k > 1 && (a.c_dtype != 0 || a.act != 0 || a.row_scale)) return false;
+  if (a.act == 3 || a.act == 4) {                      // fused softmax / softmax-backward rows
+    if (!a.a_kmajor || !a.b_kmajor || a.c_dtype != 1 || a.N > 256 || a.bias || a.residual || a.accumulate || a.row_scale ||
+        a.split_k > 1 || a.ldc % 8 != 0 || a.ldc < a.N || a.M < 64)
+      return false;
+    if (a.act == 4 && (!a.Z || a.ldz != a.ldc || ((uintptr_t)a.Z & 15))) return false;
+    return true;
+  }
   if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with bf16 outputs only
   if (a.act != 0 && (a.accumulate || a.residual)) return false;
   if (a.c_dtype != 0 && a.residual) return false;
@@ -604,6 +720,24 @@ int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
   CSTS_REQUIRE(csts_gemm_tc_supported(a), "gemm_tc: unsupported problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   if (a.act == 2) CSTS_REQUIRE(a.Z != nullptr, "gemm: act==2 needs Z");
   const bool atomic = effective_splits(a) > 1;
+  if (a.act == 3 || a.act == 4) {
+    // single column tile: the narrowest tile width that holds all N keys
+    const int bn = a.N <= 96 ? 96 : (a.N <= 128 ? 128 : (a.N <= 192 ? 192 : 256));
+    if (a.act == 3) {
+      switch (bn) {
+        case 96: return launch<96, false, false, EPI_SOFTMAX>(a, stream);
+        case 128: return launch<128, false, false, EPI_SOFTMAX>(a, stream);
+        case 192: return launch<192, false, false, EPI_SOFTMAX>(a, stream);
+        default: return launch<256, false, false, EPI_SOFTMAX>(a, stream);
+      }
+    }
+    switch (bn) {
+      case 96: return launch<96, false, false, EPI_DSOFTMAX>(a, stream);
+      case 128: return launch<128, false, false, EPI_DSOFTMAX>(a, stream);
+      case 192: return launch<192, false, false, EPI_DSOFTMAX>(a, stream);
+      default: return launch<256, false, false, EPI_DSOFTMAX>(a, stream);
+    }
+  }
   if (!a.a_kmajor) {                                    // (MN, MN): weight gradients, dV / dK of attention
     if (a.c_dtype == 1) return dispatch<true, true, EPI_BF16>(a, stream);
     return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);

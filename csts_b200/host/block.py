@@ -97,14 +97,21 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     # ---- attention: S = scale * q k^T -> softmax (+ in-frame mask) -> P v ---------------------
     ldS = (Lk + 7) // 8 * 8
     scale = d ** -0.5
-    S = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=x.device)
-    K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=S, ldc=ldS, alpha=scale, batch=(B, h),
-           sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
-    if spec.kind == "spatial":
-        P = K.softmax_fwd(S, Lk, ldS, nq=Lq, mask_hw=thw[1] * thw[2], mask_t=thw[0])
+    # Lk <= 256 (20 of the 26 blocks): softmax runs in the epilogue of the q.k^T kernel, S never reaches HBM
+    fused_softmax = Lk <= 256 and Lq >= 64 and spec.kind != "spatial"
+    if fused_softmax:
+        P = torch.empty((B, h, Lq, ldS), dtype=torch.bfloat16, device=x.device)
+        K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=P, ldc=ldS, alpha=scale, act=3, batch=(B, h),
+               sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
     else:
-        P = K.softmax_fwd(S, Lk, ldS, nq=Lq)
-    del S
+        S = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=x.device)
+        K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=S, ldc=ldS, alpha=scale, batch=(B, h),
+               sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
+        if spec.kind == "spatial":
+            P = K.softmax_fwd(S, Lk, ldS, nq=Lq, mask_hw=thw[1] * thw[2], mask_t=thw[0])
+        else:
+            P = K.softmax_fwd(S, Lk, ldS, nq=Lq)
+        del S
     Mq = B * Lq
     o = torch.empty((Mq, C), dtype=torch.bfloat16, device=x.device)
     K.gemm(P, v.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=v.sP, out=o, ldc=C, batch=(B, h),
@@ -137,7 +144,8 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     if not save:
         return y, thw_q, None, attn
     sv.update(x=x, thw=tuple(thw), mean1=mean1, rstd1=rstd1, xn1=xn1, qkv=qkv, q=q, k=k, v=v, P=P, o=o, arg=arg,
-              x1=x1, mean2=mean2, rstd2=rstd2, xn2=xn2, Z=Z, hdn=hdn, dp=dp_scale, Lq=Lq, Lk=Lk, ldS=ldS, thw_q=thw_q)
+              x1=x1, mean2=mean2, rstd2=rstd2, xn2=xn2, Z=Z, hdn=hdn, dp=dp_scale, Lq=Lq, Lk=Lk, ldS=ldS, thw_q=thw_q,
+              fused_softmax=fused_softmax)
     return y, thw_q, sv, attn
 
 
@@ -219,11 +227,17 @@ def block_backward(spec, p, wc, sv, dy):
     sP = (h * Lq * ldS, Lq * ldS)
     dv_t, tgt = grad_target(pooled_kv, Lk, 2)
     K.gemm(P, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=C, batch=(B, h), sA=sP, sB=(Lq * C, d), **tgt)
-    dP = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=dev)
-    K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP,
-           b_off=v.off)
-    dS = K.softmax_bwd(P, dP, Lk, d ** -0.5)
-    del dP
+    if sv["fused_softmax"]:
+        # dS = scale * P o (dP - rowsum(dP o P)) in the epilogue of the dO.v^T kernel: dP never reaches HBM
+        dS = torch.empty_like(P)
+        K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dS, ldc=ldS, alpha=d ** -0.5, act=4, Z=P, batch=(B, h),
+               sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP, b_off=v.off)
+    else:
+        dP = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=dev)
+        K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP,
+               b_off=v.off)
+        dS = K.softmax_bwd(P, dP, Lk, d ** -0.5)
+        del dP
     dq_t, tgt = grad_target(pooled_q, Lq, 0)
     K.gemm(dS, k.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=k.sP, batch=(B, h), sA=sP, sB=(k.sB, k.sH), b_off=k.off, **tgt)
     dk_t, tgt = grad_target(pooled_kv, Lk, 1)

@@ -54,7 +54,8 @@ typedef struct csts_gemm_args {
   int32_t a_kmajor;       /* 1: A[m*lda + k]   0: A[k*lda + m] */
   int32_t b_kmajor;       /* 1: B[n*ldb + k]   0: B[k*ldb + n] */
   int32_t c_dtype;        /* 0 f32, 1 bf16 */
-  int32_t act;            /* 0 none, 1 exact-erf GELU (nn.GELU(), common.py:21), 2 times GELU'(Z) */
+  int32_t act;            /* 0 none, 1 erf GELU (nn.GELU(), common.py:21), 2 times GELU'(Z),
+                             3 row softmax of alpha*acc (N <= 256, bf16 C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)) */
   int32_t accumulate;     /* C += result */
   int32_t res_mod;
   int32_t split_k;        /* > 1: partial sums combined with f32 atomics (C must be f32) */

@@ -150,6 +150,21 @@ def test_gemm_attention_shapes(backend, Lq, Lk, heads):
            sA=(heads * Lq * ldS, Lq * ldS), sB=(heads * Lk * d, Lk * d), sC=(Lq * 3 * Cn, d), backend=backend)
     assert rel_err(dq[:, :, 0].permute(0, 2, 1, 3), P[..., :Lk].float() @ kk.float()) < 4e-3
     assert torch.all(dq[:, :, 1:] == 0)
+    if backend == 2 and Lk <= 256:
+        # fused epilogues: softmax inside q.k^T, softmax-backward inside dO.v^T
+        Pf = torch.full((B, heads, Lq, ldS), float("nan"), dtype=torch.bfloat16, device=dev)
+        k.gemm(qkv, kk, M=Lq, N=Lk, K=d, lda=3 * Cn, ldb=d, out=Pf, ldc=ldS, alpha=0.25, act=3, batch=(B, heads),
+               sA=(Lq * 3 * Cn, d), sB=(heads * Lk * d, Lk * d), sC=(heads * Lq * ldS, Lq * ldS), backend=backend)
+        assert (Pf[..., :Lk].float() - Sref.softmax(-1)).abs().max() < 4e-3
+        assert torch.all(Pf[..., Lk:] == 0)
+        dSf = torch.full((B, heads, Lq, ldS), float("nan"), dtype=torch.bfloat16, device=dev)
+        k.gemm(do, vv, M=Lq, N=Lk, K=d, lda=Cn, ldb=d, out=dSf, ldc=ldS, alpha=0.25, act=4, Z=P, batch=(B, heads),
+               sA=(Lq * Cn, d), sB=(heads * Lk * d, Lk * d), sC=(heads * Lq * ldS, Lq * ldS), backend=backend)
+        dPref = do4 @ vv.float().transpose(-1, -2)
+        Pp = P[..., :Lk].float()
+        dSref = 0.25 * Pp * (dPref - (dPref * Pp).sum(-1, keepdim=True))
+        assert rel_err(dSf[..., :Lk], dSref) < 8e-3, rel_err(dSf[..., :Lk], dSref)
+        assert torch.all(dSf[..., Lk:] == 0)
 
 
 @pytest.mark.parametrize("backend", [1, 2])
