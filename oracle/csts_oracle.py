@@ -154,16 +154,28 @@ class _SoftmaxSavedBf16(torch.autograd.Function):
         return p * (g - (g * p).sum(-1, keepdim=True))
 
 
-def rnd(t):      # stored in bf16, gradient stored in bf16
-    return _RoundBoth.apply(t) if EMULATE_BF16 else t
+SKIP = set()     # precision study (oracle/precision_study.py): "f:<tag>" / "b:<tag>" disables one rounding point
 
 
-def rnd_f(t):    # stored in bf16 (forward only)
-    return _RoundFwd.apply(t) if EMULATE_BF16 else t
+def rnd(t, tag="x"):      # stored in bf16, gradient stored in bf16
+    if not EMULATE_BF16:
+        return t
+    f, b = ("f:" + tag) not in SKIP, ("b:" + tag) not in SKIP
+    if f and b:
+        return _RoundBoth.apply(t)
+    if f:
+        return _RoundFwd.apply(t)
+    if b:
+        return _RoundBwd.apply(t)
+    return t
 
 
-def rnd_b(t):    # gradient arriving here is cast to bf16 before it feeds the backward GEMMs
-    return _RoundBwd.apply(t) if EMULATE_BF16 else t
+def rnd_f(t, tag="x"):    # stored in bf16 (forward only)
+    return _RoundFwd.apply(t) if EMULATE_BF16 and ("f:" + tag) not in SKIP else t
+
+
+def rnd_b(t, tag="x"):    # gradient arriving here is cast to bf16 before it feeds the backward GEMMs
+    return _RoundBwd.apply(t) if EMULATE_BF16 and ("b:" + tag) not in SKIP else t
 
 
 def _gelu(z):
@@ -209,7 +221,7 @@ def pool_tokens(t, thw, w, stride, ln_w, ln_b, transposed=False):
     else:
         g = F.conv3d(g, w, None, stride=stride, padding=1, groups=d)
     t, thw = _from_grid(g, B, h)
-    t = rnd(F.layer_norm(rnd(t), (d,), ln_w, ln_b, EPS_POOL))
+    t = rnd(F.layer_norm(rnd(t,"pre"), (d,), ln_w, ln_b, EPS_POOL),"pooled")
     return t, thw
 
 
@@ -235,7 +247,7 @@ def attention(sd, pfx, x, thw, heads, stride_q, stride_kv, kind, want_attn=False
     """
     B, N, C = x.shape
     d = C // heads
-    qkv = rnd(F.linear(x, rnd_f(sd[pfx + "qkv.weight"]), sd[pfx + "qkv.bias"]))
+    qkv = rnd(F.linear(x, rnd_f(sd[pfx + "qkv.weight"],"w"), sd[pfx + "qkv.bias"]),"qkv")
     qkv = qkv.reshape(B, N, 3, heads, d).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
     q_thw = thw
@@ -250,12 +262,12 @@ def attention(sd, pfx, x, thw, heads, stride_q, stride_kv, kind, want_attn=False
                            sd[pfx + "norm_k.weight"], sd[pfx + "norm_k.bias"])
         v, _ = pool_tokens(v, thw, sd[pfx + "pool_v.weight"], stride_kv,
                            sd[pfx + "norm_v.weight"], sd[pfx + "norm_v.bias"])
-    s = rnd_b(q @ k.transpose(-2, -1)) * (d ** -0.5)
+    s = rnd_b(q @ k.transpose(-2, -1),"dS") * (d ** -0.5)
     if kind == "spatial":
         s = s - spatial_mask(thw, s.device)
     p = _softmax(s)
-    o = rnd((p @ v).transpose(1, 2).reshape(B, q.shape[2], C))
-    o = rnd_b(F.linear(o, rnd_f(sd[pfx + "proj.weight"]), sd[pfx + "proj.bias"]))
+    o = rnd((p @ v).transpose(1, 2).reshape(B, q.shape[2], C),"o")
+    o = rnd_b(F.linear(o, rnd_f(sd[pfx + "proj.weight"],"w"), sd[pfx + "proj.bias"]),"g1")
     return (o, q_thw, p) if want_attn else (o, q_thw)
 
 
@@ -281,22 +293,22 @@ def block(sd, name, x, thw, want_attn=False, spec=None):
     `spec` = (kind, dim, dim_out, heads, stride_q, stride_kv) overrides the ARCH row (unit tests)."""
     kind, dim, dim_out, heads, sq, skv = spec if spec is not None else ARCH[name][1:]
     p = name + "."
-    xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], EPS_BLOCK))
+    xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], EPS_BLOCK),"xn")
     res = attention(sd, p + "attn.", xn, thw, heads, sq, skv, kind, want_attn)
     x = skip_path(x, thw, kind, sq) + res[0]
-    xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], EPS_BLOCK))
+    xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], EPS_BLOCK),"xn")
     # decoder MLP hidden is 4*dim_out (ref attention.py:444) — implied by the weight shapes
-    hid = rnd_f(_gelu(rnd_b(F.linear(xn, rnd_f(sd[p + "mlp.fc1.weight"]), sd[p + "mlp.fc1.bias"]))))     # exact erf
-    mlp = rnd_b(F.linear(hid, rnd_f(sd[p + "mlp.fc2.weight"]), sd[p + "mlp.fc2.bias"]))
+    hid = rnd_f(_gelu(rnd_b(F.linear(xn, rnd_f(sd[p + "mlp.fc1.weight"],"w"), sd[p + "mlp.fc1.bias"]),"dZ")),"h")     # exact erf
+    mlp = rnd_b(F.linear(hid, rnd_f(sd[p + "mlp.fc2.weight"],"w"), sd[p + "mlp.fc2.bias"]),"g2")
     if dim != dim_out:
-        x = rnd_b(F.linear(xn, rnd_f(sd[p + "proj.weight"]), sd[p + "proj.bias"]))    # ref :245-246
+        x = rnd_b(F.linear(xn, rnd_f(sd[p + "proj.weight"],"wproj"), sd[p + "proj.bias"]),"gproj")    # ref :245-246
     x = x + mlp
     return (x, res[1], res[2]) if want_attn else (x, res[1])
 
 
 def patch_embed(sd, name, x):
     """ref: stem_helper.py:35-38 — Conv3d k(3,7,7) s(2,4,4) p(1,3,3), flatten, transpose."""
-    y = rnd_b(F.conv3d(rnd_f(x), rnd_f(sd[name + ".proj.weight"]), sd[name + ".proj.bias"], stride=(2, 4, 4), padding=(1, 3, 3)))
+    y = rnd_b(F.conv3d(rnd_f(x,"patchx"), rnd_f(sd[name + ".proj.weight"],"patchw"), sd[name + ".proj.bias"], stride=(2, 4, 4), padding=(1, 3, 3)),"patchg")
     return y.flatten(2).transpose(1, 2)
 
 
