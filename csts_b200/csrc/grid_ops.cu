@@ -83,9 +83,37 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 #pragma unroll
     for (int k = 0; k < 3; ++k) { ot[k] = ti[k] * sT; oh[k] = hi[k] * sH; ow[k] = wi[k] * sW; }
     const bf16* pl = in_bh + 4 * lane;
+    // interior fast path (regular conv): all 9 (kh, kw) taps of a plane are in range -> no per-tap predicates,
+    // the 9 loads of a plane are independent and issue back to back
+    const bool hw_interior = !TRANSPOSED && vh[0] && vh[2] && vw[0] && vw[2];
+    if (hw_interior) {
+      const bf16* c0 = pl + (oh[0] + ow[0]);
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        if (!vt[kt]) continue;
+        const bf16* pk = c0 + ot[kt];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (4 * lane + 128 * j < D) {
+            float v[9][4];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) ld4(pk + (kh * sH + kw * sW) + 128 * j, v[kh * 3 + kw]);
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+              float w4[4];
+              ld4(s_w + (kt * 9 + t9) * D + 4 * lane + 128 * j, w4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(v[t9][i], w4[i], acc[j][i]);
+            }
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
-      if (!any_tap || !vt[kt]) continue;
+      if (hw_interior || !any_tap || !vt[kt]) continue;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         if (!vh[kh]) continue;

@@ -86,47 +86,63 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
     for (int i = 0; i < 4; ++i) { adg[j][i] = 0.f; adb[j][i] = 0.f; g[j][i] = 0.f; }
     if (c < width) ld4(gamma + c, g[j]);
   }
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
-    const float mu = mean[row], rs = rstd[row];
-    const TX* xr = x + (int64_t)row * width;
-    const TDY* dyr = dy + (int64_t)row * width;
-    float xh[LN_MAXJ][4], gd[LN_MAXJ][4];
-    float s1 = 0.f, s2 = 0.f;
+  // U rows per warp iteration: every global read of the U rows (x, dy, add, statistics) is issued before
+  // the first reduction, so a warp keeps 3*U*LN_MAXJ vector loads in flight
+  constexpr int U = LN_MAXJ <= 2 ? 2 : 1;
+  const int wstride = gridDim.x * warps_per_block;
+  for (int row0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < rows; row0 += U * wstride) {
+    float xv[U][LN_MAXJ][4], dv[U][LN_MAXJ][4], av[U][LN_MAXJ][4], mu[U], rs[U];
 #pragma unroll
-    for (int j = 0; j < LN_MAXJ; ++j) {
-      int c = (lane + 32 * j) * 4;
-      if (c < width) {
-        float xv[4], dv[4];
-        ld4(xr + c, xv);
-        ld4(dyr + c, dv);
+    for (int u = 0; u < U; ++u) {
+      const int row = row0 + u * wstride;
+      const bool rv = row < rows;
+      mu[u] = rv ? mean[row] : 0.f;
+      rs[u] = rv ? rstd[row] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xh[j][i] = (xv[i] - mu) * rs;
-          adg[j][i] += dv[i] * xh[j][i];
-          adb[j][i] += dv[i];
-          gd[j][i] = dv[i] * g[j][i];
-          s1 += gd[j][i];
-          s2 += gd[j][i] * xh[j][i];
+      for (int j = 0; j < LN_MAXJ; ++j) {
+        const int c = (lane + 32 * j) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { xv[u][j][i] = 0.f; dv[u][j][i] = 0.f; av[u][j][i] = 0.f; }
+        if (rv && c < width) {
+          ld4(x + (int64_t)row * width + c, xv[u][j]);
+          ld4(dy + (int64_t)row * width + c, dv[u][j]);
+          if (add) ld4(add + (int64_t)row * width + c, av[u][j]);
         }
       }
     }
-    s1 = warp_sum(s1) * inv_w;
-    s2 = warp_sum(s2) * inv_w;
-    TDX* dxr = dx + (int64_t)row * width;
 #pragma unroll
-    for (int j = 0; j < LN_MAXJ; ++j) {
-      int c = (lane + 32 * j) * 4;
-      if (c < width) {
-        float o[4];
+    for (int u = 0; u < U; ++u) {
+      const int row = row0 + u * wstride;
+      if (row >= rows) continue;
+      float xh[LN_MAXJ][4], gd[LN_MAXJ][4];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = rs * (gd[j][i] - s1 - xh[j][i] * s2);
-        if (add) {
-          float a[4];
-          ld4(add + (int64_t)row * width + c, a);
+      for (int j = 0; j < LN_MAXJ; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        if (c < width) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] += a[i];
+          for (int i = 0; i < 4; ++i) {
+            xh[j][i] = (xv[u][j][i] - mu[u]) * rs[u];
+            adg[j][i] += dv[u][j][i] * xh[j][i];
+            adb[j][i] += dv[u][j][i];
+            gd[j][i] = dv[u][j][i] * g[j][i];
+            s1 += gd[j][i];
+            s2 += gd[j][i] * xh[j][i];
+          }
         }
-        st4(dxr + c, o);
+      }
+      s1 = warp_sum(s1) * inv_w;
+      s2 = warp_sum(s2) * inv_w;
+      TDX* dxr = dx + (int64_t)row * width;
+#pragma unroll
+      for (int j = 0; j < LN_MAXJ; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        if (c < width) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = rs[u] * (gd[j][i] - s1 - xh[j][i] * s2) + av[u][j][i];
+          st4(dxr + c, o);
+        }
       }
     }
   }
