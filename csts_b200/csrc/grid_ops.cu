@@ -32,24 +32,6 @@ __device__ __forceinline__ void tap_coords(int o, int shift, int n_in, int (&idx
   }
 }
 
-// Compacted tap list of the transposed gather along one axis: the taps k = k0 + a*kstep, a < n, read the
-// input coordinates i0 - a.  (stride 1: up to three consecutive taps; stride 2: {1} for even and {0,2} for
-// odd outputs; stride >= 4: at most one tap, none for most outputs.)
-struct AxisTaps { int n, k0, kstep, i0; };
-__device__ __forceinline__ AxisTaps transposed_taps(int o, int shift, int n_in) {
-  AxisTaps t;
-  const int s = 1 << shift;
-  t.kstep = s;
-  t.k0 = (o + 1) & (s - 1);
-  if (t.k0 > 2) { t.n = 0; t.i0 = 0; return t; }
-  t.n = (t.k0 + s <= 2) ? ((t.k0 + 2 * s <= 2) ? 3 : 2) : 1;
-  t.i0 = (o + 1 - t.k0) >> shift;
-  if (t.i0 >= n_in) { t.k0 += s; t.i0 -= 1; t.n -= 1; }       // first tap falls off the far edge
-  if (t.i0 - (t.n - 1) < 0) t.n = t.i0 + 1;                   // last taps fall off the near edge
-  if (t.n < 0) t.n = 0;
-  return t;
-}
-
 template <int D, bool TRANSPOSED, bool NORM>
 __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, int lh, int lw) {
   constexpr int NJ = (D + 127) / 128;
@@ -129,32 +111,6 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
         }
       }
     }
-    if (TRANSPOSED) {
-      // exact-trip-count loops over the valid taps only (on average 6.75 of 27 for stride (1,2,2))
-      const AxisTaps at = transposed_taps(to, lt, p.Ti), ah = transposed_taps(ho, lh, p.Hi), aw = transposed_taps(wo, lw, p.Wi);
-      for (int a = 0; a < at.n; ++a) {
-        const int kt = at.k0 + a * at.kstep, o_t = (at.i0 - a) * sT;
-        for (int b2 = 0; b2 < ah.n; ++b2) {
-          const int kh = ah.k0 + b2 * ah.kstep, o_th = o_t + (ah.i0 - b2) * sH;
-          for (int c2 = 0; c2 < aw.n; ++c2) {
-            const int kw = aw.k0 + c2 * aw.kstep;
-            const bf16* src = pl + (o_th + (aw.i0 - c2) * sW);
-            const float* wt = s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-              if (4 * lane + 128 * j < D) {
-                float v[4], w4[4];
-                ld4(src + 128 * j, v);
-                ld4(wt + 128 * j, w4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(v[i], w4[i], acc[j][i]);
-              }
-            }
-          }
-        }
-      }
-    }
-    if (!TRANSPOSED)
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
       if (hw_interior || !any_tap || !vt[kt]) continue;
