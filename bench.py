@@ -236,9 +236,9 @@ def run_gpu(args):
 
     clips = B * world * args.steps
     hbm_peak, tf_peak, peak_src = peaks()
-    tc = [(s.elapsed_time(e), fl) for s, e, fl, _, is_tc in prof if is_tc]
+    tc = [(r[0].elapsed_time(r[1]), r[2]) for r in prof if r[4]]
     tc_ms, tc_flops = sum(t for t, _ in tc), sum(f for _, f in tc)
-    all_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in prof)
+    all_ms = sum(r[0].elapsed_time(r[1]) for r in prof)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     out = {
         "metric": METRIC, "value": clips / (total_ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,

@@ -73,7 +73,8 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
         call("csts_gemm", C.byref(a))
         ev1.record()
         tc = _lib.load().csts_gemm_backend(C.byref(a)) == 2
-        GEMM_PROFILE.append((ev0, ev1, 2.0 * M * N * K * nb, nb * (2.0 * (M * K + N * K) + out.element_size() * M * N), tc))
+        GEMM_PROFILE.append((ev0, ev1, 2.0 * M * N * K * nb, nb * (2.0 * (M * K + N * K) + out.element_size() * M * N), tc,
+                             (M, N, K, nb, int(a_kmajor), int(b_kmajor), act, int(residual is not None), a.c_dtype, split_k)))
         return out
     call("csts_gemm", C.byref(a))
     return out
