@@ -165,21 +165,30 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
-// global -> staging.  `gbase` points at (row 0, first byte) of the 32 x 128 B window; rows beyond
-// `rows_valid` and bytes beyond `bytes_valid` are skipped.  All 8 loads are issued before the stores.
-__device__ __forceinline__ void stage_load(uint32_t stage, const unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
-                                           int bytes_valid, int lane) {
+// global -> registers -> staging.  `gbase` points at (row 0, first byte) of the 32 x 128 B window; rows beyond
+// `rows_valid` and bytes beyond `bytes_valid` read as zero.  The fetch is separated from the put so that the
+// next slice's tile can be in flight while the current slice is processed (software prefetch).
+__device__ __forceinline__ void stage_fetch(uint4 (&v)[8], const unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
+                                            int bytes_valid, int lane) {
   const int chunk = lane & 7;
   const bool col_ok = chunk * 16 < bytes_valid;
-  uint4 v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int row = 4 * i + (lane >> 3);
     v[i] = make_uint4(0, 0, 0, 0);
     if (col_ok && row < rows_valid) v[i] = __ldg(reinterpret_cast<const uint4*>(gbase + row * pitch_bytes + chunk * 16));
   }
+}
+__device__ __forceinline__ void stage_put(uint32_t stage, const uint4 (&v)[8], int lane) {
+  const int chunk = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) sts128(stage_addr(stage, 4 * i + (lane >> 3), chunk), v[i]);
+}
+__device__ __forceinline__ void stage_load(uint32_t stage, const unsigned char* gbase, int64_t pitch_bytes, int rows_valid,
+                                           int bytes_valid, int lane) {
+  uint4 v[8];
+  stage_fetch(v, gbase, pitch_bytes, rows_valid, bytes_valid, lane);
+  stage_put(stage, v, lane);
 }
 template <bool ATOMIC>
 __device__ __forceinline__ void stage_store(uint32_t stage, unsigned char* gbase, int64_t pitch_bytes, int rows_valid, int bytes_valid,
@@ -207,9 +216,36 @@ enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32
 
 // One 32-column slice of the accumulator rows owned by this warp -> epilogue math -> global memory.
 // m0 = first row of the warp's 32-row band, n0 = first column, `stage` = the warp's staging tile.
+// Which tile (if any) a slice reads from global memory before its math: the saved pre-activation Z (GELU
+// backward), the f32 residual, or the old C (accumulate).
+template <int EPI>
+__device__ __forceinline__ bool slice_side_input(const TcParams& p, bool first_split) {
+  constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
+  if (EPI == EPI_BF16_DGELU) return true;
+  if (F32 && p.residual != nullptr && first_split) return true;
+  return (EPI == EPI_F32 || EPI == EPI_BF16) && p.accumulate;
+}
+template <int EPI>
+__device__ __forceinline__ void slice_prefetch(const TcParams& p, int64_t coff, int m0, int n0, int cols_in_tile, int lane,
+                                               bool first_split, uint4 (&pre)[8]) {
+  constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
+  constexpr int ESZ = F32 ? 4 : 2;
+  const int rows_valid = min(32, p.M - m0);
+  const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
+  if (EPI == EPI_BF16_DGELU) {
+    stage_fetch(pre, reinterpret_cast<const unsigned char*>(p.Z) + ((int64_t)m0 * p.ldz + n0) * 2, p.ldz * 2, rows_valid, cols_valid * 2, lane);
+  } else if (F32 && p.residual != nullptr && first_split) {
+    int rrow = p.res_mod > 0 ? m0 % p.res_mod : m0;
+    stage_fetch(pre, reinterpret_cast<const unsigned char*>(p.residual + (int64_t)rrow * p.ldr + n0), p.ldr * 4, rows_valid, cols_valid * 4, lane);
+  } else {
+    stage_fetch(pre, reinterpret_cast<const unsigned char*>(p.C) + (coff + (int64_t)m0 * p.ldc + n0) * ESZ, p.ldc * ESZ, rows_valid,
+                cols_valid * ESZ, lane);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, uint32_t stage, int m0, int n0, int cols_in_tile,
-                                               int lane, uint32_t taddr, float rs, bool first_split) {
+                                               int lane, uint32_t taddr, float rs, bool first_split, const uint4 (&pre)[8]) {
   constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
   constexpr int ESZ = F32 ? 4 : 2;
   const int rows_valid = min(32, p.M - m0);
@@ -225,12 +261,7 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
   }
   const bool has_res = F32 && p.residual != nullptr && first_split;
   const bool has_acc = (EPI == EPI_F32 || EPI == EPI_BF16) && p.accumulate;
-  if (EPI == EPI_BF16_DGELU) stage_load(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
-  else if (has_res) {
-    int rrow = p.res_mod > 0 ? m0 % p.res_mod : m0;
-    stage_load(stage, reinterpret_cast<const unsigned char*>(p.residual + (int64_t)rrow * p.ldr + n0), p.ldr * 4, rows_valid,
-               cols_valid * 4, lane);
-  } else if (has_acc) stage_load(stage, cg, p.ldc * ESZ, rows_valid, cols_valid * ESZ, lane);
+  if (EPI == EPI_BF16_DGELU || has_res || has_acc) stage_put(stage, pre, lane);      // tile prefetched by the caller
   uint32_t r[32];
   tmem_ld32(taddr, r);
   tmem_ld_wait();
@@ -548,16 +579,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = tm * BM + quad * 32;
       float rs = 1.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + lane, p.M - 1) / p.rows_per_scale];
+      constexpr int EPI_S = (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) ? EPI_BF16 : EPI;
+      constexpr int CSTEP = (NUM_EPI_WARPS / 4) * 32;
+      const bool live = m0 < p.M && kb1 > kb0;       // rows beyond M / an empty k-range contribute nothing
+      const bool side = live && slice_side_input<EPI_S>(p, split == 0);
+      // side input (Z / residual / old C) of the first slice is requested before the accumulator wait, the
+      // next slice's while the current one is being processed
+      uint4 pre[8];
+      {
+        const int c = sub * 32, n0 = tn * BN + c;
+        if (side && c < BN && n0 < p.N) slice_prefetch<EPI_S>(p, coff, m0, n0, BN - c, lane, split == 0, pre);
+      }
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
-      const bool live = m0 < p.M && kb1 > kb0;       // rows beyond M / an empty k-range contribute nothing
 #pragma unroll 1
-      for (int c = sub * 32; c < BN; c += (NUM_EPI_WARPS / 4) * 32) {
+      for (int c = sub * 32; c < BN; c += CSTEP) {
         const int n0 = tn * BN + c;
         if (!live || n0 >= p.N) continue;
-        epilogue_slice<(EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) ? EPI_BF16 : EPI>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs,
-                                                                                       split == 0);
+        uint4 cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = pre[i];
+        const int cn = c + CSTEP, n1 = tn * BN + cn;
+        if (side && cn < BN && n1 < p.N) slice_prefetch<EPI_S>(p, coff, m0, n1, BN - cn, lane, split == 0, pre);
+        epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0, cur);
       }
       tc_fence_before();
       __syncwarp();
