@@ -100,16 +100,16 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n, float v0, 
     return;
   }
   if (e.bias) { v0 += e.bias[n]; if (two) v1 += e.bias[n + 1]; }
-  if (e.act == 1) {
+  if (e.act == 1) {          // C = gelu(v), Z = gelu'(v)
     if (e.Z) {
       bf16* z = reinterpret_cast<bf16*>(e.Z) + (int64_t)m * e.ldz + n;
-      z[0] = __float2bfloat16_rn(v0); if (two) z[1] = __float2bfloat16_rn(v1);
+      z[0] = __float2bfloat16_rn(gelu_erf_grad(v0)); if (two) z[1] = __float2bfloat16_rn(gelu_erf_grad(v1));
     }
     v0 = gelu_erf(v0); v1 = gelu_erf(v1);
-  } else if (e.act == 2) {
+  } else if (e.act == 2) {   // C = v * Z
     const bf16* z = reinterpret_cast<const bf16*>(e.Z) + (int64_t)m * e.ldz + n;
-    v0 *= gelu_erf_grad(__bfloat162float(z[0]));
-    if (two) v1 *= gelu_erf_grad(__bfloat162float(z[1]));
+    v0 *= __bfloat162float(z[0]);
+    if (two) v1 *= __bfloat162float(z[1]);
   }
   if (e.row_scale) { float rs = e.row_scale[m / e.rows_per_scale]; v0 *= rs; v1 *= rs; }
   if (e.residual) {

@@ -273,17 +273,25 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
     for (int i = 0; i < 8; ++i) { v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w; }
   }
   if (EPI == EPI_BF16_GELU) {
+    // one evaluation of (cdf, pdf) yields both gelu(v) and gelu'(v); the derivative is what backward needs,
+    // so it is stored (bf16) in Z and the backward epilogue is a plain multiply
+    float gp[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float cdf, pdf;
+      gelu_parts(v[i], cdf, pdf);
+      gp[i] = fmaf(v[i], pdf, cdf);
+      v[i] = v[i] * cdf;
+    }
     if (p.Z) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
-                                                      pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+        sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(gp[8 * j], gp[8 * j + 1]), pack_bf162(gp[8 * j + 2], gp[8 * j + 3]),
+                                                      pack_bf162(gp[8 * j + 4], gp[8 * j + 5]), pack_bf162(gp[8 * j + 6], gp[8 * j + 7])));
       __syncwarp();
       stage_store<false>(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
       __syncwarp();
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
   }
   if (EPI == EPI_BF16_DGELU) {
     __syncwarp();
@@ -293,8 +301,8 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
       const bf162* zz = reinterpret_cast<const bf162*>(&t);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        v[8 * j + 2 * i] *= gelu_erf_grad(__low2float(zz[i]));
-        v[8 * j + 2 * i + 1] *= gelu_erf_grad(__high2float(zz[i]));
+        v[8 * j + 2 * i] *= __low2float(zz[i]);
+        v[8 * j + 2 * i + 1] *= __high2float(zz[i]);
       }
     }
     __syncwarp();

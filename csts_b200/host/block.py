@@ -131,6 +131,7 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     # ---- MLP (attention.py:243-247) -----------------------------------------------------------------
     xn2, mean2, rstd2 = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], EPS_BLOCK)
     hid = spec.hidden
+    # Z receives GELU'(fc1 pre-activation): the forward epilogue already evaluates it, backward only multiplies
     Z = torch.empty((Mq, hid), dtype=torch.bfloat16, device=x.device) if save else None
     hdn = K.gemm(xn2, wc.w(p["mlp.fc1.weight"]), M=Mq, N=hid, K=C, bias=p["mlp.fc1.bias"], act=1, Z=Z)
     if spec.dim != spec.dim_out:

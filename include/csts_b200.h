@@ -41,8 +41,9 @@ typedef struct csts_gemm_args {
   const void* A;          /* bf16 */
   const void* B;          /* bf16 */
   void* C;                /* f32 or bf16 (c_dtype) */
-  void* Z;                /* bf16, same shape as C (pitch ldz): act==1 -> receives the pre-activation,
-                                                                act==2 -> is read (multiply by GELU'(Z)) */
+  void* Z;                /* bf16, same shape as C (pitch ldz): act==1 -> receives GELU'(pre-activation),
+                                                                act==2 -> is read (C = result * Z),
+                                                                act==4 -> the softmax probabilities P */
   const float* bias;      /* [N] or NULL */
   const float* residual;  /* f32 [rows, N] (pitch ldr) or NULL; row = m % res_mod when res_mod > 0 */
   const float* row_scale; /* [ceil(M / rows_per_scale)] or NULL: row m is multiplied by
@@ -54,7 +55,7 @@ typedef struct csts_gemm_args {
   int32_t a_kmajor;       /* 1: A[m*lda + k]   0: A[k*lda + m] */
   int32_t b_kmajor;       /* 1: B[n*ldb + k]   0: B[k*ldb + n] */
   int32_t c_dtype;        /* 0 f32, 1 bf16 */
-  int32_t act;            /* 0 none, 1 erf GELU (nn.GELU(), common.py:21), 2 times GELU'(Z),
+  int32_t act;            /* 0 none, 1 erf GELU (nn.GELU(), common.py:21; Z <- GELU'), 2 times Z (GELU backward),
                              3 row softmax of alpha*acc (N <= 256, bf16 C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)) */
   int32_t accumulate;     /* C += result */
   int32_t res_mod;

@@ -63,10 +63,12 @@ def test_gemm_epilogues(backend):
     bias = torch.randn(N, generator=g).to(dev)
     res = torch.randn(M, N, generator=g).to(dev)
     pre = A.float() @ B.float().t() + bias
-    # GELU + saved pre-activation
+    # GELU; Z receives GELU'(pre-activation) for the backward epilogue
     Z = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     h = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, act=1, Z=Z, backend=backend)
-    assert rel_err(Z, pre) < 4e-3
+    pr = pre.clone().requires_grad_(True)
+    (gpre,) = torch.autograd.grad(F.gelu(pr).sum(), pr)
+    assert rel_err(Z, gpre) < 4e-3
     assert rel_err(h, F.gelu(pre)) < 5e-3
     # residual, f32 out
     o = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, residual=res, out_dtype=torch.float32, backend=backend)
@@ -78,11 +80,9 @@ def test_gemm_epilogues(backend):
     acc = res.clone()
     k.gemm(A, B, M=M, N=N, K=Kd, out=acc, accumulate=True, backend=backend)
     assert rel_err(acc, res + A.float() @ B.float().t()) < 2e-5
-    # times GELU'(Z)  (the tcgen05 kernel pairs activations with bf16 outputs only)
+    # times Z (GELU backward; the tcgen05 kernel pairs activations with bf16 outputs only)
     o = k.gemm(A, B, M=M, N=N, K=Kd, act=2, Z=Z, out_dtype=torch.float32 if backend == 1 else torch.bfloat16, backend=backend)
-    zf = Z.float().requires_grad_(True)
-    (gz,) = torch.autograd.grad(F.gelu(zf).sum(), zf)
-    assert rel_err(o, (A.float() @ B.float().t()) * gz) < (1e-4 if backend == 1 else 4e-3)
+    assert rel_err(o, (A.float() @ B.float().t()) * Z.float()) < (1e-4 if backend == 1 else 4e-3)
 
 
 @pytest.mark.parametrize("backend", [1, 2])
