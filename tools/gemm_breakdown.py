@@ -28,6 +28,7 @@ def main():
     torch.cuda.synchronize()
     K.GEMM_PROFILE = []
     for _ in range(3):
+        torch.cuda._sleep(int(0.08 * 1.9e9))     # park the GPU so the eager step is fully enqueued before it runs
         train_step(cfg, model, opt, [v], a, h)
     torch.cuda.synchronize()
     prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
