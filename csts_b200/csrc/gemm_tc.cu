@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -476,6 +477,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+  // overlaps the tail of the previous kernel in the stream; global memory is first touched below.
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
   // work item -> (tile_m, tile_n, split); consecutive items walk M first so that the B (weight)
   // tile stays hot in L2 across neighbouring CTAs
@@ -698,11 +702,25 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   }
   int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits * p.batch;
   int grid = items < csts_num_sms() ? items : csts_num_sms();
-  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, EPI>, ta, tb, p));
   return csts_check_launch("gemm_tc_kernel");
 }
 
 int pick_bn(int M, int N, int work_mult) {
+  if (const char* f = getenv("CSTS_FORCE_BN")) {       // tuning experiments only
+    int bn = atoi(f);
+    if (bn == 96 || bn == 128 || bn == 192 || bn == 256) return bn;
+  }
   // least padded columns first; among equals the widest tile that still gives every SM work, else
   // the narrowest (most CTAs)
   const int cands[4] = {256, 192, 128, 96};
