@@ -126,6 +126,21 @@ def run_reference(args):
     }))
 
 
+def ncu_traffic(prefix):
+    """Average DRAM bytes (read + write) per launch of the kernels whose name starts with `prefix`, from the
+    committed ncu launch list of this command (profiles/rNN_kernel_dram.json, written by tools/ncu_summary.py).
+    ncu cannot run inside the timed region, so this is a recorded measurement, not a live one."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernel_dram.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    n = sum(v["launches"] for k, v in d.items() if k.startswith(prefix))
+    b = sum(v["dram_bytes"] for k, v in d.items() if k.startswith(prefix))
+    return (b / n if n else None), os.path.relpath(files[-1], ROOT) + f" (ncu dram__bytes_read+write.sum over {n} launches of one step)"
+
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -239,6 +254,7 @@ def run_gpu(args):
 
     clips = B * world * args.steps
     hbm_peak, tf_peak, peak_src = peaks()
+    traffic, traffic_src = ncu_traffic("gemm_tc_kernel")
     tc = [(r[0].elapsed_time(r[1]), r[2]) for r in prof if r[4]]
     tc_ms, tc_flops = sum(t for t, _ in tc), sum(f for _, f in tc)
     all_ms = sum(r[0].elapsed_time(r[1]) for r in prof)
@@ -255,7 +271,8 @@ def run_gpu(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "gemm_tc_kernel (tcgen05 Linear GEMMs, all shapes of the step)", "bound": "tensor",
-                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "peak_source": f"{peak_src} sustained bf16", "launches": len(tc), "kernel_ms_per_step": tc_ms / args.steps,
                      "share_of_step": tc_ms / total_ms, "all_gemm_ms_per_step": all_ms / args.steps,
                      "timing": "CUDA events around every launch" + (" (eager replay of the same step; the timed region itself is one CUDA-graph launch per step)" if graphed is not None else "")},

@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsts_b200.so")
+# CSTS_B200_LIB selects another build of the same library (A/B tuning runs only)
+LIB_PATH = os.environ.get("CSTS_B200_LIB") or os.path.join(_HERE, "libcsts_b200.so")
 
 F32, BF16 = 0, 1
 _DT = {torch.float32: F32, torch.bfloat16: BF16}

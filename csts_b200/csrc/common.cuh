@@ -32,6 +32,39 @@ int csts_check_launch(const char* what);   // cudaGetLastError() -> 0 / error co
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 int csts_num_sms();
 
+// ---- programmatic dependent launch --------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and
+// calls pdl_wait() before its first global-memory access: the launch latency and CTA dispatch of
+// kernel N+1 then overlap the tail of kernel N (the step is ~1100 short launches, so the gaps
+// between kernels are a measurable share of it).  griddepcontrol.wait returns only once the
+// preceding kernel has completed and flushed, so no data hazard is introduced; launch_dependents
+// right after it lets the next kernel's CTAs become resident as soon as this one's are all running.
+#ifndef CSTS_PDL_TRIGGER
+#define CSTS_PDL_TRIGGER 1
+#endif
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if CSTS_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

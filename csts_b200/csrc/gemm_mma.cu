@@ -129,6 +129,7 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n, float v0, 
 
 template <bool AK, bool BKM>
 __global__ void __launch_bounds__(THREADS) gemm_mma_kernel(csts_gemm_args p, int k_per_split) {
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   bf16* sA = reinterpret_cast<bf16*>(smem_raw);
   bf16* sB = sA + STAGES * TILE_ELEMS;
@@ -248,7 +249,7 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   csts_gemm_args p = a;
   p.split_k = split;
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM), a.batch1 * a.batch2 * split);
-  gemm_mma_kernel<AK, BKM><<<grid, THREADS, SMEM_BYTES, stream>>>(p, k_per_split);
+  launch_pdl(gemm_mma_kernel<AK, BKM>, dim3(grid), dim3(THREADS), SMEM_BYTES, stream, p, k_per_split);
   return csts_check_launch("gemm_mma_kernel");
 }
 

@@ -479,7 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
   // overlaps the tail of the previous kernel in the stream; global memory is first touched below.
-  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  pdl_wait();
 
   // work item -> (tile_m, tile_n, split); consecutive items walk M first so that the B (weight)
   // tile stays hot in L2 across neighbouring CTAs

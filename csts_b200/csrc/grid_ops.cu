@@ -34,6 +34,7 @@ __device__ __forceinline__ void tap_coords(int o, int shift, int n_in, int (&idx
 
 template <int D, bool TRANSPOSED, bool NORM>
 __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, int lh, int lw) {
+  pdl_wait();
   constexpr int NJ = (D + 127) / 128;
   __shared__ float s_w[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 // slide over `big` through registers: stride 1 re-uses two of three loads, stride 2 one of three.
 template <int D, int SW>
 __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, int lt, int lh, int lw, int rows_per_block) {
+  pdl_wait();
   constexpr int NJ = (D + 127) / 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kt = warp / 3, kh = warp % 3;
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ arg,
                                                           int B, int T, int H, int W, int C) {
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const int64_t total = (int64_t)B * T * Ho * Wo * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
 // dx[i] = sum over the (<= 4) windows containing i of dy[o] * [arg[o] == tap(i, o)]
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg,
                                                           float* __restrict__ dx, int B, int T, int H, int W, int C) {
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const int64_t total = (int64_t)B * T * H * W * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -362,6 +366,7 @@ __device__ __forceinline__ void lin_coef(int o, int f, int n_in, int& i0, int& i
 
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int H, int W,
                                                            int C, int ft, int fh, int fw) {
+  pdl_wait();
   const int To = T * ft, Ho = H * fh, Wo = W * fw, C4 = C / 4;
   const int64_t total = (int64_t)B * To * Ho * Wo * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -412,6 +417,7 @@ __device__ __forceinline__ float lin_adj(int i, int o, int f, int n_in) {
 }
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int T, int H, int W,
                                                            int C, int ft, int fh, int fw, int accumulate) {
+  pdl_wait();
   const int To = T * ft, Ho = H * fh, Wo = W * fw, C4 = C / 4;
   const int64_t total = (int64_t)B * T * H * W * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -471,11 +477,11 @@ int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   int lt = log2_exact(p.st), lh = log2_exact(p.sh), lw = log2_exact(p.sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv: strides must be powers of two (%d,%d,%d)", p.st, p.sh, p.sw);
   if (p.transposed) {
-    if (norm) dwconv_kernel<D, true, true><<<grid, 256, 0, st>>>(p, lt, lh, lw);
-    else dwconv_kernel<D, true, false><<<grid, 256, 0, st>>>(p, lt, lh, lw);
+    if (norm) launch_pdl(dwconv_kernel<D, true, true>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    else launch_pdl(dwconv_kernel<D, true, false>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
   } else {
-    if (norm) dwconv_kernel<D, false, true><<<grid, 256, 0, st>>>(p, lt, lh, lw);
-    else dwconv_kernel<D, false, false><<<grid, 256, 0, st>>>(p, lt, lh, lw);
+    if (norm) launch_pdl(dwconv_kernel<D, false, true>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    else launch_pdl(dwconv_kernel<D, false, false>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
   }
   return csts_check_launch("dwconv");
 }
@@ -507,7 +513,7 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   int rows_per_block = (int)((rows_total + grid - 1) / grid);
   grid = (int)((rows_total + rows_per_block - 1) / rows_per_block);
   cudaStream_t st = (cudaStream_t)stream;
-#define WGRAD(D_, SW_) dwconv_wgrad_kernel<D_, SW_><<<grid, 288, 0, st>>>(*p, lt, lh, lw, rows_per_block)
+#define WGRAD(D_, SW_) launch_pdl(dwconv_wgrad_kernel<D_, SW_>, dim3(grid), dim3(288), 0, st, *p, lt, lh, lw, rows_per_block)
   if (p->d == 96) { if (p->sw == 1) WGRAD(96, 1); else if (p->sw == 2) WGRAD(96, 2); else WGRAD(96, 0); }
   else { if (p->sw == 1) WGRAD(192, 1); else if (p->sw == 2) WGRAD(192, 2); else WGRAD(192, 0); }
 #undef WGRAD
@@ -518,27 +524,27 @@ int csts_maxpool_fwd(const float* x, float* y, void* arg, int B, int T, int H, i
   CSTS_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: C%%4, H%%2, W%%2 required");
   int64_t total = (int64_t)B * T * (H / 2) * (W / 2) * (C / 4);
   if (total == 0) return 0;
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, (uint8_t*)arg, B, T, H, W, C);
+  launch_pdl(maxpool_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, (uint8_t*)arg, B, T, H, W, C);
   return csts_check_launch("maxpool_fwd");
 }
 int csts_maxpool_bwd(const float* dy, const void* arg, float* dx, int B, int T, int H, int W, int C, void* stream) {
   int64_t total = (int64_t)B * T * H * W * (C / 4);
   if (total == 0) return 0;
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, (const uint8_t*)arg, dx, B, T, H, W, C);
+  launch_pdl(maxpool_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, (const uint8_t*)arg, dx, B, T, H, W, C);
   return csts_check_launch("maxpool_bwd");
 }
 int csts_upsample_fwd(const float* x, float* y, int B, int T, int H, int W, int C, int ft, int fh, int fw, void* stream) {
   CSTS_REQUIRE(C % 4 == 0 && ft >= 1 && fh >= 1 && fw >= 1, "upsample: bad arguments");
   int64_t total = (int64_t)B * T * ft * H * fh * W * fw * (C / 4);
   if (total == 0) return 0;
-  upsample_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, T, H, W, C, ft, fh, fw);
+  launch_pdl(upsample_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, B, T, H, W, C, ft, fh, fw);
   return csts_check_launch("upsample_fwd");
 }
 int csts_upsample_bwd(const float* dy, float* dx, int B, int T, int H, int W, int C, int ft, int fh, int fw, int accumulate, void* stream) {
   CSTS_REQUIRE(C % 4 == 0 && ft >= 1 && fh >= 1 && fw >= 1, "upsample: bad arguments");
   int64_t total = (int64_t)B * T * H * W * (C / 4);
   if (total == 0) return 0;
-  upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, B, T, H, W, C, ft, fh, fw, accumulate);
+  launch_pdl(upsample_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, dx, B, T, H, W, C, ft, fh, fw, accumulate);
   return csts_check_launch("upsample_bwd");
 }
 

@@ -17,6 +17,7 @@ template <int PER_THREAD>
 __global__ void __launch_bounds__(256) kldiv_frame_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                           float* __restrict__ prob, float* __restrict__ frame_kl,
                                                           float* __restrict__ dlogits, int HW, float inv_tau, float norm) {
+  pdl_wait();
   __shared__ float red[33];
   const int64_t base = (int64_t)blockIdx.x * HW;
   float l[PER_THREAD], q[PER_THREAD];
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) kldiv_frame_kernel(const float* __restric
 
 // loss[0] = scale * sum_i v[i]     (single block, deterministic)
 __global__ void reduce_scale_kernel(const float* __restrict__ v, int n, float scale, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[33];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
@@ -78,6 +80,7 @@ __global__ void reduce_scale_kernel(const float* __restrict__ v, int n, float sc
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sim_matrix_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ sim,
                                                              float* __restrict__ na, float* __restrict__ nb, int n, int D, float eps) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int r = warp; r < 2 * n; r += nw) {
     const float* v = r < n ? a + (int64_t)r * D : b + (int64_t)(r - n) * D;
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(256) sim_matrix_bwd_kernel(const float* __rest
                                                              const float* __restrict__ sim, const float* __restrict__ dsim,
                                                              const float* __restrict__ na, const float* __restrict__ nb,
                                                              float* __restrict__ da, float* __restrict__ db, int n, int D) {
+  pdl_wait();
   const int64_t total = (int64_t)2 * n * D;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(idx % D);
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(256) sim_matrix_bwd_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) egonce_kernel(const float* __restrict__ sim, float* __restrict__ loss, float* __restrict__ dsim,
                                                      float* __restrict__ lse_row, float* __restrict__ lse_col, int n, float inv_temp) {
+  pdl_wait();
   __shared__ float red[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int r = warp; r < 2 * n; r += nw) {
@@ -170,30 +175,30 @@ int csts_kldiv_frame_softmax(const float* logits, const float* target, float* pr
   CSTS_REQUIRE(target != nullptr, "kldiv: target required (uniform-prior variant is not used by CSTS)");
   cudaStream_t st = (cudaStream_t)stream;
   float norm = 1.f / ((float)T * logf((float)HW) * ((float)frames / (float)T));
-  if (HW <= 4 * 256) kldiv_frame_kernel<4><<<frames, 256, 0, st>>>(logits, target, prob, frame_kl, dlogits, HW, 1.f / temperature, norm);
-  else kldiv_frame_kernel<16><<<frames, 256, 0, st>>>(logits, target, prob, frame_kl, dlogits, HW, 1.f / temperature, norm);
+  if (HW <= 4 * 256) launch_pdl(kldiv_frame_kernel<4>, dim3(frames), dim3(256), 0, st, logits, target, prob, frame_kl, dlogits, HW, 1.f / temperature, norm);
+  else launch_pdl(kldiv_frame_kernel<16>, dim3(frames), dim3(256), 0, st, logits, target, prob, frame_kl, dlogits, HW, 1.f / temperature, norm);
   int rc = csts_check_launch("kldiv_frame");
   if (rc) return rc;
-  reduce_scale_kernel<<<1, 256, 0, st>>>(frame_kl, frames, norm, loss);
+  launch_pdl(reduce_scale_kernel, dim3(1), dim3(256), 0, st, frame_kl, frames, norm, loss);
   return csts_check_launch("kldiv_reduce");
 }
 
 int csts_sim_matrix_fwd(const float* a, const float* b, float* sim, float* na, float* nb, int n, int D, float eps, void* stream) {
   CSTS_REQUIRE(n > 0 && D > 0, "sim_matrix: empty input");
-  sim_matrix_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, b, sim, na, nb, n, D, eps);
+  launch_pdl(sim_matrix_fwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, a, b, sim, na, nb, n, D, eps);
   return csts_check_launch("sim_matrix_fwd");
 }
 int csts_sim_matrix_bwd(const float* a, const float* b, const float* sim, const float* dsim, const float* na, const float* nb, float* da,
                         float* db, int n, int D, void* stream) {
   int64_t total = (int64_t)2 * n * D;
   int grid = (int)((total + 255) / 256);
-  sim_matrix_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, sim, dsim, na, nb, da, db, n, D);
+  launch_pdl(sim_matrix_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a, b, sim, dsim, na, nb, da, db, n, D);
   return csts_check_launch("sim_matrix_bwd");
 }
 // lse_scratch: [2*n] floats
 int csts_egonce(const float* sim, float* loss, float* dsim, float* lse_scratch, int n, float temperature, void* stream) {
   CSTS_REQUIRE(n > 0, "egonce: empty similarity matrix");
-  egonce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sim, loss, dsim, lse_scratch, lse_scratch + n, n, 1.f / temperature);
+  launch_pdl(egonce_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, sim, loss, dsim, lse_scratch, lse_scratch + n, n, 1.f / temperature);
   return csts_check_launch("egonce");
 }
 

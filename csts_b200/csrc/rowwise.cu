@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI* __restrict
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             int rows, int width, float eps) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_w = 1.f / (float)width;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
                                                             const float* __restrict__ gamma, const float* __restrict__ add,
                                                             TDX* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int rows, int width) {
+  pdl_wait();
   __shared__ float s_dg[768], s_db[768];
   for (int i = threadIdx.x; i < width; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
@@ -169,6 +171,7 @@ __device__ __forceinline__ int frame_of(int i, int thw, int hw) { return i < thw
 
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, int64_t rows, int n,
                                                           int lds, int ldp, int nq, int mask_hw, int mask_t) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
 // dS = scale * P o (dP - rowsum(dP o P)); dS bf16 with zeroed pad columns
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
                                                           int64_t rows, int n, int ldp, int lddp, float scale) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict
 // f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns)
 __global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int cols, int ld_out,
                                 const float* __restrict__ row_scale, int rows_per_scale) {
+  pdl_wait();
   int64_t total = rows * ld_out;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / ld_out;
@@ -236,6 +241,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict_
 // cols must be a multiple of 4 (a 4-vector never straddles rows)
 __global__ void cast_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4, int cols4,
                                 const float* __restrict__ row_scale, int rows_per_scale) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4];
     ld4(src + 4 * i, v);
@@ -250,6 +256,7 @@ __global__ void cast_vec_kernel(const float* __restrict__ src, bf16* __restrict_
 // src [a][b][c] -> dst [a][c][b]   (tile transpose through shared memory), TO in {float, bf16}
 template <typename TO>
 __global__ void permute_021_kernel(const float* __restrict__ src, TO* __restrict__ dst, int a, int b, int c) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int64_t base = (int64_t)blockIdx.z * b * c;
   int b0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -266,6 +273,7 @@ __global__ void permute_021_kernel(const float* __restrict__ src, TO* __restrict
 
 // out = a + b (f32), vectorised
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n4) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
     reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
@@ -273,6 +281,7 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 }
 // out = a * (*scalar)   (device scalar; used to apply the upstream loss gradient)
 __global__ void scale_kernel(const float* __restrict__ a, const float* __restrict__ scalar, float* __restrict__ out, int64_t n) {
+  pdl_wait();
   const float s = *scalar;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] * s;
 }
@@ -281,6 +290,7 @@ __global__ void scale_kernel(const float* __restrict__ a, const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, float* __restrict__ out, int64_t M, int N, int64_t ld,
                                                      int rows_per_block) {
+  pdl_wait();
   __shared__ float red[8][128];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * 4;
@@ -327,7 +337,7 @@ int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const f
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(rows, 8);
-#define LN_FWD_J(TI, TO, J) layernorm_fwd_kernel<TI, TO, J><<<grid, 256, 0, st>>>((const TI*)x, (TO*)y, gamma, beta, mean, rstd, (int)rows, width, eps)
+#define LN_FWD_J(TI, TO, J) launch_pdl(layernorm_fwd_kernel<TI, TO, J>, dim3(grid), dim3(256), 0, st, (const TI*)x, (TO*)y, gamma, beta, mean, rstd, (int)rows, width, eps)
 #define LN_FWD(TI, TO)                                   \
   do {                                                   \
     if (width <= 128) LN_FWD_J(TI, TO, 1);               \
@@ -354,7 +364,7 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
   int64_t blocks = (rows + 31) / 32;       // >= 4 rows per warp so the column atomics amortise
   int grid = (int)(blocks < csts_num_sms() * 8 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 8);
 #define LN_BWD_J(TX, TDY, TDX, J) \
-  layernorm_bwd_kernel<TX, TDY, TDX, J><<<grid, 256, 0, st>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
+  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, J>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
 #define LN_BWD(TX, TDY, TDX)                             \
   do {                                                   \
     if (width <= 128) LN_BWD_J(TX, TDY, TDX, 1);         \
@@ -374,13 +384,13 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
 int csts_softmax_fwd(const float* S, void* P, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t, void* stream) {
   if (rows == 0) return 0;
   CSTS_REQUIRE(ldp >= n && lds >= n, "softmax: leading dims smaller than n");
-  softmax_fwd_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(S, (bf16*)P, rows, n, lds, ldp, nq, mask_hw, mask_t);
+  launch_pdl(softmax_fwd_kernel, dim3(grid_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, S, (bf16*)P, rows, n, lds, ldp, nq, mask_hw, mask_t);
   return csts_check_launch("softmax_fwd");
 }
 
 int csts_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n, int ldp, int lddp, float scale, void* stream) {
   if (rows == 0) return 0;
-  softmax_bwd_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)P, dP, (bf16*)dS, rows, n, ldp, lddp, scale);
+  launch_pdl(softmax_bwd_kernel, dim3(grid_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)P, dP, (bf16*)dS, rows, n, ldp, lddp, scale);
   return csts_check_launch("softmax_bwd");
 }
 
@@ -392,10 +402,10 @@ int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_o
   if (row_scale) CSTS_REQUIRE(rows_per_scale > 0, "cast: rows_per_scale must be positive");
   if (ld_out == cols && cols % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
     int64_t n4 = rows * cols / 4;
-    cast_vec_kernel<<<grid_for(n4, 256), 256, 0, st>>>(src, (bf16*)dst, n4, cols / 4, row_scale, rows_per_scale);
+    launch_pdl(cast_vec_kernel, dim3(grid_for(n4, 256)), dim3(256), 0, st, src, (bf16*)dst, n4, cols / 4, row_scale, rows_per_scale);
   } else {
     CSTS_REQUIRE(ld_out >= cols, "cast: ld_out < cols");
-    cast_pad_kernel<<<grid_for(rows * ld_out, 256), 256, 0, st>>>(src, (bf16*)dst, rows, cols, ld_out, row_scale, rows_per_scale);
+    launch_pdl(cast_pad_kernel, dim3(grid_for(rows * ld_out, 256)), dim3(256), 0, st, src, (bf16*)dst, rows, cols, ld_out, row_scale, rows_per_scale);
   }
   return csts_check_launch("cast_bf16");
 }
@@ -405,21 +415,21 @@ int csts_permute_021(const float* src, void* dst, int dst_dtype, int a, int b, i
   if ((int64_t)a * b * c == 0) return 0;
   dim3 grid(ceil_div(c, 32), ceil_div(b, 32), a), block(32, 8);
   CSTS_REQUIRE(a <= 65535 && grid.y <= 65535, "permute_021: dims too large");
-  if (dst_dtype == 0) permute_021_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (float*)dst, a, b, c);
-  else permute_021_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, a, b, c);
+  if (dst_dtype == 0) launch_pdl(permute_021_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (float*)dst, a, b, c);
+  else launch_pdl(permute_021_kernel<bf16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (bf16*)dst, a, b, c);
   return csts_check_launch("permute_021");
 }
 
 int csts_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
   if (n == 0) return 0;
   CSTS_REQUIRE(n % 4 == 0, "add: n must be a multiple of 4");
-  add_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4);
+  launch_pdl(add_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, a, b, out, n / 4);
   return csts_check_launch("add_f32");
 }
 
 int csts_scale_f32(const float* a, const float* device_scalar, float* out, int64_t n, void* stream) {
   if (n == 0) return 0;
-  scale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, device_scalar, out, n);
+  launch_pdl(scale_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, a, device_scalar, out, n);
   return csts_check_launch("scale_f32");
 }
 
@@ -433,8 +443,8 @@ int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_
   int rows_per_block = (int)((M + want_y - 1) / want_y);
   if (rows_per_block < 64) rows_per_block = 64;
   dim3 grid(bx, ceil_div(M, rows_per_block));
-  if (x_dtype == 0) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, out, M, N, ld, rows_per_block);
-  else colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)X, out, M, N, ld, rows_per_block);
+  if (x_dtype == 0) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)X, out, M, N, ld, rows_per_block);
+  else launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)X, out, M, N, ld, rows_per_block);
   return csts_check_launch("colsum");
 }
 

@@ -17,6 +17,7 @@ int grid_for(int64_t work_items, int per_block) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int T, int H,
                                                      int W, int Kp) {
+  pdl_wait();
   const int To = T / 2, Ho = H / 4, Wo = W / 4;
   const int K = Cin * 147;
   const int64_t total = (int64_t)B * To * Ho * Wo * Kp;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 // pos[t*HW + s][c] = spatial[s][c] + temporal[t][c]       ref: custom_multimodal_builder.py:362-365
 __global__ void pos_embed_kernel(const float* __restrict__ spatial, const float* __restrict__ temporal, float* __restrict__ pos, int T,
                                  int HW, int C) {
+  pdl_wait();
   const int64_t total = (int64_t)T * HW * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -49,6 +51,7 @@ __global__ void pos_embed_kernel(const float* __restrict__ spatial, const float*
 // dspatial[s][c] = sum_{b,t} dY[b][t][s][c];  dtemporal[t][c] += sum_{b,s} dY[b][t][s][c]
 __global__ void __launch_bounds__(128) pos_embed_bwd_kernel(const float* __restrict__ dY, float* __restrict__ dspatial,
                                                             float* __restrict__ dtemporal, int B, int T, int HW, int C, int s_per_block) {
+  pdl_wait();
   const int c = threadIdx.x;
   if (c >= C) return;
   int s0 = blockIdx.x * s_per_block, s1 = min(HW, s0 + s_per_block);
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(128) pos_embed_bwd_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void reweight_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int B, int T, int S,
                                     int C, int64_t w_sB) {
+  pdl_wait();
   const int C4 = C / 4;
   const int64_t total = (int64_t)B * T * S * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -96,6 +100,7 @@ __global__ void reweight_fwd_kernel(const float* __restrict__ x, const float* __
 // dx = dout * w ; dw[b][t][c] = sum_s dout * x        (one thread owns (b, t, 4 channels): no atomics)
 __global__ void reweight_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w,
                                     float* __restrict__ dx, float* __restrict__ dw, int B, int T, int S, int C, int64_t w_sB) {
+  pdl_wait();
   const int C4 = C / 4;
   const int64_t total = (int64_t)B * T * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -120,6 +125,7 @@ __global__ void reweight_bwd_kernel(const float* __restrict__ dout, const float*
 
 // out[b][c] = mean_n x[b][n][c]  (bf16 out: it is the A operand of the NCE projection GEMM)
 __global__ void token_mean_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int N, int C) {
+  pdl_wait();
   const int64_t total = (int64_t)B * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -131,6 +137,7 @@ __global__ void token_mean_fwd_kernel(const float* __restrict__ x, bf16* __restr
 }
 // dx[b][n][c] (+)= dout[b][c] / N
 __global__ void token_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int N, int C, int accumulate) {
+  pdl_wait();
   const int64_t total = (int64_t)B * N * C;
   const float inv = 1.f / (float)N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -157,6 +164,7 @@ __device__ __forceinline__ void t_coef(int to, int Ti, int& i0, int& i1, float& 
 __global__ void __launch_bounds__(256) classifier_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ stem,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              float* __restrict__ logits, int B, int Ti, int S, int C) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int To = 2 * Ti;
   const int64_t total = (int64_t)B * To * S;
@@ -179,6 +187,7 @@ __global__ void __launch_bounds__(256) classifier_bwd_feat_kernel(const float* _
                                                                   const float* __restrict__ stem, const float* __restrict__ w,
                                                                   float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ dbias,
                                                                   int B, int Ti, int S, int C) {
+  pdl_wait();
   __shared__ float s_dw[256];
   __shared__ float s_db;
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_dw[i] = 0.f;
@@ -224,6 +233,7 @@ __global__ void __launch_bounds__(256) classifier_bwd_feat_kernel(const float* _
 // dstem[b][ti][s][c] = w[c] * sum_{to} coef(to -> ti) * dlogit[b][to][s]
 __global__ void classifier_bwd_stem_kernel(const float* __restrict__ dlogits, const float* __restrict__ w, float* __restrict__ dstem, int B,
                                            int Ti, int S, int C) {
+  pdl_wait();
   const int To = 2 * Ti;
   const int64_t total = (int64_t)B * Ti * S * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -252,42 +262,42 @@ int csts_im2col_patch(const float* x, void* patches, int B, int Cin, int T, int 
   CSTS_REQUIRE(T % 2 == 0 && H % 4 == 0 && W % 4 == 0 && Kp >= Cin * 147 && Kp % 8 == 0, "im2col: bad geometry");
   int64_t total = (int64_t)B * (T / 2) * (H / 4) * (W / 4) * Kp;
   if (total == 0) return 0;
-  im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)patches, B, Cin, T, H, W, Kp);
+  launch_pdl(im2col_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)patches, B, Cin, T, H, W, Kp);
   return csts_check_launch("im2col_patch");
 }
 int csts_pos_embed(const float* spatial, const float* temporal, float* pos, int T, int HW, int C, void* stream) {
-  pos_embed_kernel<<<grid_for((int64_t)T * HW * C, 256), 256, 0, (cudaStream_t)stream>>>(spatial, temporal, pos, T, HW, C);
+  launch_pdl(pos_embed_kernel, dim3(grid_for((int64_t)T * HW * C, 256)), dim3(256), 0, (cudaStream_t)stream, spatial, temporal, pos, T, HW, C);
   return csts_check_launch("pos_embed");
 }
 // dtemporal must be zeroed by the caller; dspatial is overwritten
 int csts_pos_embed_bwd(const float* dY, float* dspatial, float* dtemporal, int B, int T, int HW, int C, void* stream) {
   CSTS_REQUIRE(C <= 128 && T <= 8, "pos_embed_bwd: C <= 128 and T <= 8 required");
   int s_per_block = 8;
-  pos_embed_bwd_kernel<<<ceil_div(HW, s_per_block), 128, 0, (cudaStream_t)stream>>>(dY, dspatial, dtemporal, B, T, HW, C, s_per_block);
+  launch_pdl(pos_embed_bwd_kernel, dim3(ceil_div(HW, s_per_block)), dim3(128), 0, (cudaStream_t)stream, dY, dspatial, dtemporal, B, T, HW, C, s_per_block);
   return csts_check_launch("pos_embed_bwd");
 }
 int csts_reweight_fwd(const float* x, const float* w, float* out, int B, int T, int S, int C, int64_t w_sB, void* stream) {
   CSTS_REQUIRE(C % 4 == 0 && w_sB % 4 == 0, "reweight: C and w_sB must be multiples of 4");
-  reweight_fwd_kernel<<<grid_for((int64_t)B * T * S * C / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, w, out, B, T, S, C, w_sB);
+  launch_pdl(reweight_fwd_kernel, dim3(grid_for((int64_t)B * T * S * C / 4, 256)), dim3(256), 0, (cudaStream_t)stream, x, w, out, B, T, S, C, w_sB);
   return csts_check_launch("reweight_fwd");
 }
 int csts_reweight_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, int B, int T, int S, int C, int64_t w_sB,
                       void* stream) {
   CSTS_REQUIRE(C % 4 == 0 && w_sB % 4 == 0, "reweight: C and w_sB must be multiples of 4");
-  reweight_bwd_kernel<<<grid_for((int64_t)B * T * C / 4, 64), 64, 0, (cudaStream_t)stream>>>(dout, x, w, dx, dw, B, T, S, C, w_sB);
+  launch_pdl(reweight_bwd_kernel, dim3(grid_for((int64_t)B * T * C / 4, 64)), dim3(64), 0, (cudaStream_t)stream, dout, x, w, dx, dw, B, T, S, C, w_sB);
   return csts_check_launch("reweight_bwd");
 }
 int csts_token_mean_fwd(const float* x, void* out_bf16, int B, int N, int C, void* stream) {
-  token_mean_fwd_kernel<<<grid_for((int64_t)B * C, 64), 64, 0, (cudaStream_t)stream>>>(x, (bf16*)out_bf16, B, N, C);
+  launch_pdl(token_mean_fwd_kernel, dim3(grid_for((int64_t)B * C, 64)), dim3(64), 0, (cudaStream_t)stream, x, (bf16*)out_bf16, B, N, C);
   return csts_check_launch("token_mean_fwd");
 }
 int csts_token_mean_bwd(const float* dout, float* dx, int B, int N, int C, int accumulate, void* stream) {
-  token_mean_bwd_kernel<<<grid_for((int64_t)B * N * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, N, C, accumulate);
+  launch_pdl(token_mean_bwd_kernel, dim3(grid_for((int64_t)B * N * C, 256)), dim3(256), 0, (cudaStream_t)stream, dout, dx, B, N, C, accumulate);
   return csts_check_launch("token_mean_bwd");
 }
 int csts_classifier_fwd(const float* feat, const float* stem, const float* w, const float* bias, float* logits, int B, int Ti, int S, int C,
                         void* stream) {
-  classifier_fwd_kernel<<<grid_for((int64_t)B * 2 * Ti * S, 8), 256, 0, (cudaStream_t)stream>>>(feat, stem, w, bias, logits, B, Ti, S, C);
+  launch_pdl(classifier_fwd_kernel, dim3(grid_for((int64_t)B * 2 * Ti * S, 8)), dim3(256), 0, (cudaStream_t)stream, feat, stem, w, bias, logits, B, Ti, S, C);
   return csts_check_launch("classifier_fwd");
 }
 // dw, dbias must be zeroed by the caller
@@ -297,10 +307,10 @@ int csts_classifier_bwd(const float* dlogits, const float* feat, const float* st
   int64_t toks = (int64_t)B * 2 * Ti * S;
   int64_t blocks = (toks + 255) / 256;
   int grid = (int)(blocks < csts_num_sms() * 2 ? blocks : csts_num_sms() * 2);
-  classifier_bwd_feat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dlogits, feat, stem, w, dfeat, dw, dbias, B, Ti, S, C);
+  launch_pdl(classifier_bwd_feat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dlogits, feat, stem, w, dfeat, dw, dbias, B, Ti, S, C);
   int rc = csts_check_launch("classifier_bwd_feat");
   if (rc) return rc;
-  classifier_bwd_stem_kernel<<<grid_for((int64_t)B * Ti * S * C, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, w, dstem, B, Ti, S, C);
+  launch_pdl(classifier_bwd_stem_kernel, dim3(grid_for((int64_t)B * Ti * S * C, 256)), dim3(256), 0, (cudaStream_t)stream, dlogits, w, dstem, B, Ti, S, C);
   return csts_check_launch("classifier_bwd_stem");
 }
 
