@@ -813,8 +813,9 @@ int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
     if (a.c_dtype == 1) return dispatch<true, true, EPI_BF16>(a, stream);
     return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);
   }
-  if (!a.b_kmajor) {                                    // (K, MN): P.V and dS.K of attention
-    CSTS_REQUIRE(a.act == 0 && !atomic, "gemm_tc: (K-major, MN-major) products have plain epilogues");
+  if (!a.b_kmajor) {                                    // (K, MN): P.V and dS.K of attention; dX = dY . W of every Linear
+    CSTS_REQUIRE((a.act == 0 || a.act == 2) && !atomic, "gemm_tc: (K-major, MN-major) products have no GELU / split-K epilogue");
+    if (a.act == 2) return dispatch<false, true, EPI_BF16_DGELU>(a, stream);
     return a.c_dtype == 1 ? dispatch<false, true, EPI_BF16>(a, stream) : dispatch<false, true, EPI_F32>(a, stream);
   }
   if (a.c_dtype == 0) return atomic ? dispatch<false, false, EPI_F32_ATOMIC>(a, stream) : dispatch<false, false, EPI_F32>(a, stream);

@@ -182,17 +182,17 @@ def block_backward(spec, p, wc, sv, dy):
     dy = dy.contiguous().view(Mq, Co)
     g2 = K.cast_bf16(dy, row_scale=dp, rows_per_scale=rps)             # gradient entering the (drop-path scaled) MLP branch
     # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
-    dZ = K.gemm(g2, wc.wt(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, act=2, Z=sv["Z"])
+    dZ = K.gemm(g2, wc.w(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, b_kmajor=False, act=2, Z=sv["Z"])
     g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq)
     g["mlp.fc2.bias"] = K.colsum(g2, Mq, Co, out=zeros(Co))
-    dxn2 = K.gemm(dZ, wc.wt(p["mlp.fc1.weight"]), M=Mq, N=C, K=hid)
+    dxn2 = K.gemm(dZ, wc.w(p["mlp.fc1.weight"]), M=Mq, N=C, K=hid, b_kmajor=False)
     g["mlp.fc1.weight"] = wgrad(dZ, sv["xn2"], hid, C, Mq)
     g["mlp.fc1.bias"] = K.colsum(dZ, Mq, hid, out=zeros(hid))
     del dZ
     g["norm2.weight"], g["norm2.bias"] = zeros(C), zeros(C)
     if spec.dim != spec.dim_out:
         gp = g2 if dp is None else K.cast_bf16(dy)                       # the re-based residual is not drop-path scaled
-        K.gemm(gp, wc.wt(p["proj.weight"]), M=Mq, N=C, K=Co, out=dxn2, accumulate=True)
+        K.gemm(gp, wc.w(p["proj.weight"]), M=Mq, N=C, K=Co, b_kmajor=False, out=dxn2, accumulate=True)
         g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq)
         g["proj.bias"] = K.colsum(dy, Mq, Co, out=zeros(Co))
         dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"])
@@ -202,7 +202,7 @@ def block_backward(spec, p, wc, sv, dy):
     del dxn2, g2
     # ---- attention output projection ------------------------------------------------------------------
     g1 = K.cast_bf16(dx1, row_scale=dp, rows_per_scale=rps)
-    do = K.gemm(g1, wc.wt(p["attn.proj.weight"]), M=Mq, N=C, K=C)       # (B, Lq, heads, d)
+    do = K.gemm(g1, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, b_kmajor=False)       # (B, Lq, heads, d)
     g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq)
     g["attn.proj.bias"] = K.colsum(g1, Mq, C, out=zeros(C))
     del g1
@@ -270,7 +270,7 @@ def block_backward(spec, p, wc, sv, dy):
         pool_backward(dk_t, "k_pool", 1, spec.stride_kv, "attn.pool_k.weight", "attn.norm_k", False, k.thw)
         pool_backward(dv_t, "v_pool", 2, spec.stride_kv, "attn.pool_v.weight", "attn.norm_v", False, v.thw)
     # ---- qkv projection and norm1 ---------------------------------------------------------------------------
-    dxn1 = K.gemm(dqkv, wc.wt(p["attn.qkv.weight"]), M=M, N=C, K=3 * C)
+    dxn1 = K.gemm(dqkv, wc.w(p["attn.qkv.weight"]), M=M, N=C, K=3 * C, b_kmajor=False)
     g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M)
     g["attn.qkv.bias"] = K.colsum(dqkv, M, 3 * C, out=zeros(3 * C))
     g["norm1.weight"], g["norm1.bias"] = zeros(C), zeros(C)

@@ -298,6 +298,7 @@ class CSTS(nn.Module):
         trunc_normal_(self.pos_embed_temporal_audio, std=0.02)
         self.apply(self._init_weights)
         self._wc = WeightCache()
+        self._dp_site, self._dp_keep, self._dp_scales = None, None, None
 
     @staticmethod
     def _init_weights(m):
@@ -321,12 +322,24 @@ class CSTS(nn.Module):
         spec = blk.spec
         dp_scale = None
         if self.training and spec.drop_path > 0.0:
-            # DropPath (common.py:46-59): per-sample keep mask, scaled by 1/keep_prob
-            keep = 1.0 - spec.drop_path
-            dp_scale = torch.floor(keep + torch.rand(x.shape[0], dtype=torch.float32, device=x.device)) / keep
+            dp_scale = self._dp_scales[self._dp_site[id(blk)]]
         meta = (spec, self._wc, tuple(thw), dp_scale, blk._names)
         y = BlockFn.apply(meta, x, *blk.tensors())
         return y, spec.q_grid(thw)
+
+    def _draw_drop_path(self, batch, device):
+        """DropPath (common.py:46-59): per-sample keep mask scaled by 1/keep_prob, floor(keep + U[0,1)) / keep.
+        The masks of every block of the step are drawn in one shot (three launches instead of four per block)."""
+        if self._dp_site is None:
+            blks = [m for m in self.modules() if isinstance(m, Block) and m.spec.drop_path > 0.0]
+            self._dp_site = {id(b): i for i, b in enumerate(blks)}
+            self._dp_keep = torch.tensor([[1.0 - b.spec.drop_path] for b in blks], dtype=torch.float32)
+        if not self._dp_site:
+            return
+        if self._dp_keep.device != device:
+            self._dp_keep = self._dp_keep.to(device)
+        u = torch.rand(len(self._dp_site), batch, dtype=torch.float32, device=device)
+        self._dp_scales = torch.floor(u.add_(self._dp_keep)).div_(self._dp_keep)
 
     def forward(self, x, y, return_embed=False, return_spatial_attn=False, return_temporal_attn=False):
         if return_spatial_attn or return_temporal_attn:
@@ -335,6 +348,8 @@ class CSTS(nn.Module):
         if not video.is_cuda:
             raise RuntimeError("csts_b200.CSTS runs on CUDA (sm_100a) only; there is no CPU path")
         video, audio = video.float(), y.float()
+        if self.training:
+            self._draw_drop_path(video.shape[0], video.device)
         wc = self._wc
         x = PatchEmbedFn.apply(wc, video, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
                                self.pos_embed_spatial, self.pos_embed_temporal)

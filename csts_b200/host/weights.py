@@ -2,8 +2,9 @@
 
 Parameters stay fp32 ``nn.Parameter``s under the reference's names (checkpoints, optimizer and DDP
 see exactly the reference's state).  The tensor-core kernels consume bf16 operands, so each GEMM
-weight gets a cached bf16 copy (and, for backward, a transposed copy so that dX = dY . W is again a
-K-major x K-major product for the tcgen05 kernel).  A copy is refreshed whenever the parameter's
+weight gets a cached bf16 copy.  The same (N, K) copy serves forward (K-major B operand of Y = X . W^T)
+and backward (MN-major B operand of dX = dY . W) — the tcgen05 kernel takes either layout through its
+shared-memory descriptors, so no transposed copy is kept.  A copy is refreshed whenever the parameter's
 version counter or storage changes, i.e. once per optimizer step.
 """
 import torch
@@ -29,11 +30,6 @@ class WeightCache:
     def w(self, param):
         """Linear weight (N, K) f32 -> bf16 (N, K)."""
         return self._get(param, "w", lambda p: K.cast_bf16(p.reshape(p.shape[0], -1)))
-
-    def wt(self, param):
-        """Linear weight (N, K) f32 -> bf16 (K, N)."""
-        return self._get(param, "wt", lambda p: K.permute_021(p.reshape(p.shape[0], -1), 1, p.shape[0],
-                                                               p.numel() // p.shape[0], torch.bfloat16)[0])
 
     def w_padded(self, param, kp):
         """Conv weight (N, ...) f32 -> bf16 (N, kp), zero padded columns (patch embed)."""

@@ -87,16 +87,21 @@ ARCH = arch_table()
 # plain fp32 oracle measures).  Off by default: the oracle proper is fp32.
 # --------------------------------------------------------------------------------------------
 EMULATE_BF16 = False
+FWD_DTYPE = torch.bfloat16     # precision study only: storage type of the forward activations / weights
 
 
 def _bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _fw(t):
+    return t.to(FWD_DTYPE).to(torch.float32)
+
+
 class _RoundBoth(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t):
-        return _bf(t)
+        return _fw(t)
 
     @staticmethod
     def backward(ctx, g):
@@ -116,7 +121,7 @@ class _RoundBwd(torch.autograd.Function):
 class _RoundFwd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t):
-        return _bf(t)
+        return _fw(t)
 
     @staticmethod
     def backward(ctx, g):
@@ -128,7 +133,7 @@ class _GeluSavedBf16(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z):
-        ctx.save_for_backward(_bf(z))
+        ctx.save_for_backward(_fw(z))
         return F.gelu(z)
 
     @staticmethod
@@ -144,7 +149,7 @@ class _SoftmaxSavedBf16(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, s):
-        p = _bf(s.softmax(dim=-1))
+        p = _fw(s.softmax(dim=-1))
         ctx.save_for_backward(p)
         return p
 

@@ -118,6 +118,24 @@ def test_optimizer_grouping(cpu_model):
     assert all(p.dim() == 1 for p in no_decay["params"])
 
 
+def test_drop_path_masks_are_drawn_once_per_step(cpu_model):
+    """DropPath (ref common.py:46-59): scale is 0 or 1/keep per sample, E[scale] = 1, rate = the block's
+    linearly increasing drop probability (ref custom_multimodal_builder.py:90)."""
+    model, _ = cpu_model                                              # built with DROPPATH_RATE 0.2
+    torch.manual_seed(0)
+    model._draw_drop_path(20000, torch.device("cpu"))
+    sites = model._dp_site
+    blocks = [b for b in model.blocks if b.spec.drop_path > 0]
+    assert len(blocks) == 15 and all(id(b) in sites for b in blocks)
+    for b in (blocks[0], blocks[7], blocks[-1]):
+        sc = model._dp_scales[sites[id(b)]]
+        keep = 1.0 - b.spec.drop_path
+        vals = torch.unique(sc)
+        assert all(min(abs(v - 0.0), abs(v - 1.0 / keep)) < 1e-6 for v in vals.tolist())
+        assert abs((sc > 0).float().mean().item() - keep) < 0.012
+    assert abs(blocks[-1].spec.drop_path - 0.2) < 1e-6
+
+
 def test_cpu_forward_fails_loudly(cpu_model):
     model, _ = cpu_model
     with pytest.raises(RuntimeError):

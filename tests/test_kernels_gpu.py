@@ -187,6 +187,28 @@ def test_gemm_weight_gradient_layout(backend, M, N, Kd, split):
 
 
 @pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("M,N,Kd", [(640, 3072, 768), (1568, 96, 288), (300, 768, 3072), (2080, 192, 768)])
+def test_gemm_data_gradient_layout(backend, M, N, Kd):
+    """dX = dY . W with the forward's own (N_out, K_in) bf16 weight as an MN-major B operand (no
+    transposed copy): plain, times-Z (GELU backward) and bf16-accumulate epilogues."""
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + Kd)
+    dY = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    W = bf(torch.randn(Kd, N, generator=g) * 0.05).to(dev)            # Linear(N -> Kd).weight
+    ref = dY.float() @ W.float()
+    o = k.gemm(dY, W, M=M, N=N, K=Kd, b_kmajor=False, backend=backend)
+    assert rel_err(o, ref) < 4e-3
+    Z = bf(torch.rand(M, N, generator=g)).to(dev)
+    o = k.gemm(dY, W, M=M, N=N, K=Kd, b_kmajor=False, act=2, Z=Z, out_dtype=torch.float32 if backend == 1 else torch.bfloat16,
+               backend=backend)
+    assert rel_err(o, ref * Z.float()) < 4e-3
+    base = bf(torch.randn(M, N, generator=g)).to(dev)
+    acc = base.clone()
+    k.gemm(dY, W, M=M, N=N, K=Kd, b_kmajor=False, out=acc, accumulate=True, backend=backend)
+    assert rel_err(acc, base.float() + ref) < 6e-3
+
+
+@pytest.mark.parametrize("backend", [1, 2])
 def test_gemm_rowscale_and_bf16_accumulate(backend):
     k = K()
     M, N, Kd = 4 * 300, 192, 96
