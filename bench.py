@@ -76,12 +76,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_cfg(n_gpus):
+def make_cfg(n_gpus, precision="bf16"):
     from csts_b200.host.config import assert_and_infer_cfg, get_cfg
     cfg = get_cfg()
     cfg.merge_from_file(os.path.join(ROOT, "configs", "Ego4D", "CSTS_Ego4D_Gaze_Forecast.yaml"))
     cfg.merge_from_list(["NUM_GPUS", n_gpus, "MODEL.LOSS_FUNC", "kldiv+egonce", "TRAIN.BATCH_SIZE", BATCH_PER_GPU * n_gpus,
-                         "TEST.BATCH_SIZE", BATCH_PER_GPU * n_gpus])
+                         "TEST.BATCH_SIZE", BATCH_PER_GPU * n_gpus, "TRAIN.MIXED_PRECISION", precision == "fp16"])
     return assert_and_infer_cfg(cfg)
 
 
@@ -148,7 +148,7 @@ def run_gpu(args):
     import csts_oracle as O
     from csts_b200 import _lib, kernels as K
     from csts_b200.host.build import build_model
-    from csts_b200.host.train_step import GraphedTrainStep, construct_optimizer, train_step
+    from csts_b200.host.train_step import GraphedTrainStep, construct_optimizer, make_grad_scaler, train_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,7 +158,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = make_cfg(world)
+    cfg = make_cfg(world, args.precision)
     torch.manual_seed(cfg.RNG_SEED)
     use_graph = args.graph
     model = build_model(cfg, ddp=not use_graph)
@@ -178,18 +178,19 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graphed = GraphedTrainStep(cfg, model, opt, video_d, audio_d, hm_d) if use_graph else None
+    scaler = make_grad_scaler(cfg)           # enabled in the fp16 mode only (reference loop, train_avgaze_net.py:277)
+    graphed = GraphedTrainStep(cfg, model, opt, video_d, audio_d, hm_d, scaler=scaler) if use_graph else None
     launches_per_step = None
     if graphed is not None:
         # launch count of one step, taken from an eager (un-captured) step: a graph replay launches the same kernels
         _lib.launch_count(reset=True)
-        train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync)
+        train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync, scaler=scaler)
         launches_per_step = _lib.launch_count()
 
     def resident_step():
         if graphed is not None:
             return graphed(None, None, None)            # inputs already resident in the static buffers
-        return train_step(cfg, model, opt, [video_d], audio_d, hm_d, lr=cfg.SOLVER.BASE_LR)
+        return train_step(cfg, model, opt, [video_d], audio_d, hm_d, lr=cfg.SOLVER.BASE_LR, scaler=scaler)
 
     def e2e_step():
         if graphed is not None:
@@ -198,7 +199,7 @@ def run_gpu(args):
             v = video_h.to(dev, non_blocking=True)
             a = audio_h.to(dev, non_blocking=True)
             h = hm_h.to(dev, non_blocking=True)
-            loss = train_step(cfg, model, opt, [v], a, h, lr=cfg.SOLVER.BASE_LR)
+            loss = train_step(cfg, model, opt, [v], a, h, lr=cfg.SOLVER.BASE_LR, scaler=scaler)
         loss_h.copy_(loss.reshape(1), non_blocking=True)
         return loss
 
@@ -206,7 +207,7 @@ def run_gpu(args):
         # Park the GPU behind a ~70 ms spin kernel so the host can enqueue the whole eager step first: the
         # per-launch CUDA events then bracket kernels that run back to back (no host-side gaps inside the deltas).
         torch.cuda._sleep(int(0.07 * 1.9e9))
-        return train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync)
+        return train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync, scaler=scaler)
 
     def timed(fn, steps, profile=False):
         barrier()
@@ -262,8 +263,9 @@ def run_gpu(args):
     out = {
         "metric": METRIC, "value": clips / (total_ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}", "droppath": cfg.MVIT.DROPPATH_RATE,
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "precision": args.precision + (" storage, fp32 accumulate / master weights" if args.precision == "bf16" else
+                                                                        " storage + GradScaler (TRAIN.MIXED_PRECISION), fp32 accumulate / master weights"), "global_batch": B * world, "parallelism": f"dp{world}", "droppath": cfg.MVIT.DROPPATH_RATE,
                    "l2": "192 MiB buffer rewritten before every timed step (activations per step also exceed L2)",
                    "optimizer": "AdamW (torch fused) + clip_grad_norm_ 1.0", "cuda_graph": graphed is not None},
         "e2e": {"value": clips / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -293,6 +295,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="csts_b200", choices=["csts_b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit storage mode: bf16 (headline, BASELINE.json) or fp16 = TRAIN.MIXED_PRECISION with GradScaler")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

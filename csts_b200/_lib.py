@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSTS_B200_LIB selects another build of the same library (A/B tuning runs only)
 LIB_PATH = os.environ.get("CSTS_B200_LIB") or os.path.join(_HERE, "libcsts_b200.so")
 
-F32, BF16 = 0, 1
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+F32, BF16, F16 = 0, 1, 2
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 
 class GemmArgs(C.Structure):
@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("a_kmajor", C.c_int32), ("b_kmajor", C.c_int32),
         ("c_dtype", C.c_int32), ("act", C.c_int32), ("accumulate", C.c_int32), ("res_mod", C.c_int32),
         ("split_k", C.c_int32), ("alpha", C.c_float), ("backend", C.c_int32), ("rows_per_scale", C.c_int32),
+        ("a_dtype", C.c_int32), ("b_dtype", C.c_int32), ("z_dtype", C.c_int32),
     ]
 
 
@@ -41,7 +42,7 @@ class PoolArgs(C.Structure):
         ("Ti", C.c_int32), ("Hi", C.c_int32), ("Wi", C.c_int32),
         ("To", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
-        ("transposed", C.c_int32), ("eps", C.c_float),
+        ("transposed", C.c_int32), ("eps", C.c_float), ("dtype", C.c_int32),
     ]
 
 
@@ -54,6 +55,7 @@ class WgradArgs(C.Structure):
         ("Ts", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
         ("Tb", C.c_int32), ("Hb", C.c_int32), ("Wb", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("small_dtype", C.c_int32), ("big_dtype", C.c_int32),
     ]
 
 
@@ -66,9 +68,9 @@ SIGNATURES = {
     "csts_gemm": [C.POINTER(GemmArgs), _P],
     "csts_layernorm_fwd": [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _F, _P],
     "csts_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
-    "csts_softmax_fwd": [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
-    "csts_softmax_bwd": [_P, _P, _P, _L, _I, _I, _I, _F, _P],
-    "csts_cast_bf16": [_P, _P, _L, _I, _I, _P, _I, _P],
+    "csts_softmax_fwd": [_P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
+    "csts_softmax_bwd": [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P],
+    "csts_cast16": [_P, _P, _I, _L, _I, _I, _P, _I, _P],
     "csts_permute_021": [_P, _P, _I, _I, _I, _I, _P],
     "csts_add_f32": [_P, _P, _P, _L, _P],
     "csts_scale_f32": [_P, _P, _P, _L, _P],
@@ -79,12 +81,12 @@ SIGNATURES = {
     "csts_maxpool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "csts_upsample_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "csts_upsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "csts_im2col_patch": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "csts_im2col_patch": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "csts_pos_embed": [_P, _P, _P, _I, _I, _I, _P],
     "csts_pos_embed_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "csts_reweight_fwd": [_P, _P, _P, _I, _I, _I, _I, _L, _P],
     "csts_reweight_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _P],
-    "csts_token_mean_fwd": [_P, _P, _I, _I, _I, _P],
+    "csts_token_mean_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "csts_token_mean_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "csts_classifier_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csts_classifier_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -78,6 +78,10 @@ int csts_gemm_backend(const csts_gemm_args* a) {
 
 int csts_gemm(const csts_gemm_args* a, void* stream) {
   CSTS_REQUIRE(a != nullptr, "gemm: null argument block");
+  CSTS_REQUIRE((a->a_dtype == CSTS_BF16 || a->a_dtype == CSTS_F16) && (a->b_dtype == CSTS_BF16 || a->b_dtype == CSTS_F16),
+               "gemm: a_dtype / b_dtype must be 1 (bf16) or 2 (f16), got %d / %d", a->a_dtype, a->b_dtype);
+  CSTS_REQUIRE(a->c_dtype >= 0 && a->c_dtype <= 2, "gemm: c_dtype %d", a->c_dtype);
+  if (a->Z) CSTS_REQUIRE(a->z_dtype == CSTS_BF16 || a->z_dtype == CSTS_F16, "gemm: z_dtype must be 1 (bf16) or 2 (f16)");
   cudaStream_t st = (cudaStream_t)stream;
   if (a->backend == 1) return csts_gemm_mma_launch(*a, st);
   if (a->backend == 2) return csts_gemm_tc_launch(*a, st);

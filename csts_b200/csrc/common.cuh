@@ -1,12 +1,19 @@
 // Shared device/host helpers for libcsts_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
+typedef __half f16;
+typedef __half2 f162;
+
+// Storage types (include/csts_b200.h): forward activations and operand copies of the weights are IEEE
+// fp16 (10 mantissa bits — their rounding is what limits gradient parity), gradients are bf16 (fp32 range).
+enum { CSTS_F32 = 0, CSTS_BF16 = 1, CSTS_F16 = 2 };
 
 // ---- error plumbing (no exception crosses the C ABI) -----------------------------------------
 void csts_set_error(const char* fmt, ...);
@@ -142,7 +149,10 @@ template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
 template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_f<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// 4-wide vector access (16 B for float, 8 B for bf16); pointer must be aligned accordingly
+template <> __device__ __forceinline__ float ld_f<f16>(const f16* p) { return __half2float(*p); }
+template <> __device__ __forceinline__ void st_f<f16>(f16* p, float v) { *p = __float2half_rn(v); }
+
+// 4-wide vector access (16 B for float, 8 B for bf16 / f16); pointer must be aligned accordingly
 template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
 template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
   float4 t = *reinterpret_cast<const float4*>(p);
@@ -165,7 +175,33 @@ template <> __device__ __forceinline__ void st4<bf16>(bf16* p, const float (&v)[
   *reinterpret_cast<uint2*>(p) = t;
 }
 
+template <> __device__ __forceinline__ void ld4<f16>(const f16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __half22float2(*reinterpret_cast<f162*>(&t.x)), b = __half22float2(*reinterpret_cast<f162*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <> __device__ __forceinline__ void st4<f16>(f16* p, const float (&v)[4]) {
+  f162 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
 __device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
   bf162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ uint32_t pack_f162(float a, float b) {
+  f162 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// two 16-bit values in one register <-> two floats, for T in {bf16, f16}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float a, float b) { return pack_bf162(a, b); }
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float a, float b) { return pack_f162(a, b); }
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<bf16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack2<f16>(uint32_t w) { return __half22float2(*reinterpret_cast<f162*>(&w)); }

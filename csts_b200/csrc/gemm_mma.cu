@@ -1,4 +1,4 @@
-// Generic strided / batched bf16 GEMM on legacy tensor-core instructions (mma.sync m16n8k16).
+// Generic strided / batched 16-bit GEMM on legacy tensor-core instructions (mma.sync m16n8k16).
 //
 // Role in the design: this is the *shape-agnostic* kernel — any operand
 // majorness, two-level batch strides (batch, head), ragged M/N/K (Nk = 260, M = 8), split-K with
@@ -36,6 +36,18 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// mma.sync needs one operand type: a mixed (bf16 gradient x f16 activation) product re-rounds the f16
+// fragment to bf16 in registers (this kernel only carries the small odd-shaped GEMMs of the path)
+__device__ __forceinline__ uint32_t f162_to_bf162(uint32_t h) {
+  float2 f = unpack2<f16>(h);
+  return pack_bf162(f.x, f.y);
 }
 
 // smem element offset of the 16-byte chunk holding (row, k) for a tile of extent 128 (mn) x 32 (k)
@@ -78,7 +90,7 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, int64_t ld, in
 struct Epi {
   void* C; void* Z; const float* bias; const float* residual; const float* row_scale; int rows_per_scale;
   int64_t ldc, ldz, ldr;
-  int M, N, c_dtype, act, accumulate, res_mod, atomic, first_split;
+  int M, N, c_dtype, z_half, act, accumulate, res_mod, atomic, first_split;
   float alpha;
 };
 
@@ -101,12 +113,19 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n, float v0, 
   }
   if (e.bias) { v0 += e.bias[n]; if (two) v1 += e.bias[n + 1]; }
   if (e.act == 1) {          // C = gelu(v), Z = gelu'(v)
-    if (e.Z) {
+    if (e.Z && e.z_half) {
+      f16* z = reinterpret_cast<f16*>(e.Z) + (int64_t)m * e.ldz + n;
+      z[0] = __float2half_rn(gelu_erf_grad(v0)); if (two) z[1] = __float2half_rn(gelu_erf_grad(v1));
+    } else if (e.Z) {
       bf16* z = reinterpret_cast<bf16*>(e.Z) + (int64_t)m * e.ldz + n;
       z[0] = __float2bfloat16_rn(gelu_erf_grad(v0)); if (two) z[1] = __float2bfloat16_rn(gelu_erf_grad(v1));
     }
     v0 = gelu_erf(v0); v1 = gelu_erf(v1);
-  } else if (e.act == 2) {   // C = v * Z
+  } else if (e.act == 2 && e.z_half) {   // C = v * Z
+    const f16* z = reinterpret_cast<const f16*>(e.Z) + (int64_t)m * e.ldz + n;
+    v0 *= __half2float(z[0]);
+    if (two) v1 *= __half2float(z[1]);
+  } else if (e.act == 2) {
     const bf16* z = reinterpret_cast<const bf16*>(e.Z) + (int64_t)m * e.ldz + n;
     v0 *= __bfloat162float(z[0]);
     if (two) v1 *= __bfloat162float(z[1]);
@@ -120,6 +139,10 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n, float v0, 
     float* c = reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n;
     if (e.accumulate) { v0 += c[0]; if (two) v1 += c[1]; }
     c[0] = v0; if (two) c[1] = v1;
+  } else if (e.c_dtype == CSTS_F16) {
+    f16* c = reinterpret_cast<f16*>(e.C) + (int64_t)m * e.ldc + n;
+    if (e.accumulate) { v0 += __half2float(c[0]); if (two) v1 += __half2float(c[1]); }
+    c[0] = __float2half_rn(v0); if (two) c[1] = __float2half_rn(v1);
   } else {
     bf16* c = reinterpret_cast<bf16*>(e.C) + (int64_t)m * e.ldc + n;
     if (e.accumulate) { v0 += __bfloat162float(c[0]); if (two) v1 += __bfloat162float(c[1]); }
@@ -136,6 +159,8 @@ __global__ void __launch_bounds__(THREADS) gemm_mma_kernel(csts_gemm_args p, int
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps, warp tile 64 x 32
+  const bool a_half = p.a_dtype == CSTS_F16, b_half = p.b_dtype == CSTS_F16;
+  const bool both_half = a_half && b_half;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   int z = blockIdx.z;
   const int split = z % p.split_k;
@@ -207,18 +232,38 @@ __global__ void __launch_bounds__(THREADS) gemm_mma_kernel(csts_gemm_args p, int
           ldsm4t(smem_u32(b_s + tile_off<false>(n, k)), bfr[nj]);
         }
       }
+      if (both_half) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-          mma16816(acc[mi][ni], af[mi], bfr[ni >> 1][(ni & 1) * 2], bfr[ni >> 1][(ni & 1) * 2 + 1]);
+          for (int ni = 0; ni < 4; ++ni)
+            mma16816_f16(acc[mi][ni], af[mi], bfr[ni >> 1][(ni & 1) * 2], bfr[ni >> 1][(ni & 1) * 2 + 1]);
+      } else {
+        if (a_half) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) af[mi][r] = f162_to_bf162(af[mi][r]);
+        }
+        if (b_half) {
+#pragma unroll
+          for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) bfr[nj][r] = f162_to_bf162(bfr[nj][r]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni)
+            mma16816(acc[mi][ni], af[mi], bfr[ni >> 1][(ni & 1) * 2], bfr[ni >> 1][(ni & 1) * 2 + 1]);
+      }
     }
   }
   cp_async_wait<0>();
 
   Epi e;
   e.ldc = p.ldc; e.ldz = p.ldz; e.ldr = p.ldr;
-  e.M = p.M; e.N = p.N; e.c_dtype = p.c_dtype; e.act = p.act; e.accumulate = p.accumulate;
+  e.M = p.M; e.N = p.N; e.c_dtype = p.c_dtype; e.z_half = p.z_dtype == CSTS_F16; e.act = p.act; e.accumulate = p.accumulate;
   e.res_mod = p.res_mod; e.atomic = p.split_k > 1; e.first_split = (split == 0);
   e.alpha = p.alpha; e.bias = p.bias; e.residual = p.residual;
   e.row_scale = p.row_scale; e.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1;

@@ -1,7 +1,7 @@
 // tcgen05 / TMEM / TMA GEMM (sm_100a) for the Linear layers of CSTS: forward, data-gradient and
 // weight-gradient products.
 //
-//   C[M,N] = epi( sum_k A[m,k] * B[n,k] )         bf16 operands, f32 accumulate in TMEM
+//   C[M,N] = epi( sum_k A[m,k] * B[n,k] )         bf16 / f16 operands (independently), f32 accumulate in TMEM
 //
 //   operand storage   K-major : X[mn][k]  (k contiguous)   forward  (x . W^T)  and dX (dY . W^T^T)
 //                     MN-major: X[k][mn]  (mn contiguous)  weight gradients dW = dY^T . X  (both operands
@@ -122,11 +122,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major [15],
-// b_major [16] (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A format [7,10), B format [10,13) (0 = f16, 1 = bf16, chosen
+// per operand), a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn, int a_bf16, int b_bf16) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct TcParams {
@@ -135,6 +135,8 @@ struct TcParams {
   int64_t sC1, sC2;                 // batch strides of C (elements)
   int M, N, K;
   int c_dtype, act, accumulate, res_mod, rows_per_scale;
+  int a_bf16, b_bf16;               // operand formats of the MMA (0 = f16, 1 = bf16)
+  int c_half, z_half;               // 16-bit C / Z stored as f16 (else bf16)
   int splits, kblocks_per_split;
   int batch, batch2;                // batch = batch1 * batch2; z -> (z / batch2, z % batch2)
   float alpha;
@@ -165,6 +167,34 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+// lane's 32 f32 values -> 16-bit row (64 B = chunks 0..3) of its staging tile
+__device__ __forceinline__ void stage_row16(uint32_t stage, int lane, const float (&v)[32], bool half) {
+  if (half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stage_addr(stage, lane, j), make_uint4(pack_f162(v[8 * j], v[8 * j + 1]), pack_f162(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_f162(v[8 * j + 4], v[8 * j + 5]), pack_f162(v[8 * j + 6], v[8 * j + 7])));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+  }
+}
+// lane's 16-bit staging row -> 32 floats
+__device__ __forceinline__ void unstage_row16(uint32_t stage, int lane, float (&o)[32], bool half) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 t = lds128(stage_addr(stage, lane, j));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = half ? unpack2<f16>(w[i]) : unpack2<bf16>(w[i]);
+      o[8 * j + 2 * i] = f.x;
+      o[8 * j + 2 * i + 1] = f.y;
+    }
+  }
 }
 // global -> registers -> staging.  `gbase` points at (row 0, first byte) of the 32 x 128 B window; rows beyond
 // `rows_valid` and bytes beyond `bytes_valid` read as zero.  The fetch is separated from the put so that the
@@ -285,10 +315,7 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
       v[i] = v[i] * cdf;
     }
     if (p.Z) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(gp[8 * j], gp[8 * j + 1]), pack_bf162(gp[8 * j + 2], gp[8 * j + 3]),
-                                                      pack_bf162(gp[8 * j + 4], gp[8 * j + 5]), pack_bf162(gp[8 * j + 6], gp[8 * j + 7])));
+      stage_row16(stage, lane, gp, p.z_half);
       __syncwarp();
       stage_store<false>(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
       __syncwarp();
@@ -296,16 +323,10 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
   }
   if (EPI == EPI_BF16_DGELU) {
     __syncwarp();
+    float zf[32];
+    unstage_row16(stage, lane, zf, p.z_half);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 t = lds128(stage_addr(stage, lane, j));
-      const bf162* zz = reinterpret_cast<const bf162*>(&t);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[8 * j + 2 * i] *= __low2float(zz[i]);
-        v[8 * j + 2 * i + 1] *= __high2float(zz[i]);
-      }
-    }
+    for (int i = 0; i < 32; ++i) v[i] *= zf[i];
     __syncwarp();
   }
   if (p.row_scale) {
@@ -334,13 +355,10 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
     }
   } else if (!F32 && has_acc) {
     __syncwarp();
+    float of[32];
+    unstage_row16(stage, lane, of, p.c_half);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 t = lds128(stage_addr(stage, lane, j));
-      const bf162* oo = reinterpret_cast<const bf162*>(&t);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { v[8 * j + 2 * i] += __low2float(oo[i]); v[8 * j + 2 * i + 1] += __high2float(oo[i]); }
-    }
+    for (int i = 0; i < 32; ++i) v[i] += of[i];
     __syncwarp();
   }
   if (F32) {
@@ -349,10 +367,7 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
       sts128(stage_addr(stage, lane, j), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
   } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
-                                                    pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+    stage_row16(stage, lane, v, p.c_half);
   }
   __syncwarp();
   stage_store<EPI == EPI_F32_ATOMIC>(stage, cg, p.ldc * ESZ, rows_valid, cols_valid * ESZ, lane);
@@ -361,7 +376,7 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
 
 // Fused attention-softmax epilogues for key counts that fit one tile (N = Lk <= BN <= 256): a warp owns
 // 32 complete rows (lane = row), so the row reductions need no cross-lane traffic at all.
-//   EPI_SOFTMAX : acc = q.k^T          -> C = P  = softmax(alpha * acc)                (bf16, pad columns zero)
+//   EPI_SOFTMAX : acc = q.k^T          -> C = P  = softmax(alpha * acc)                (16-bit, pad columns zero)
 //   EPI_DSOFTMAX: acc = dO.v^T (= dP)  -> C = dS = alpha * P o (dP - rowsum(dP o P))   (P read from Z)
 // replacing the f32 S / dP round trips through HBM and the separate softmax kernels (attention.py:154-155).
 template <int EPI>
@@ -393,17 +408,11 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
       m = mnew;
     } else {
       __syncwarp();
+      float pf[32];
+      unstage_row16(stage, lane, pf, p.z_half);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 t = lds128(stage_addr(stage, lane, j));
-        const bf162* pp = reinterpret_cast<const bf162*>(&t);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int col = c + 8 * j + 2 * i;
-          if (col < ncols) dot = fmaf(__low2float(pp[i]), __uint_as_float(r[8 * j + 2 * i]), dot);
-          if (col + 1 < ncols) dot = fmaf(__high2float(pp[i]), __uint_as_float(r[8 * j + 2 * i + 1]), dot);
-        }
-      }
+      for (int i = 0; i < 32; ++i)
+        if (c + i < ncols) dot = fmaf(pf[i], __uint_as_float(r[i]), dot);
       __syncwarp();
     }
   }
@@ -420,23 +429,13 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
       for (int i = 0; i < 32; ++i) v[i] = (c + i < ncols) ? __expf(__uint_as_float(r[i]) * p.alpha - m) * inv : 0.f;
     } else {
       __syncwarp();
+      float pf[32];
+      unstage_row16(stage, lane, pf, p.z_half);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 t = lds128(stage_addr(stage, lane, j));
-        const bf162* pp = reinterpret_cast<const bf162*>(&t);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int col = c + 8 * j + 2 * i;
-          v[8 * j + 2 * i] = (col < ncols) ? p.alpha * __low2float(pp[i]) * (__uint_as_float(r[8 * j + 2 * i]) - dot) : 0.f;
-          v[8 * j + 2 * i + 1] = (col + 1 < ncols) ? p.alpha * __high2float(pp[i]) * (__uint_as_float(r[8 * j + 2 * i + 1]) - dot) : 0.f;
-        }
-      }
+      for (int i = 0; i < 32; ++i) v[i] = (c + i < ncols) ? p.alpha * pf[i] * (__uint_as_float(r[i]) - dot) : 0.f;
       __syncwarp();
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      sts128(stage_addr(stage, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
-                                                    pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+    stage_row16(stage, lane, v, p.c_half);
     __syncwarp();
     stage_store<false>(stage, cg + c * 2, p.ldc * 2, rows_valid, min(32, nstore - c) * 2, lane);
     __syncwarp();
@@ -527,7 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t idesc = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, p.a_bf16, p.b_bf16);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -691,6 +690,8 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   p.sC1 = a.sC1; p.sC2 = a.sC2; p.batch = a.batch1 * a.batch2; p.batch2 = a.batch2;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.c_dtype = a.c_dtype; p.act = a.act; p.accumulate = a.accumulate; p.res_mod = a.res_mod; p.alpha = a.alpha;
+  p.a_bf16 = a.a_dtype == CSTS_F16 ? 0 : 1; p.b_bf16 = a.b_dtype == CSTS_F16 ? 0 : 1;
+  p.c_half = a.c_dtype == CSTS_F16; p.z_half = a.z_dtype == CSTS_F16;
   const int kblocks = ceil_div(a.K, BK);
   int splits = a.split_k > 1 ? a.split_k : 1;
   if (splits > kblocks) splits = kblocks;
@@ -760,6 +761,7 @@ int effective_splits(const csts_gemm_args& a) {
 
 bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   if (!a.a_kmajor && a.b_kmajor) return false;         // (MN-major A, K-major B) never occurs on the path
+  if (a.a_dtype != a.b_dtype) return false;            // one kind::f16 MMA cannot mix f16 and bf16 operands (faults on sm_100a)
   const int nb = a.batch1 * a.batch2;
   if (a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
   if (((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
@@ -774,13 +776,13 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   if (a.bias && (((uintptr_t)a.bias & 15) || a.N % 4 != 0)) return false;
   if (a.split_k > 1 && (a.c_dtype != 0 || a.act != 0 || a.row_scale)) return false;
   if (a.act == 3 || a.act == 4) {                      // fused softmax / softmax-backward rows
-    if (!a.a_kmajor || !a.b_kmajor || a.c_dtype != 1 || a.N > 256 || a.bias || a.residual || a.accumulate || a.row_scale ||
+    if (!a.a_kmajor || !a.b_kmajor || a.c_dtype == 0 || a.N > 256 || a.bias || a.residual || a.accumulate || a.row_scale ||
         a.split_k > 1 || a.ldc % 8 != 0 || a.ldc < a.N || a.M < 64)
       return false;
     if (a.act == 4 && (!a.Z || a.ldz != a.ldc || ((uintptr_t)a.Z & 15))) return false;
     return true;
   }
-  if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with bf16 outputs only
+  if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with 16-bit outputs only
   if (a.act != 0 && (a.accumulate || a.residual)) return false;
   if (a.c_dtype != 0 && a.residual) return false;
   if (a.M < 64) return false;                          // skinny problems: the generic kernel with split-K
@@ -810,13 +812,13 @@ int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
     }
   }
   if (!a.a_kmajor) {                                    // (MN, MN): weight gradients, dV / dK of attention
-    if (a.c_dtype == 1) return dispatch<true, true, EPI_BF16>(a, stream);
+    if (a.c_dtype != 0) return dispatch<true, true, EPI_BF16>(a, stream);
     return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);
   }
   if (!a.b_kmajor) {                                    // (K, MN): P.V and dS.K of attention; dX = dY . W of every Linear
     CSTS_REQUIRE((a.act == 0 || a.act == 2) && !atomic, "gemm_tc: (K-major, MN-major) products have no GELU / split-K epilogue");
     if (a.act == 2) return dispatch<false, true, EPI_BF16_DGELU>(a, stream);
-    return a.c_dtype == 1 ? dispatch<false, true, EPI_BF16>(a, stream) : dispatch<false, true, EPI_F32>(a, stream);
+    return a.c_dtype != 0 ? dispatch<false, true, EPI_BF16>(a, stream) : dispatch<false, true, EPI_F32>(a, stream);
   }
   if (a.c_dtype == 0) return atomic ? dispatch<false, false, EPI_F32_ATOMIC>(a, stream) : dispatch<false, false, EPI_F32>(a, stream);
   if (a.act == 1) return dispatch<false, false, EPI_BF16_GELU>(a, stream);

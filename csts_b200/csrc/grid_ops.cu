@@ -32,7 +32,7 @@ __device__ __forceinline__ void tap_coords(int o, int shift, int n_in, int (&idx
   }
 }
 
-template <int D, bool TRANSPOSED, bool NORM>
+template <int D, bool TRANSPOSED, bool NORM, typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, int lh, int lw) {
   pdl_wait();
   constexpr int NJ = (D + 127) / 128;
@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
   const int wpb = blockDim.x >> 5;
   const int Lo = p.To * p.Ho * p.Wo;
   const int64_t total = (int64_t)p.B * p.heads * Lo;
-  const bf16* in = reinterpret_cast<const bf16*>(p.in);
-  bf16* out = reinterpret_cast<bf16*>(p.out);
-  bf16* pre = reinterpret_cast<bf16*>(p.pre);
+  const T* in = reinterpret_cast<const T*>(p.in);
+  T* out = reinterpret_cast<T*>(p.out);
+  T* pre = reinterpret_cast<T*>(p.pre);
   const int sW = (int)p.in_sP, sH = p.Wi * sW, sT = p.Hi * sH;      // input strides in elements (32-bit)
 
   // each warp walks a contiguous range of output positions: coordinates are decoded once and then
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
   }
   for (; idx < idx_end; ++idx) {
     const int o = (to * p.Ho + ho) * p.Wo + wo;
-    const bf16* in_bh = in + b * p.in_sB + hd * p.in_sH;
+    const T* in_bh = in + b * p.in_sB + hd * p.in_sH;
     float acc[NJ][4];
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
@@ -83,16 +83,16 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
     int ot[3], oh[3], ow[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { ot[k] = ti[k] * sT; oh[k] = hi[k] * sH; ow[k] = wi[k] * sW; }
-    const bf16* pl = in_bh + 4 * lane;
+    const T* pl = in_bh + 4 * lane;
     // interior fast path (regular conv): all 9 (kh, kw) taps of a plane are in range -> no per-tap predicates,
     // the 9 loads of a plane are independent and issue back to back
     const bool hw_interior = !TRANSPOSED && vh[0] && vh[2] && vw[0] && vw[2];
     if (hw_interior) {
-      const bf16* c0 = pl + (oh[0] + ow[0]);
+      const T* c0 = pl + (oh[0] + ow[0]);
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         if (!vt[kt]) continue;
-        const bf16* pk = c0 + ot[kt];
+        const T* pk = c0 + ot[kt];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           if (4 * lane + 128 * j < D) {
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           if (!vw[kw]) continue;
-          const bf16* src = pl + (orow + ow[kw]);
+          const T* src = pl + (orow + ow[kw]);
           const float* wt = s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane;
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
         }
       }
     }
-    bf16* dst = out + b * p.out_sB + hd * p.out_sH + (int64_t)o * p.out_sP;
+    T* dst = out + b * p.out_sB + hd * p.out_sH + (int64_t)o * p.out_sP;
     if (!NORM) {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
         if (c < D) st4(dst + c, acc[j]);
       }
     } else {
-      // the raw conv result is rounded to bf16 first (it is what backward re-reads), and the
+      // the raw conv result is rounded to its storage type first (it is what backward re-reads), and the
       // statistics are taken from the rounded values so forward and backward agree exactly
       float s = 0.f;
 #pragma unroll
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
         int c = 4 * lane + 128 * j;
         if (c < D) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { acc[j][i] = __bfloat162float(__float2bfloat16_rn(acc[j][i])); s += acc[j][i]; }
+          for (int i = 0; i < 4; ++i) { T r16; st_f(&r16, acc[j][i]); acc[j][i] = ld_f(&r16); s += acc[j][i]; }
         }
       }
       const float mean = warp_sum(s) * (1.f / D);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
       }
       const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + p.eps);
       if (lane == 0) { p.mean[idx] = mean; p.rstd[idx] = rstd; }
-      bf16* pdst = pre + idx * D;                 // pre is dense (B, heads, Lo, d)
+      T* pdst = pre + idx * D;                 // pre is dense (B, heads, Lo, d)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         int c = 4 * lane + 128 * j;
@@ -195,15 +195,15 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 // cross-warp reduction is needed and each lane carries only 3 x 4 accumulators per channel group.
 // A block walks a contiguous range of `small` ROWS (b, head, to, ho); inside a row the three kw taps
 // slide over `big` through registers: stride 1 re-uses two of three loads, stride 2 one of three.
-template <int D, int SW>
+template <int D, int SW, typename TS, typename TB>
 __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, int lt, int lh, int lw, int rows_per_block) {
   pdl_wait();
   constexpr int NJ = (D + 127) / 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kt = warp / 3, kh = warp % 3;
   const int64_t rows_total = (int64_t)p.B * p.heads * p.Ts * p.Hs;
-  const bf16* small = reinterpret_cast<const bf16*>(p.small);
-  const bf16* big = reinterpret_cast<const bf16*>(p.big);
+  const TS* small = reinterpret_cast<const TS*>(p.small);
+  const TB* big = reinterpret_cast<const TB*>(p.big);
   float acc[NJ][3][4];
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
@@ -223,14 +223,14 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
   for (int64_t row = beg; row < end; ++row) {
     const int ti = (to << lt) + kt - 1, hi = (ho << lh) + kh - 1;
     if (ti >= 0 && ti < p.Tb && hi >= 0 && hi < p.Hb) {                  // warp-uniform
-      const bf16* srow = small + b * p.small_sB + hd * p.small_sH + (int64_t)((to * p.Hs + ho) * p.Ws) * p.small_sP;
-      const bf16* brow = big + b * p.big_sB + hd * p.big_sH + (int64_t)((ti * p.Hb + hi) * p.Wb) * p.big_sP;
+      const TS* srow = small + b * p.small_sB + hd * p.small_sH + (int64_t)((to * p.Hs + ho) * p.Ws) * p.small_sP;
+      const TB* brow = big + b * p.big_sB + hd * p.big_sH + (int64_t)((ti * p.Hb + hi) * p.Wb) * p.big_sP;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int c = 4 * lane + 128 * j;
         if (c >= D) continue;
-        const bf16* bcol = brow + c;
-        const bf16* scol = srow + c;
+        const TB* bcol = brow + c;
+        const TS* scol = srow + c;
         const int bsP = (int)p.big_sP, ssP = (int)p.small_sP;
         auto ld_big = [&](int wi, float (&v)[4]) {
           if (wi >= 0 && wi < p.Wb) ld4(bcol + wi * bsP, v);
@@ -469,7 +469,7 @@ int log2_exact(int v) {
   return (1 << l) == v ? l : -1;
 }
 
-template <int D>
+template <int D, typename T>
 int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   int64_t total = (int64_t)p.B * p.heads * p.To * p.Ho * p.Wo;
   int grid = grid_for(total, 8);
@@ -477,11 +477,11 @@ int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   int lt = log2_exact(p.st), lh = log2_exact(p.sh), lw = log2_exact(p.sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv: strides must be powers of two (%d,%d,%d)", p.st, p.sh, p.sw);
   if (p.transposed) {
-    if (norm) launch_pdl(dwconv_kernel<D, true, true>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
-    else launch_pdl(dwconv_kernel<D, true, false>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    if (norm) launch_pdl(dwconv_kernel<D, true, true, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    else launch_pdl(dwconv_kernel<D, true, false, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
   } else {
-    if (norm) launch_pdl(dwconv_kernel<D, false, true>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
-    else launch_pdl(dwconv_kernel<D, false, false>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    if (norm) launch_pdl(dwconv_kernel<D, false, true, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    else launch_pdl(dwconv_kernel<D, false, false, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
   }
   return csts_check_launch("dwconv");
 }
@@ -498,7 +498,10 @@ int csts_dwconv(const csts_pool_args* p, void* stream) {
   if (p->gamma) CSTS_REQUIRE(p->beta && p->pre && p->mean && p->rstd, "dwconv: norm epilogue needs beta/pre/mean/rstd");
   if ((int64_t)p->B * p->heads * p->To * p->Ho * p->Wo == 0) return 0;
   CSTS_REQUIRE((int64_t)p->Ti * p->Hi * p->Wi * p->in_sP < (1LL << 31), "dwconv: one (batch, head) slab must stay below 2^31 elements");
-  return p->d == 96 ? launch_dwconv<96>(*p, (cudaStream_t)stream) : launch_dwconv<192>(*p, (cudaStream_t)stream);
+  CSTS_REQUIRE(p->dtype == CSTS_BF16 || p->dtype == CSTS_F16, "dwconv: dtype must be 1 (bf16) or 2 (f16)");
+  if (p->dtype == CSTS_F16)
+    return p->d == 96 ? launch_dwconv<96, f16>(*p, (cudaStream_t)stream) : launch_dwconv<192, f16>(*p, (cudaStream_t)stream);
+  return p->d == 96 ? launch_dwconv<96, bf16>(*p, (cudaStream_t)stream) : launch_dwconv<192, bf16>(*p, (cudaStream_t)stream);
 }
 
 int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
@@ -513,10 +516,20 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   int rows_per_block = (int)((rows_total + grid - 1) / grid);
   grid = (int)((rows_total + rows_per_block - 1) / rows_per_block);
   cudaStream_t st = (cudaStream_t)stream;
-#define WGRAD(D_, SW_) launch_pdl(dwconv_wgrad_kernel<D_, SW_>, dim3(grid), dim3(288), 0, st, *p, lt, lh, lw, rows_per_block)
+  CSTS_REQUIRE((p->small_dtype == CSTS_BF16 || p->small_dtype == CSTS_F16) && (p->big_dtype == CSTS_BF16 || p->big_dtype == CSTS_F16),
+               "dwconv_wgrad: operand dtypes must be 1 (bf16) or 2 (f16)");
+#define WGRAD_T(D_, SW_, TS_, TB_) launch_pdl(dwconv_wgrad_kernel<D_, SW_, TS_, TB_>, dim3(grid), dim3(288), 0, st, *p, lt, lh, lw, rows_per_block)
+#define WGRAD(D_, SW_)                                                                        \
+  do {                                                                                        \
+    if (p->small_dtype == CSTS_BF16 && p->big_dtype == CSTS_F16) WGRAD_T(D_, SW_, bf16, f16); \
+    else if (p->small_dtype == CSTS_F16 && p->big_dtype == CSTS_BF16) WGRAD_T(D_, SW_, f16, bf16); \
+    else if (p->small_dtype == CSTS_BF16) WGRAD_T(D_, SW_, bf16, bf16);                       \
+    else WGRAD_T(D_, SW_, f16, f16);                                                          \
+  } while (0)
   if (p->d == 96) { if (p->sw == 1) WGRAD(96, 1); else if (p->sw == 2) WGRAD(96, 2); else WGRAD(96, 0); }
   else { if (p->sw == 1) WGRAD(192, 1); else if (p->sw == 2) WGRAD(192, 2); else WGRAD(192, 0); }
 #undef WGRAD
+#undef WGRAD_T
   return csts_check_launch("dwconv_wgrad");
 }
 

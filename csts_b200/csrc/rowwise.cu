@@ -169,14 +169,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int frame_of(int i, int thw, int hw) { return i < thw ? i / hw : i - thw; }
 
-__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, bf16* __restrict__ P, int64_t rows, int n,
+template <typename TP>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, TP* __restrict__ P, int64_t rows, int n,
                                                           int lds, int ldp, int nq, int mask_hw, int mask_t) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
     const float* s = S + row * lds;
-    bf16* p = P + row * ldp;
+    TP* p = P + row * ldp;
     const int thw = mask_t * mask_hw;
     const int fq = mask_hw > 0 ? frame_of((int)(row % nq), thw, mask_hw) : 0;
     float mx = -INFINITY;
@@ -197,27 +198,28 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
         bool ok = mask_hw <= 0 || frame_of(c, thw, mask_hw) == fq;
         if (ok) v = __expf(s[c] - mx) * inv;
       }
-      p[c] = __float2bfloat16_rn(v);
+      st_f(p + c, v);
     }
   }
 }
 
-// dS = scale * P o (dP - rowsum(dP o P)); dS bf16 with zeroed pad columns
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
+// dS = scale * P o (dP - rowsum(dP o P)); dS 16-bit with zeroed pad columns
+template <typename TP, typename TDS>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const TP* __restrict__ P, const float* __restrict__ dP, TDS* __restrict__ dS,
                                                           int64_t rows, int n, int ldp, int lddp, float scale) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
-    const bf16* p = P + row * ldp;
+    const TP* p = P + row * ldp;
     const float* dp = dP + row * lddp;
-    bf16* ds = dS + row * ldp;
+    TDS* ds = dS + row * ldp;
     float dot = 0.f;
-    for (int c = lane; c < n; c += 32) dot += __bfloat162float(p[c]) * dp[c];
+    for (int c = lane; c < n; c += 32) dot += ld_f(p + c) * dp[c];
     dot = warp_sum(dot);
     for (int c = lane; c < ldp; c += 32) {
-      float v = c < n ? scale * __bfloat162float(p[c]) * (dp[c] - dot) : 0.f;
-      ds[c] = __float2bfloat16_rn(v);
+      float v = c < n ? scale * ld_f(p + c) * (dp[c] - dot) : 0.f;
+      st_f(ds + c, v);
     }
   }
 }
@@ -225,8 +227,9 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict
 // ------------------------------------------------------------------------------------------------
 // casts / permutes / elementwise
 // ------------------------------------------------------------------------------------------------
-// f32 [rows, cols] -> bf16 [rows, ld_out] (zero padded columns)
-__global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int cols, int ld_out,
+// f32 [rows, cols] -> 16-bit [rows, ld_out] (zero padded columns), T in {bf16, f16}
+template <typename T>
+__global__ void cast_pad_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t rows, int cols, int ld_out,
                                 const float* __restrict__ row_scale, int rows_per_scale) {
   pdl_wait();
   int64_t total = rows * ld_out;
@@ -235,11 +238,12 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict_
     int c = (int)(i - r * ld_out);
     float v = c < cols ? src[r * cols + c] : 0.f;
     if (row_scale) v *= row_scale[r / rows_per_scale];
-    dst[i] = __float2bfloat16_rn(v);
+    st_f(dst + i, v);
   }
 }
 // cols must be a multiple of 4 (a 4-vector never straddles rows)
-__global__ void cast_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n4, int cols4,
+template <typename T>
+__global__ void cast_vec_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n4, int cols4,
                                 const float* __restrict__ row_scale, int rows_per_scale) {
   pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -330,7 +334,7 @@ int grid_for(int64_t work_items, int per_block) {
 
 extern "C" {
 
-// dtype codes: 0 = f32, 1 = bf16
+// dtype codes: 0 = f32, 1 = bf16, 2 = f16
 int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,
                        float* rstd, int64_t rows, int width, float eps, void* stream) {
   CSTS_REQUIRE(width % 4 == 0 && width <= LN_MAX_WIDTH, "layernorm: width %d unsupported (multiple of 4, <= 768)", width);
@@ -345,8 +349,10 @@ int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const f
     else if (width <= 384) LN_FWD_J(TI, TO, 3);          \
     else LN_FWD_J(TI, TO, 6);                            \
   } while (0)
-  if (x_dtype == 0 && y_dtype == 1) LN_FWD(float, bf16);
+  if (x_dtype == 0 && y_dtype == 2) LN_FWD(float, f16);
+  else if (x_dtype == 0 && y_dtype == 1) LN_FWD(float, bf16);
   else if (x_dtype == 0 && y_dtype == 0) LN_FWD(float, float);
+  else if (x_dtype == 2 && y_dtype == 2) LN_FWD(f16, f16);
   else if (x_dtype == 1 && y_dtype == 1) LN_FWD(bf16, bf16);
   else if (x_dtype == 1 && y_dtype == 0) LN_FWD(bf16, float);
   else CSTS_REQUIRE(false, "layernorm: bad dtype codes %d %d", x_dtype, y_dtype);
@@ -373,6 +379,9 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
     else LN_BWD_J(TX, TDY, TDX, 6);                      \
   } while (0)
   if (x_dtype == 0 && dy_dtype == 1 && dx_dtype == 0) LN_BWD(float, bf16, float);
+  else if (x_dtype == 0 && dy_dtype == 2 && dx_dtype == 0) LN_BWD(float, f16, float);
+  else if (x_dtype == 2 && dy_dtype == 2 && dx_dtype == 2) LN_BWD(f16, f16, f16);
+  else if (x_dtype == 2 && dy_dtype == 1 && dx_dtype == 1) LN_BWD(f16, bf16, bf16);
   else if (x_dtype == 1 && dy_dtype == 1 && dx_dtype == 1) LN_BWD(bf16, bf16, bf16);
   else if (x_dtype == 0 && dy_dtype == 0 && dx_dtype == 0) LN_BWD(float, float, float);
   else CSTS_REQUIRE(false, "layernorm_bwd: unsupported dtype combination x=%d dy=%d dx=%d", x_dtype, dy_dtype, dx_dtype);
@@ -381,41 +390,60 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
   return csts_check_launch("layernorm_bwd");
 }
 
-int csts_softmax_fwd(const float* S, void* P, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t, void* stream) {
+int csts_softmax_fwd(const float* S, void* P, int p_dtype, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t,
+                     void* stream) {
   if (rows == 0) return 0;
   CSTS_REQUIRE(ldp >= n && lds >= n, "softmax: leading dims smaller than n");
-  launch_pdl(softmax_fwd_kernel, dim3(grid_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, S, (bf16*)P, rows, n, lds, ldp, nq, mask_hw, mask_t);
+  CSTS_REQUIRE(p_dtype == CSTS_BF16 || p_dtype == CSTS_F16, "softmax: P must be bf16 or f16");
+  if (p_dtype == CSTS_F16)
+    launch_pdl(softmax_fwd_kernel<f16>, dim3(grid_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, S, (f16*)P, rows, n, lds, ldp, nq, mask_hw, mask_t);
+  else
+    launch_pdl(softmax_fwd_kernel<bf16>, dim3(grid_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, S, (bf16*)P, rows, n, lds, ldp, nq, mask_hw, mask_t);
   return csts_check_launch("softmax_fwd");
 }
 
-int csts_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n, int ldp, int lddp, float scale, void* stream) {
+int csts_softmax_bwd(const void* P, int p_dtype, const float* dP, void* dS, int ds_dtype, int64_t rows, int n, int ldp, int lddp,
+                     float scale, void* stream) {
   if (rows == 0) return 0;
-  launch_pdl(softmax_bwd_kernel, dim3(grid_for(rows, 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)P, dP, (bf16*)dS, rows, n, ldp, lddp, scale);
+  CSTS_REQUIRE((p_dtype == CSTS_BF16 || p_dtype == CSTS_F16) && (ds_dtype == CSTS_BF16 || ds_dtype == CSTS_F16),
+               "softmax_bwd: P and dS must be bf16 or f16");
+  cudaStream_t st = (cudaStream_t)stream;
+#define SM_BWD(TP, TDS) launch_pdl(softmax_bwd_kernel<TP, TDS>, dim3(grid_for(rows, 8)), dim3(256), 0, st, (const TP*)P, dP, (TDS*)dS, rows, n, ldp, lddp, scale)
+  if (p_dtype == CSTS_F16 && ds_dtype == CSTS_F16) SM_BWD(f16, f16);
+  else if (p_dtype == CSTS_F16) SM_BWD(f16, bf16);
+  else if (ds_dtype == CSTS_F16) SM_BWD(bf16, f16);
+  else SM_BWD(bf16, bf16);
+#undef SM_BWD
   return csts_check_launch("softmax_bwd");
 }
 
 // row m of the result is multiplied by row_scale[m / rows_per_scale] when row_scale != NULL
-int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_out, const float* row_scale, int rows_per_scale,
-                   void* stream) {
+int csts_cast16(const float* src, void* dst, int dst_dtype, int64_t rows, int cols, int ld_out, const float* row_scale,
+                int rows_per_scale, void* stream) {
   if (rows * cols == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  CSTS_REQUIRE(dst_dtype == CSTS_BF16 || dst_dtype == CSTS_F16, "cast: dst must be bf16 or f16");
   if (row_scale) CSTS_REQUIRE(rows_per_scale > 0, "cast: rows_per_scale must be positive");
+  const bool half = dst_dtype == CSTS_F16;
   if (ld_out == cols && cols % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
     int64_t n4 = rows * cols / 4;
-    launch_pdl(cast_vec_kernel, dim3(grid_for(n4, 256)), dim3(256), 0, st, src, (bf16*)dst, n4, cols / 4, row_scale, rows_per_scale);
+    if (half) launch_pdl(cast_vec_kernel<f16>, dim3(grid_for(n4, 256)), dim3(256), 0, st, src, (f16*)dst, n4, cols / 4, row_scale, rows_per_scale);
+    else launch_pdl(cast_vec_kernel<bf16>, dim3(grid_for(n4, 256)), dim3(256), 0, st, src, (bf16*)dst, n4, cols / 4, row_scale, rows_per_scale);
   } else {
     CSTS_REQUIRE(ld_out >= cols, "cast: ld_out < cols");
-    launch_pdl(cast_pad_kernel, dim3(grid_for(rows * ld_out, 256)), dim3(256), 0, st, src, (bf16*)dst, rows, cols, ld_out, row_scale, rows_per_scale);
+    if (half) launch_pdl(cast_pad_kernel<f16>, dim3(grid_for(rows * ld_out, 256)), dim3(256), 0, st, src, (f16*)dst, rows, cols, ld_out, row_scale, rows_per_scale);
+    else launch_pdl(cast_pad_kernel<bf16>, dim3(grid_for(rows * ld_out, 256)), dim3(256), 0, st, src, (bf16*)dst, rows, cols, ld_out, row_scale, rows_per_scale);
   }
-  return csts_check_launch("cast_bf16");
+  return csts_check_launch("cast16");
 }
 
-// src f32 [a][b][c] -> dst [a][c][b], dst dtype 0 f32 / 1 bf16
+// src f32 [a][b][c] -> dst [a][c][b], dst dtype 0 f32 / 1 bf16 / 2 f16
 int csts_permute_021(const float* src, void* dst, int dst_dtype, int a, int b, int c, void* stream) {
   if ((int64_t)a * b * c == 0) return 0;
   dim3 grid(ceil_div(c, 32), ceil_div(b, 32), a), block(32, 8);
   CSTS_REQUIRE(a <= 65535 && grid.y <= 65535, "permute_021: dims too large");
   if (dst_dtype == 0) launch_pdl(permute_021_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (float*)dst, a, b, c);
+  else if (dst_dtype == CSTS_F16) launch_pdl(permute_021_kernel<f16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (f16*)dst, a, b, c);
   else launch_pdl(permute_021_kernel<bf16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (bf16*)dst, a, b, c);
   return csts_check_launch("permute_021");
 }
@@ -444,6 +472,7 @@ int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_
   if (rows_per_block < 64) rows_per_block = 64;
   dim3 grid(bx, ceil_div(M, rows_per_block));
   if (x_dtype == 0) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)X, out, M, N, ld, rows_per_block);
+  else if (x_dtype == CSTS_F16) launch_pdl(colsum_kernel<f16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const f16*)X, out, M, N, ld, rows_per_block);
   else launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)X, out, M, N, ld, rows_per_block);
   return csts_check_launch("colsum");
 }

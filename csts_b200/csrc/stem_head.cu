@@ -12,10 +12,11 @@ int grid_for(int64_t work_items, int per_block) {
 
 // ------------------------------------------------------------------------------------------------
 // im2col for PatchEmbed: Conv3d k(3,7,7) s(2,4,4) p(1,3,3)      ref: stem_helper.py:27-38
-// x f32 (B, Cin, T, H, W) -> patches bf16 [B*To*Ho*Wo, Kp], column = ((c*3 + kt)*7 + kh)*7 + kw,
+// x f32 (B, Cin, T, H, W) -> patches (bf16 / f16) [B*To*Ho*Wo, Kp], column = ((c*3 + kt)*7 + kh)*7 + kw,
 // columns >= Cin*147 are zero (Kp is the GEMM-friendly padded width).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int T, int H,
+template <typename TO>
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, TO* __restrict__ out, int B, int Cin, int T, int H,
                                                      int W, int Kp) {
   pdl_wait();
   const int To = T / 2, Ho = H / 4, Wo = W / 4;
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
       int ti = to * 2 + kt - 1, hi = ho * 4 + kh - 3, wi = wo * 4 + kw - 3;
       if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((b * Cin + c) * T + ti) * H + hi) * W + wi];
     }
-    out[i] = __float2bfloat16_rn(v);
+    st_f(out + i, v);
   }
 }
 
@@ -123,8 +124,9 @@ __global__ void reweight_bwd_kernel(const float* __restrict__ dout, const float*
   }
 }
 
-// out[b][c] = mean_n x[b][n][c]  (bf16 out: it is the A operand of the NCE projection GEMM)
-__global__ void token_mean_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int N, int C) {
+// out[b][c] = mean_n x[b][n][c]  (16-bit out: it is the A operand of the NCE projection GEMM)
+template <typename TO>
+__global__ void token_mean_fwd_kernel(const float* __restrict__ x, TO* __restrict__ out, int B, int N, int C) {
   pdl_wait();
   const int64_t total = (int64_t)B * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -132,7 +134,7 @@ __global__ void token_mean_fwd_kernel(const float* __restrict__ x, bf16* __restr
     int64_t b = i / C;
     float acc = 0.f;
     for (int n = 0; n < N; ++n) acc += x[(b * N + n) * C + c];
-    out[i] = __float2bfloat16_rn(acc / (float)N);
+    st_f(out + i, acc / (float)N);
   }
 }
 // dx[b][n][c] (+)= dout[b][c] / N
@@ -258,11 +260,13 @@ __global__ void classifier_bwd_stem_kernel(const float* __restrict__ dlogits, co
 
 extern "C" {
 
-int csts_im2col_patch(const float* x, void* patches, int B, int Cin, int T, int H, int W, int Kp, void* stream) {
+int csts_im2col_patch(const float* x, void* patches, int dtype, int B, int Cin, int T, int H, int W, int Kp, void* stream) {
+  CSTS_REQUIRE(dtype == CSTS_BF16 || dtype == CSTS_F16, "im2col: patches must be bf16 or f16");
   CSTS_REQUIRE(T % 2 == 0 && H % 4 == 0 && W % 4 == 0 && Kp >= Cin * 147 && Kp % 8 == 0, "im2col: bad geometry");
   int64_t total = (int64_t)B * (T / 2) * (H / 4) * (W / 4) * Kp;
   if (total == 0) return 0;
-  launch_pdl(im2col_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)patches, B, Cin, T, H, W, Kp);
+  if (dtype == CSTS_F16) launch_pdl(im2col_kernel<f16>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (f16*)patches, B, Cin, T, H, W, Kp);
+  else launch_pdl(im2col_kernel<bf16>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)patches, B, Cin, T, H, W, Kp);
   return csts_check_launch("im2col_patch");
 }
 int csts_pos_embed(const float* spatial, const float* temporal, float* pos, int T, int HW, int C, void* stream) {
@@ -287,8 +291,10 @@ int csts_reweight_bwd(const float* dout, const float* x, const float* w, float* 
   launch_pdl(reweight_bwd_kernel, dim3(grid_for((int64_t)B * T * C / 4, 64)), dim3(64), 0, (cudaStream_t)stream, dout, x, w, dx, dw, B, T, S, C, w_sB);
   return csts_check_launch("reweight_bwd");
 }
-int csts_token_mean_fwd(const float* x, void* out_bf16, int B, int N, int C, void* stream) {
-  launch_pdl(token_mean_fwd_kernel, dim3(grid_for((int64_t)B * C, 64)), dim3(64), 0, (cudaStream_t)stream, x, (bf16*)out_bf16, B, N, C);
+int csts_token_mean_fwd(const float* x, void* out, int out_dtype, int B, int N, int C, void* stream) {
+  CSTS_REQUIRE(out_dtype == CSTS_BF16 || out_dtype == CSTS_F16, "token_mean: out must be bf16 or f16");
+  if (out_dtype == CSTS_F16) launch_pdl(token_mean_fwd_kernel<f16>, dim3(grid_for((int64_t)B * C, 64)), dim3(64), 0, (cudaStream_t)stream, x, (f16*)out, B, N, C);
+  else launch_pdl(token_mean_fwd_kernel<bf16>, dim3(grid_for((int64_t)B * C, 64)), dim3(64), 0, (cudaStream_t)stream, x, (bf16*)out, B, N, C);
   return csts_check_launch("token_mean_fwd");
 }
 int csts_token_mean_bwd(const float* dout, float* dx, int B, int N, int C, int accumulate, void* stream) {

@@ -6,10 +6,15 @@ Forward follows ``MultiScaleBlock.forward`` / ``MultiScaleAttention.forward``
 (av_attention.py:120-152, :229-250, :322-372, :450-473).  Data layout:
 
   residual stream x            f32  (B, N, C)           token-major
-  LayerNorm outputs, qkv, MLP  bf16 (B*N, ...)          GEMM operands
-  qkv                          bf16 (B, N, 3, heads, d) exactly as the qkv GEMM writes it
-  pooled q / k / v             bf16 (B, heads, L', d)
-  attention out                bf16 (B, Lq, heads*d)    written strided by the P.V GEMM
+  LayerNorm outputs, qkv, MLP  16b  (B*N, ...)          GEMM operands
+  qkv                          16b  (B, N, 3, heads, d) exactly as the qkv GEMM writes it
+  pooled q / k / v             16b  (B, heads, L', d)
+  attention out                16b  (B, Lq, heads*d)    written strided by the P.V GEMM
+
+"16b" is the storage type of the model's precision mode (weights.Precision): bf16 for activations and
+their gradients by default, fp16 for both under TRAIN.MIXED_PRECISION (the reference's fp16 autocast +
+GradScaler contract, tools/train_avgaze_net.py:70,99-109).  One tcgen05 MMA cannot mix the two formats,
+so a mode uses a single 16-bit type throughout.
 
 The reference's reshape/permute/contiguous copies around the pooling convs and the head
 split/merge do not exist here: the pooling and attention kernels take element strides.
@@ -44,7 +49,7 @@ def _split_k(m_out, n_out, k_tokens):
 
 
 class _Ref:
-    """A (B, heads, L, d) bf16 tensor addressed by element strides inside `buf`."""
+    """A (B, heads, L, d) 16-bit tensor addressed by element strides inside `buf`."""
     __slots__ = ("buf", "off", "sB", "sH", "sP", "L", "thw")
 
     def __init__(self, buf, off, sB, sH, sP, L, thw):
@@ -65,7 +70,7 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     h, d = spec.heads, spec.head_dim
     M = B * N
     dec = spec.kind == "dec"
-    xn1, mean1, rstd1 = K.layernorm_fwd(x, p["norm1.weight"], p["norm1.bias"], EPS_BLOCK)
+    xn1, mean1, rstd1 = K.layernorm_fwd(x, p["norm1.weight"], p["norm1.bias"], EPS_BLOCK, out_dtype=wc.act)
     qkv = K.gemm(xn1.view(M, C), wc.w(p["attn.qkv.weight"]), M=M, N=3 * C, K=C, bias=p["attn.qkv.bias"])
     qs = (N * 3 * C, d, 3 * C)                       # (batch, head, position) strides inside qkv
     sv = {}
@@ -100,7 +105,7 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     # Lk <= 256 (20 of the 26 blocks): softmax runs in the epilogue of the q.k^T kernel, S never reaches HBM
     fused_softmax = Lk <= 256 and Lq >= 64 and spec.kind != "spatial"
     if fused_softmax:
-        P = torch.empty((B, h, Lq, ldS), dtype=torch.bfloat16, device=x.device)
+        P = torch.empty((B, h, Lq, ldS), dtype=wc.act, device=x.device)
         K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=P, ldc=ldS, alpha=scale, act=3, batch=(B, h),
                sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
     else:
@@ -108,12 +113,12 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
         K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=S, ldc=ldS, alpha=scale, batch=(B, h),
                sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
         if spec.kind == "spatial":
-            P = K.softmax_fwd(S, Lk, ldS, nq=Lq, mask_hw=thw[1] * thw[2], mask_t=thw[0])
+            P = K.softmax_fwd(S, Lk, ldS, nq=Lq, mask_hw=thw[1] * thw[2], mask_t=thw[0], dtype=wc.act)
         else:
-            P = K.softmax_fwd(S, Lk, ldS, nq=Lq)
+            P = K.softmax_fwd(S, Lk, ldS, nq=Lq, dtype=wc.act)
         del S
     Mq = B * Lq
-    o = torch.empty((Mq, C), dtype=torch.bfloat16, device=x.device)
+    o = torch.empty((Mq, C), dtype=wc.act, device=x.device)
     K.gemm(P, v.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=v.sP, out=o, ldc=C, batch=(B, h),
            sA=(h * Lq * ldS, Lq * ldS), sB=(v.sB, v.sH), sC=(Lq * C, d), b_off=v.off)
     # ---- residual path (attention.py:240 / :471) --------------------------------------------------
@@ -129,10 +134,10 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     x1 = K.gemm(o, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, bias=p["attn.proj.bias"], residual=x_res.view(Mq, C),
                 out_dtype=torch.float32, row_scale=dp_scale, rows_per_scale=rps)
     # ---- MLP (attention.py:243-247) -----------------------------------------------------------------
-    xn2, mean2, rstd2 = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], EPS_BLOCK)
+    xn2, mean2, rstd2 = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], EPS_BLOCK, out_dtype=wc.act)
     hid = spec.hidden
     # Z receives GELU'(fc1 pre-activation): the forward epilogue already evaluates it, backward only multiplies
-    Z = torch.empty((Mq, hid), dtype=torch.bfloat16, device=x.device) if save else None
+    Z = torch.empty((Mq, hid), dtype=wc.act, device=x.device) if save else None
     hdn = K.gemm(xn2, wc.w(p["mlp.fc1.weight"]), M=Mq, N=hid, K=C, bias=p["mlp.fc1.bias"], act=1, Z=Z)
     if spec.dim != spec.dim_out:
         base = K.gemm(xn2, wc.w(p["proj.weight"]), M=Mq, N=spec.dim_out, K=C, bias=p["proj.bias"], out_dtype=torch.float32)
@@ -180,7 +185,7 @@ def block_backward(spec, p, wc, sv, dy):
                       out_dtype=torch.float32, split_k=_split_k(m_out, n_out, ktok))
 
     dy = dy.contiguous().view(Mq, Co)
-    g2 = K.cast_bf16(dy, row_scale=dp, rows_per_scale=rps)             # gradient entering the (drop-path scaled) MLP branch
+    g2 = K.cast16(dy, wc.grad, row_scale=dp, rows_per_scale=rps)            # gradient entering the (drop-path scaled) MLP branch
     # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
     dZ = K.gemm(g2, wc.w(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, b_kmajor=False, act=2, Z=sv["Z"])
     g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq)
@@ -191,7 +196,7 @@ def block_backward(spec, p, wc, sv, dy):
     del dZ
     g["norm2.weight"], g["norm2.bias"] = zeros(C), zeros(C)
     if spec.dim != spec.dim_out:
-        gp = g2 if dp is None else K.cast_bf16(dy)                       # the re-based residual is not drop-path scaled
+        gp = g2 if dp is None else K.cast16(dy, wc.grad)                     # the re-based residual is not drop-path scaled
         K.gemm(gp, wc.w(p["proj.weight"]), M=Mq, N=C, K=Co, b_kmajor=False, out=dxn2, accumulate=True)
         g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq)
         g["proj.bias"] = K.colsum(dy, Mq, Co, out=zeros(Co))
@@ -201,7 +206,7 @@ def block_backward(spec, p, wc, sv, dy):
                               add=dy)
     del dxn2, g2
     # ---- attention output projection ------------------------------------------------------------------
-    g1 = K.cast_bf16(dx1, row_scale=dp, rows_per_scale=rps)
+    g1 = K.cast16(dx1, wc.grad, row_scale=dp, rows_per_scale=rps)
     do = K.gemm(g1, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, b_kmajor=False)       # (B, Lq, heads, d)
     g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq)
     g["attn.proj.bias"] = K.colsum(g1, Mq, C, out=zeros(C))
@@ -215,13 +220,13 @@ def block_backward(spec, p, wc, sv, dy):
         dx_skip = K.maxpool_bwd(dx1, sv["arg"], B, thw, C)
     # ---- attention backward ------------------------------------------------------------------------------
     q, k, v, P = sv["q"], sv["k"], sv["v"], sv["P"]
-    dqkv = torch.empty((M, 3 * C), dtype=torch.bfloat16, device=dev)
+    dqkv = torch.empty((M, 3 * C), dtype=wc.grad, device=dev)
     qs = (N * 3 * C, d, 3 * C)
     pooled_q, pooled_kv = spec.stride_q is not None, spec.stride_kv is not None
 
     def grad_target(pooled, L, slot):
         if pooled:
-            t = torch.empty((B, h, L, d), dtype=torch.bfloat16, device=dev)
+            t = torch.empty((B, h, L, d), dtype=wc.grad, device=dev)
             return t, dict(out=t, ldc=d, sC=(h * L * d, L * d), c_off=0)
         return None, dict(out=dqkv, ldc=3 * C, sC=(qs[0], qs[1]), c_off=slot * C)
 
@@ -230,14 +235,14 @@ def block_backward(spec, p, wc, sv, dy):
     K.gemm(P, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=C, batch=(B, h), sA=sP, sB=(Lq * C, d), **tgt)
     if sv["fused_softmax"]:
         # dS = scale * P o (dP - rowsum(dP o P)) in the epilogue of the dO.v^T kernel: dP never reaches HBM
-        dS = torch.empty_like(P)
+        dS = torch.empty(P.shape, dtype=wc.grad, device=dev)
         K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dS, ldc=ldS, alpha=d ** -0.5, act=4, Z=P, batch=(B, h),
                sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP, b_off=v.off)
     else:
         dP = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=dev)
         K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP,
                b_off=v.off)
-        dS = K.softmax_bwd(P, dP, Lk, d ** -0.5)
+        dS = K.softmax_bwd(P, dP, Lk, d ** -0.5, dtype=wc.grad)
         del dP
     dq_t, tgt = grad_target(pooled_q, Lq, 0)
     K.gemm(dS, k.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=k.sP, batch=(B, h), sA=sP, sB=(k.sB, k.sH), b_off=k.off, **tgt)
@@ -251,7 +256,7 @@ def block_backward(spec, p, wc, sv, dy):
         L = grid_out[0] * grid_out[1] * grid_out[2]
         g[nname + ".weight"], g[nname + ".bias"] = zeros(d), zeros(d)
         du = K.layernorm_bwd(dt, pre, mean, rstd, p[nname + ".weight"], g[nname + ".weight"], g[nname + ".bias"],
-                             dx_dtype=torch.bfloat16)
+                             dx_dtype=wc.grad)
         dense = (h * L * d, L * d, d)
         # data gradient: the adjoint gather of the forward conv, written straight into the qkv-gradient slice
         K.dwconv(du, dense, 0, B, h, d, grid_out, stride, p[wname], transposed=not transposed, out=dqkv, out_strides=qs,

@@ -19,7 +19,7 @@ from .. import kernels as K
 from .block import BlockFn, block_forward, block_param_names
 from .build import MODEL_REGISTRY
 from .plan import build_plan
-from .weights import WeightCache
+from .weights import WeightCache, precision_of
 
 
 # ---------------------------------------------------------------------------------------------
@@ -102,12 +102,13 @@ class PatchEmbedFn(torch.autograd.Function):
         B = x.shape[0]
         kdim = weight[0].numel()
         kp = (kdim + 7) // 8 * 8
-        patches = K.im2col_patch(x.contiguous(), kp)
+        patches = K.im2col_patch(x.contiguous(), kp, dtype=wc.act)
         pos = K.pos_embed(pos_spatial, pos_temporal)
         n_tok = pos.shape[0]
         tok = K.gemm(patches, wc.w_padded(weight, kp), M=B * n_tok, N=weight.shape[0], K=kp, bias=bias, residual=pos, res_mod=n_tok,
                      out_dtype=torch.float32)
         ctx.save_for_backward(patches)
+        ctx.wc = wc
         ctx.dims = (B, n_tok, pos_temporal.shape[1], pos_spatial.shape[1], weight.shape, kp)
         return tok.view(B, n_tok, weight.shape[0])
 
@@ -117,7 +118,7 @@ class PatchEmbedFn(torch.autograd.Function):
         B, n_tok, T, HW, wshape, kp = ctx.dims
         Cn = wshape[0]
         dtok = dtok.contiguous()
-        g = K.cast_bf16(dtok.view(B * n_tok, Cn))
+        g = K.cast16(dtok.view(B * n_tok, Cn), ctx.wc.grad)
         M = B * n_tok
         dwp = K.gemm(g, patches, M=Cn, N=kp, K=M, a_kmajor=False, b_kmajor=False, lda=Cn, ldb=kp, out_dtype=torch.float32,
                      split_k=max(1, min(64, M // 2048)))
@@ -136,7 +137,7 @@ class FramePoolFn(torch.autograd.Function):
     def forward(ctx, wc, tok, weight, bias):
         B, N, Cn = tok.shape
         T = N // 64
-        a = K.cast_bf16(tok.contiguous())
+        a = K.cast16(tok.contiguous(), wc.act)
         w = wc.frame_pool_w(weight)
         Kd = 64 * Cn
         out = K.gemm(a.view(B * T, Kd), w, M=B * T, N=weight.shape[0], K=Kd, bias=bias, out_dtype=torch.float32, split_k=24)
@@ -151,7 +152,7 @@ class FramePoolFn(torch.autograd.Function):
         B, N, Cn = a.shape
         T, O, Kd = N // 64, weight.shape[0], 64 * Cn
         dout = dout.contiguous().view(B * T, O)
-        g = K.cast_bf16(dout)
+        g = K.cast16(dout, ctx.wc.grad)
         w = ctx.wc.frame_pool_w(weight)
         dtok = K.gemm(g, w, M=B * T, N=Kd, K=O, b_kmajor=False, ldb=Kd, out_dtype=torch.float32)
         dwp = K.gemm(g, a.view(B * T, Kd), M=O, N=Kd, K=B * T, a_kmajor=False, b_kmajor=False, lda=O, ldb=Kd, out_dtype=torch.float32)
@@ -188,7 +189,7 @@ class MeanProjFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wc, x, weight, bias):
         B, N, Cn = x.shape
-        m = K.token_mean_fwd(x.contiguous(), B, N, Cn)
+        m = K.token_mean_fwd(x.contiguous(), B, N, Cn, dtype=wc.act)
         out = K.gemm(m, wc.w(weight), M=B, N=weight.shape[0], K=Cn, bias=bias, out_dtype=torch.float32)
         ctx.save_for_backward(m)
         ctx.wc, ctx.weight, ctx.dims = wc, weight, (B, N, Cn)
@@ -200,7 +201,7 @@ class MeanProjFn(torch.autograd.Function):
         B, N, Cn = ctx.dims
         O = ctx.weight.shape[0]
         dout = dout.contiguous()
-        g = K.cast_bf16(dout)
+        g = K.cast16(dout, ctx.wc.grad)
         dm = K.gemm(g, ctx.wc.w(ctx.weight), M=B, N=Cn, K=O, b_kmajor=False, ldb=Cn, out_dtype=torch.float32)
         dx = K.token_mean_bwd(dm, B, N, Cn)
         dw = K.gemm(g, m, M=O, N=Cn, K=B, a_kmajor=False, b_kmajor=False, lda=O, ldb=Cn, out_dtype=torch.float32)
@@ -297,7 +298,7 @@ class CSTS(nn.Module):
         trunc_normal_(self.pos_embed_spatial_audio, std=0.02)
         trunc_normal_(self.pos_embed_temporal_audio, std=0.02)
         self.apply(self._init_weights)
-        self._wc = WeightCache()
+        self._wc = WeightCache(precision_of(cfg))
         self._dp_site, self._dp_keep, self._dp_scales = None, None, None
 
     @staticmethod

@@ -56,10 +56,17 @@ def compute_loss(cfg, model, inputs, audio_frames, labels_hm):
     raise NotImplementedError(f"loss {cfg.MODEL.LOSS_FUNC} is outside the CSTS hot path")
 
 
-def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, grad_sync=None):
+def make_grad_scaler(cfg, **kw):
+    """tools/train_avgaze_net.py:277 — enabled only under TRAIN.MIXED_PRECISION (fp16 storage mode)."""
+    return torch.amp.GradScaler("cuda", enabled=bool(cfg.TRAIN.MIXED_PRECISION), **kw)
+
+
+def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, grad_sync=None, scaler=None):
     """Forward, loss, backward, [gradient exchange], clip, optimizer step.  Returns the (device) loss tensor;
     no host sync.  With a DDP-wrapped model the exchange happens inside backward (DDP reducer); for an
-    un-wrapped replica pass grad_sync (e.g. distributed.allreduce_gradients) to average gradients here."""
+    un-wrapped replica pass grad_sync (e.g. distributed.allreduce_gradients) to average gradients here.
+    `scaler` is the reference loop's GradScaler (lines 99-109: scale(loss).backward(), unscale_, clip, step,
+    update); with the fused AdamW none of its calls synchronises the host, so the step stays graph-capturable."""
     if lr is not None:
         for group in optimizer.param_groups:
             if torch.is_tensor(group["lr"]):
@@ -68,17 +75,26 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, 
                 group["lr"] = lr
     loss, _, _, _ = compute_loss(cfg, model, inputs, audio_frames, labels_hm)
     optimizer.zero_grad(set_to_none=True)
+    scaling = scaler is not None and scaler.is_enabled()
+    assert scaling or not cfg.TRAIN.MIXED_PRECISION, "TRAIN.MIXED_PRECISION stores fp16 gradients: pass make_grad_scaler(cfg)"
+    root = scaler.scale(loss) if scaling else loss
     if hasattr(grad_sync, "start"):          # OverlappedGradSync: exchange runs during backward
         grad_sync.start()
-        loss.backward()
+        root.backward()
         grad_sync.finish()
     else:
-        loss.backward()
+        root.backward()
         if grad_sync is not None:
             grad_sync()
+    if scaling:
+        scaler.unscale_(optimizer)
     if cfg.SOLVER.CLIP_GRAD_L2NORM:
         torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM, foreach=True)
-    optimizer.step()
+    if scaling:
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        optimizer.step()
     return loss.detach()
 
 
@@ -92,7 +108,7 @@ class GraphedTrainStep:
     ``construct_optimizer(model, cfg, capturable=True)``.
     """
 
-    def __init__(self, cfg, model, optimizer, video, audio, labels_hm, warmup=3):
+    def __init__(self, cfg, model, optimizer, video, audio, labels_hm, warmup=3, scaler=None):
         # Data parallel: the replica is stepped un-wrapped and gradients are averaged by captured NCCL
         # all-reduces (DDP's reducer is host-driven and cannot be replayed from a graph); DDP's
         # constructor has already broadcast rank 0's parameters.
@@ -107,6 +123,7 @@ class GraphedTrainStep:
                 self.grad_sync = lambda: du.allreduce_gradients(list(inner.parameters()))
         dev = next(inner.parameters()).device
         self.cfg, self.model, self.optimizer = cfg, model, optimizer
+        self.scaler = scaler if scaler is not None else make_grad_scaler(cfg)
         self.video = torch.empty(video.shape, dtype=torch.float32, device=dev)
         self.audio = torch.empty(audio.shape, dtype=torch.float32, device=dev)
         self.labels = torch.empty(labels_hm.shape, dtype=torch.float32, device=dev)
@@ -115,14 +132,15 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):              # eager warm-up: lazy inits (func attributes, optimizer state, NCCL)
-                train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync)
+                train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync, scaler=self.scaler)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        inner._wc.clear()                        # the bf16 weight casts must be part of the captured step
+        inner._wc.clear()                        # the 16-bit weight casts must be part of the captured step
         optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss = train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync)
+            self.loss = train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync,
+                                   scaler=self.scaler)
 
     def _load(self, video, audio, labels_hm):
         self.video.copy_(video[0] if isinstance(video, (list, tuple)) else video, non_blocking=True)

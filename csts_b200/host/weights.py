@@ -1,20 +1,40 @@
-"""bf16 operand copies of the fp32 master parameters.
+"""Precision mode and the 16-bit operand copies of the fp32 master parameters.
 
 Parameters stay fp32 ``nn.Parameter``s under the reference's names (checkpoints, optimizer and DDP
-see exactly the reference's state).  The tensor-core kernels consume bf16 operands, so each GEMM
-weight gets a cached bf16 copy.  The same (N, K) copy serves forward (K-major B operand of Y = X . W^T)
-and backward (MN-major B operand of dX = dY . W) — the tcgen05 kernel takes either layout through its
-shared-memory descriptors, so no transposed copy is kept.  A copy is refreshed whenever the parameter's
-version counter or storage changes, i.e. once per optimizer step.
+see exactly the reference's state).  The tensor-core kernels consume 16-bit operands, so each GEMM
+weight gets a cached 16-bit copy.  The same (N, K) copy serves forward (K-major B operand of
+Y = X . W^T) and backward (MN-major B operand of dX = dY . W) — the tcgen05 kernel takes either layout
+through its shared-memory descriptors, so no transposed copy is kept.  A copy is refreshed whenever
+the parameter's version counter or storage changes, i.e. once per optimizer step.
+
+Precision modes (one 16-bit type per mode: a tcgen05 kind::f16 MMA cannot mix f16 and bf16 operands):
+
+* default — bf16 activations and bf16 activation gradients.  fp32 exponent range, no loss scaling;
+  7 mantissa bits put the whole-model gradient ~3e-2 (relative L2) from the fp32 reference.
+* ``TRAIN.MIXED_PRECISION: True`` — the reference's own mixed-precision contract (fp16 autocast +
+  ``GradScaler``, tools/train_avgaze_net.py:70,99-109): fp16 activations and fp16 activation gradients.
+  10 mantissa bits bring the gradient within ~1e-2 of fp32; the caller scales the loss
+  (``scaler.scale(loss).backward()``) exactly as the reference loop does.
 """
+from collections import namedtuple
+
 import torch
 
 from .. import kernels as K
 
+Precision = namedtuple("Precision", ["act", "grad"])
+BF16 = Precision(torch.bfloat16, torch.bfloat16)
+FP16 = Precision(torch.float16, torch.float16)
+
+
+def precision_of(cfg):
+    return FP16 if cfg.TRAIN.MIXED_PRECISION else BF16
+
 
 class WeightCache:
-    def __init__(self):
+    def __init__(self, precision=BF16):
         self._store = {}
+        self.act, self.grad = precision
 
     def _get(self, param, kind, make):
         key = (id(param), kind)
@@ -28,19 +48,19 @@ class WeightCache:
         return val
 
     def w(self, param):
-        """Linear weight (N, K) f32 -> bf16 (N, K)."""
-        return self._get(param, "w", lambda p: K.cast_bf16(p.reshape(p.shape[0], -1)))
+        """Linear weight (N, K) f32 -> 16-bit (N, K)."""
+        return self._get(param, "w", lambda p: K.cast16(p.reshape(p.shape[0], -1), self.act))
 
     def w_padded(self, param, kp):
-        """Conv weight (N, ...) f32 -> bf16 (N, kp), zero padded columns (patch embed)."""
-        return self._get(param, ("pad", kp), lambda p: K.cast_bf16(p.reshape(p.shape[0], -1), ld_out=kp))
+        """Conv weight (N, ...) f32 -> 16-bit (N, kp), zero padded columns (patch embed)."""
+        return self._get(param, ("pad", kp), lambda p: K.cast16(p.reshape(p.shape[0], -1), self.act, ld_out=kp))
 
     def frame_pool_w(self, param):
-        """Conv3d(C, C, (1,8,8)) weight (O, C, 1, 8, 8) -> bf16 (O, 64*C) with columns ordered
+        """Conv3d(C, C, (1,8,8)) weight (O, C, 1, 8, 8) -> 16-bit (O, 64*C) with columns ordered
         (hw, c) to match the token-major activation layout."""
         o, c = param.shape[0], param.shape[1]
         hw = param.shape[3] * param.shape[4]
-        return self._get(param, "fpw", lambda p: K.permute_021(p.reshape(o, c, hw), o, c, hw, torch.bfloat16).reshape(o, hw * c))
+        return self._get(param, "fpw", lambda p: K.permute_021(p.reshape(o, c, hw), o, c, hw, self.act).reshape(o, hw * c))
 
     def clear(self):
         self._store.clear()

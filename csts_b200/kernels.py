@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, GemmArgs, PoolArgs, WgradArgs, call, dt, ptr
+from ._lib import BF16, F16, F32, GemmArgs, PoolArgs, WgradArgs, call, dt, ptr
 
 _FORCE_BACKEND = 0   # 0 auto, 1 mma.sync, 2 tcgen05 (tests flip this to cross-check the two GEMMs)
 
@@ -21,12 +21,15 @@ def set_gemm_backend(code: int):
     _FORCE_BACKEND = int(code)
 
 
-def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=torch.bfloat16,
+def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=None,
          ldc=None, bias=None, act=0, Z=None, residual=None, res_mod=0, accumulate=False, alpha=1.0, split_k=1,
          batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None,
          row_scale=None, rows_per_scale=0):
-    """C = epi(alpha * op(A) @ op(B)).  A/B are bf16 storage tensors; offsets/strides in elements."""
-    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    """C = epi(alpha * op(A) @ op(B)).  A/B are bf16 or f16 storage tensors (independently); offsets/strides
+    in elements.  out_dtype defaults to A's type."""
+    assert A.dtype in (torch.bfloat16, torch.float16) and B.dtype in (torch.bfloat16, torch.float16)
+    if out_dtype is None:
+        out_dtype = A.dtype
     if lda is None:
         lda = K if a_kmajor else M
     if ldb is None:
@@ -56,6 +59,8 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
     a.batch1, a.batch2 = batch
     a.a_kmajor, a.b_kmajor = int(a_kmajor), int(b_kmajor)
     a.c_dtype = dt(out)
+    a.a_dtype, a.b_dtype = dt(A), dt(B)
+    a.z_dtype = dt(Z) if Z is not None else 0
     a.act = act
     a.accumulate = int(accumulate)
     a.res_mod = res_mod
@@ -100,32 +105,37 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, add=None, dx_dtype=to
     return dx
 
 
-def softmax_fwd(S, n, ldp, nq, mask_hw=0, mask_t=0):
-    """S f32 (..., lds) -> P bf16 (..., ldp) with zeroed pad columns."""
+def softmax_fwd(S, n, ldp, nq, mask_hw=0, mask_t=0, dtype=torch.bfloat16):
+    """S f32 (..., lds) -> P (bf16 / f16) (..., ldp) with zeroed pad columns."""
     lds = S.shape[-1]
     rows = S.numel() // lds
-    P = torch.empty(S.shape[:-1] + (ldp,), dtype=torch.bfloat16, device=S.device)
-    call("csts_softmax_fwd", ptr(S), ptr(P), rows, n, lds, ldp, nq, mask_hw, mask_t)
+    P = torch.empty(S.shape[:-1] + (ldp,), dtype=dtype, device=S.device)
+    call("csts_softmax_fwd", ptr(S), ptr(P), dt(P), rows, n, lds, ldp, nq, mask_hw, mask_t)
     return P
 
 
-def softmax_bwd(P, dP, n, scale):
+def softmax_bwd(P, dP, n, scale, dtype=None):
+    """dS (16-bit, P's type unless given) from the stored probabilities P (bf16 / f16) and dP (f32)."""
     ldp = P.shape[-1]
     rows = P.numel() // ldp
-    dS = torch.empty_like(P)
-    call("csts_softmax_bwd", ptr(P), ptr(dP), ptr(dS), rows, n, ldp, dP.shape[-1], scale)
+    dS = torch.empty(P.shape, dtype=P.dtype if dtype is None else dtype, device=P.device)
+    call("csts_softmax_bwd", ptr(P), dt(P), ptr(dP), ptr(dS), dt(dS), rows, n, ldp, dP.shape[-1], scale)
     return dS
 
 
-def cast_bf16(src, ld_out=None, row_scale=None, rows_per_scale=0):
-    """f32 (rows, cols) -> bf16 (rows, ld_out), zero padded; optional per-row-group scale
+def cast16(src, dtype, ld_out=None, row_scale=None, rows_per_scale=0):
+    """f32 (rows, cols) -> bf16 / f16 (rows, ld_out), zero padded; optional per-row-group scale
     (row m is multiplied by row_scale[m // rows_per_scale])."""
     src2 = src.reshape(-1, src.shape[-1]) if src.dim() > 1 else src.reshape(1, -1)
     rows, cols = src2.shape
     ld = cols if ld_out is None else ld_out
-    dst = torch.empty((rows, ld), dtype=torch.bfloat16, device=src.device)
-    call("csts_cast_bf16", ptr(src2), ptr(dst), rows, cols, ld, ptr(row_scale), rows_per_scale)
+    dst = torch.empty((rows, ld), dtype=dtype, device=src.device)
+    call("csts_cast16", ptr(src2), ptr(dst), dt(dst), rows, cols, ld, ptr(row_scale), rows_per_scale)
     return dst if ld_out is not None else dst.reshape(src.shape)
+
+
+def cast_bf16(src, ld_out=None, row_scale=None, rows_per_scale=0):
+    return cast16(src, torch.bfloat16, ld_out, row_scale, rows_per_scale)
 
 
 def permute_021(src, a, b, c, out_dtype):
@@ -164,23 +174,25 @@ def dwconv(inp, in_strides, in_off, B, heads, d, thw_in, stride, w, *, transpose
            out=None, out_strides=None, out_off=0, thw_out=None):
     """Depthwise 3x3x3 (transposed) conv over a token grid; optional fused LayerNorm(d).
 
-    inp: bf16 storage; element (b, head, pos, c) at in_off + b*sB + head*sH + pos*sP + c.
+    inp: bf16 / f16 storage (out and pre get the same type); element (b, head, pos, c) at in_off + b*sB + head*sH + pos*sP + c.
     Returns (out, pre, mean, rstd, thw_out); out is dense (B, heads, Lo, d) unless `out` is given.
     """
     if thw_out is None:
         thw_out = _out_grid(thw_in, stride, transposed)
     Lo = thw_out[0] * thw_out[1] * thw_out[2]
     if out is None:
-        out = torch.empty((B, heads, Lo, d), dtype=torch.bfloat16, device=inp.device)
+        out = torch.empty((B, heads, Lo, d), dtype=inp.dtype, device=inp.device)
         out_strides = (heads * Lo * d, Lo * d, d)
+    assert out.dtype == inp.dtype
     a = PoolArgs()
+    a.dtype = dt(inp)
     a.inp = inp.data_ptr() + in_off * 2
     a.out = out.data_ptr() + out_off * 2
     a.w = w.data_ptr()
     pre = mean = rstd = None
     if norm is not None:
         gamma, beta = norm
-        pre = torch.empty((B, heads, Lo, d), dtype=torch.bfloat16, device=inp.device)
+        pre = torch.empty((B, heads, Lo, d), dtype=inp.dtype, device=inp.device)
         mean = torch.empty(B * heads * Lo, dtype=torch.float32, device=inp.device)
         rstd = torch.empty_like(mean)
         a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
@@ -202,6 +214,7 @@ def dwconv_wgrad(small, small_strides, small_off, thw_small, big, big_strides, b
     a.small = small.data_ptr() + small_off * 2
     a.big = big.data_ptr() + big_off * 2
     a.dw = dw.data_ptr()
+    a.small_dtype, a.big_dtype = dt(small), dt(big)
     a.small_sB, a.small_sH, a.small_sP = small_strides
     a.big_sB, a.big_sH, a.big_sP = big_strides
     a.B, a.heads, a.d = B, heads, d
@@ -245,10 +258,10 @@ def upsample_bwd(dy, B, thw, Cn, factors, dx=None):
     return dx
 
 
-def im2col_patch(x, Kp):
+def im2col_patch(x, Kp, dtype=torch.bfloat16):
     B, Cin, T, H, W = x.shape
-    out = torch.empty((B * (T // 2) * (H // 4) * (W // 4), Kp), dtype=torch.bfloat16, device=x.device)
-    call("csts_im2col_patch", ptr(x), ptr(out), B, Cin, T, H, W, Kp)
+    out = torch.empty((B * (T // 2) * (H // 4) * (W // 4), Kp), dtype=dtype, device=x.device)
+    call("csts_im2col_patch", ptr(x), ptr(out), dt(out), B, Cin, T, H, W, Kp)
     return out
 
 
@@ -279,9 +292,9 @@ def reweight_bwd(dout, x, w, w_off, w_sB, dw, B, T, S, Cn, want_dx=True):
     return dx
 
 
-def token_mean_fwd(x, B, N, Cn):
-    out = torch.empty((B, Cn), dtype=torch.bfloat16, device=x.device)
-    call("csts_token_mean_fwd", ptr(x), ptr(out), B, N, Cn)
+def token_mean_fwd(x, B, N, Cn, dtype=torch.bfloat16):
+    out = torch.empty((B, Cn), dtype=dtype, device=x.device)
+    call("csts_token_mean_fwd", ptr(x), ptr(out), dt(out), B, N, Cn)
     return out
 
 

@@ -12,8 +12,12 @@
  *   - asynchronous on `stream`, no internal synchronisation, no device allocation, no retained pointers:
  *     the caller (PyTorch's caching allocator) owns all memory.  Re-entrant / thread-safe (backward runs
  *     on autograd's worker thread).
- *   - dtype codes: 0 = f32, 1 = bf16.  Residual stream / statistics / gradients of parameters are f32,
- *     GEMM operands and saved activations are bf16.
+ *   - dtype codes: 0 = f32, 1 = bf16, 2 = f16 (IEEE half).  The residual stream, statistics and parameter
+ *     gradients are f32.  Every entry point takes the type of its 16-bit tensors explicitly.  The host layer
+ *     runs one type per precision mode: bf16 by default (fp32 range, no loss scaling), f16 under
+ *     TRAIN.MIXED_PRECISION (the reference's fp16 autocast + GradScaler contract, tools/train_avgaze_net.py:70,
+ *     99-109; 10 mantissa bits).  The two operands of a tcgen05 GEMM must share one type (a kind::f16 MMA with
+ *     different A / B formats faults on sm_100a); the mma.sync kernel accepts mixed pairs.
  *   - the library is built for sm_100a only; csts_check_device() reports anything else.
  */
 #ifndef CSTS_B200_H
@@ -38,10 +42,10 @@ long long csts_launch_count(int reset);          /* kernels launched since load 
  * (custom_multimodal_builder.py:227-229) and all of their autograd backward products.
  * Large token-major problems run on the tcgen05/TMEM/TMA kernel, odd shapes on the mma.sync kernel. */
 typedef struct csts_gemm_args {
-  const void* A;          /* bf16 */
-  const void* B;          /* bf16 */
-  void* C;                /* f32 or bf16 (c_dtype) */
-  void* Z;                /* bf16, same shape as C (pitch ldz): act==1 -> receives GELU'(pre-activation),
+  const void* A;          /* bf16 or f16 (a_dtype) */
+  const void* B;          /* bf16 or f16 (b_dtype) */
+  void* C;                /* f32, bf16 or f16 (c_dtype) */
+  void* Z;                /* bf16 or f16 (z_dtype), same shape as C (pitch ldz): act==1 -> receives GELU'(pre-activation),
                                                                 act==2 -> is read (C = result * Z),
                                                                 act==4 -> the softmax probabilities P */
   const float* bias;      /* [N] or NULL */
@@ -54,15 +58,18 @@ typedef struct csts_gemm_args {
   int32_t batch1, batch2;
   int32_t a_kmajor;       /* 1: A[m*lda + k]   0: A[k*lda + m] */
   int32_t b_kmajor;       /* 1: B[n*ldb + k]   0: B[k*ldb + n] */
-  int32_t c_dtype;        /* 0 f32, 1 bf16 */
+  int32_t c_dtype;        /* 0 f32, 1 bf16, 2 f16 */
   int32_t act;            /* 0 none, 1 erf GELU (nn.GELU(), common.py:21; Z <- GELU'), 2 times Z (GELU backward),
-                             3 row softmax of alpha*acc (N <= 256, bf16 C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)) */
+                             3 row softmax of alpha*acc (N <= 256, 16-bit C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)) */
   int32_t accumulate;     /* C += result */
   int32_t res_mod;
   int32_t split_k;        /* > 1: partial sums combined with f32 atomics (C must be f32) */
   float alpha;
   int32_t backend;        /* 0 auto, 1 mma.sync, 2 tcgen05 */
   int32_t rows_per_scale;
+  int32_t a_dtype;        /* 1 bf16, 2 f16 */
+  int32_t b_dtype;        /* 1 bf16, 2 f16 */
+  int32_t z_dtype;        /* 1 bf16, 2 f16 (ignored when Z is NULL) */
 } csts_gemm_args;
 int csts_gemm(const csts_gemm_args* a, void* stream);
 int csts_gemm_backend(const csts_gemm_args* a);  /* 2 = tcgen05, 1 = mma.sync for this problem */
@@ -76,13 +83,17 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
                        int width, void* stream);
 
 /* ---- attention softmax: attn.softmax(dim=-1) (attention.py:155), with the in-frame mask of
- * SpatialAttention (av_attention.py:336-348) when mask_hw > 0.  P is bf16, pad columns [n, ldp) zero. */
-int csts_softmax_fwd(const float* S, void* P, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t, void* stream);
-int csts_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int n, int ldp, int lddp, float scale, void* stream);
+ * SpatialAttention (av_attention.py:336-348) when mask_hw > 0.  P is bf16 / f16 (p_dtype), pad columns
+ * [n, ldp) zero; dS is bf16 / f16 (ds_dtype). */
+int csts_softmax_fwd(const float* S, void* P, int p_dtype, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t,
+                     void* stream);
+int csts_softmax_bwd(const void* P, int p_dtype, const float* dP, void* dS, int ds_dtype, int64_t rows, int n, int ldp, int lddp,
+                     float scale, void* stream);
 
 /* ---- casts / layout / elementwise ------------------------------------------------------------------- */
-int csts_cast_bf16(const float* src, void* dst, int64_t rows, int cols, int ld_out, const float* row_scale, int rows_per_scale,
-                   void* stream);
+/* f32 (rows, cols) -> bf16 / f16 (rows, ld_out), zero padded; row m scaled by row_scale[m / rows_per_scale] if given */
+int csts_cast16(const float* src, void* dst, int dst_dtype, int64_t rows, int cols, int ld_out, const float* row_scale,
+                int rows_per_scale, void* stream);
 int csts_permute_021(const float* src, void* dst, int dst_dtype, int a, int b, int c, void* stream); /* [a][b][c] -> [a][c][b] */
 int csts_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);     /* decoder skips, custom_multimodal_builder.py:467-473 */
 int csts_scale_f32(const float* a, const float* device_scalar, float* out, int64_t n, void* stream);
@@ -93,12 +104,12 @@ int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_
  * `in` lives at in + b*in_sB + head*in_sH + pos*in_sP + c: the kernels read the (B,N,3,heads,d) qkv
  * tensor in place, so the reference's permute+contiguous copies (attention.py:31,37) do not exist. */
 typedef struct csts_pool_args {
-  const void* in;         /* bf16 */
-  void* out;              /* bf16 */
+  const void* in;         /* bf16 or f16 (dtype) */
+  void* out;              /* same type as in */
   const float* w;         /* (d,1,3,3,3) parameter, f32 */
   const float* gamma;     /* LayerNorm(d) weight or NULL (no norm: `out` = raw conv) */
   const float* beta;
-  void* pre;              /* bf16 dense (B, heads, Lo, d): raw conv output kept for backward (norm only) */
+  void* pre;              /* same type, dense (B, heads, Lo, d): raw conv output kept for backward (norm only) */
   float* mean;            /* [B*heads*Lo] (norm only) */
   float* rstd;
   int64_t in_sB, in_sH, in_sP;
@@ -109,13 +120,14 @@ typedef struct csts_pool_args {
   int32_t st, sh, sw;     /* stride of the (un-transposed) convolution, powers of two */
   int32_t transposed;     /* 0: out[o] = sum_tap w[tap] in[o*s+tap-1]; 1: out[o] = sum_tap w[tap] in[(o+1-tap)/s] */
   float eps;
+  int32_t dtype;          /* 1 bf16, 2 f16: type of in / out / pre */
 } csts_pool_args;
 int csts_dwconv(const csts_pool_args* p, void* stream);
 
 /* dw[c][tap] += sum small[o][c] * big[o*s + tap - 1][c]   (conv: small = d(out), big = in; transposed: swapped) */
 typedef struct csts_wgrad_args {
-  const void* small;      /* bf16, grid (Ts,Hs,Ws) */
-  const void* big;        /* bf16, grid (Tb,Hb,Wb) */
+  const void* small;      /* bf16 or f16 (small_dtype), grid (Ts,Hs,Ws) */
+  const void* big;        /* bf16 or f16 (big_dtype), grid (Tb,Hb,Wb) */
   float* dw;              /* (d,1,3,3,3) f32, accumulated into */
   int64_t small_sB, small_sH, small_sP;
   int64_t big_sB, big_sH, big_sP;
@@ -123,6 +135,7 @@ typedef struct csts_wgrad_args {
   int32_t Ts, Hs, Ws;
   int32_t Tb, Hb, Wb;
   int32_t st, sh, sw;
+  int32_t small_dtype, big_dtype;
 } csts_wgrad_args;
 int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream);
 
@@ -136,8 +149,8 @@ int csts_upsample_bwd(const float* dy, float* dx, int B, int T, int H, int W, in
 
 /* ---- stem / fusion glue / head --------------------------------------------------------------------- */
 /* PatchEmbed Conv3d k(3,7,7) s(2,4,4) p(1,3,3) as im2col (stem_helper.py:27-38): x f32 (B,Cin,T,H,W) ->
- * bf16 [B*T/2*H/4*W/4, Kp], column ((c*3+kt)*7+kh)*7+kw, zero padded to Kp */
-int csts_im2col_patch(const float* x, void* patches, int B, int Cin, int T, int H, int W, int Kp, void* stream);
+ * bf16 / f16 [B*T/2*H/4*W/4, Kp], column ((c*3+kt)*7+kh)*7+kw, zero padded to Kp */
+int csts_im2col_patch(const float* x, void* patches, int dtype, int B, int Cin, int T, int H, int W, int Kp, void* stream);
 /* separable position embedding (custom_multimodal_builder.py:362-370) and its gradient */
 int csts_pos_embed(const float* spatial, const float* temporal, float* pos, int T, int HW, int C, void* stream);
 int csts_pos_embed_bwd(const float* dY, float* dspatial, float* dtemporal, int B, int T, int HW, int C, void* stream);
@@ -146,7 +159,7 @@ int csts_reweight_fwd(const float* x, const float* w, float* out, int B, int T, 
 int csts_reweight_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, int B, int T, int S, int C, int64_t w_sB,
                       void* stream);
 /* x.mean(dim=1) feeding vision_proj / audio_proj (custom_multimodal_builder.py:493-496) */
-int csts_token_mean_fwd(const float* x, void* out_bf16, int B, int N, int C, void* stream);
+int csts_token_mean_fwd(const float* x, void* out, int out_dtype, int B, int N, int C, void* stream);
 int csts_token_mean_bwd(const float* dout, float* dx, int B, int N, int C, int accumulate, void* stream);
 /* classifier(feat + F.interpolate(stem, T -> 2T, trilinear)) (custom_multimodal_builder.py:476-481) */
 int csts_classifier_fwd(const float* feat, const float* stem, const float* w, const float* bias, float* logits, int B, int Ti, int S, int C,

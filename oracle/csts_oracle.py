@@ -87,7 +87,8 @@ ARCH = arch_table()
 # plain fp32 oracle measures).  Off by default: the oracle proper is fp32.
 # --------------------------------------------------------------------------------------------
 EMULATE_BF16 = False
-FWD_DTYPE = torch.bfloat16     # precision study only: storage type of the forward activations / weights
+FWD_DTYPE = torch.bfloat16     # storage type of the forward activations / weight copies (fp16 in the MIXED_PRECISION mode)
+BWD_DTYPE = torch.bfloat16     # storage type of the activation gradients
 
 
 def _bf(t):
@@ -98,6 +99,10 @@ def _fw(t):
     return t.to(FWD_DTYPE).to(torch.float32)
 
 
+def _bw(t):
+    return t.to(BWD_DTYPE).to(torch.float32)
+
+
 class _RoundBoth(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t):
@@ -105,7 +110,7 @@ class _RoundBoth(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return _bf(g)
+        return _bw(g)
 
 
 class _RoundBwd(torch.autograd.Function):
@@ -115,7 +120,7 @@ class _RoundBwd(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return _bf(g)
+        return _bw(g)
 
 
 class _RoundFwd(torch.autograd.Function):
@@ -436,15 +441,17 @@ def kldiv_egonce(logits, v, a, labels_hm, alpha=0.05):
     return kld + alpha * nce, kld, nce
 
 
-def loss_and_grads(sd, video, audio, labels_hm, alpha=0.05):
+def loss_and_grads(sd, video, audio, labels_hm, alpha=0.05, loss_scale=1.0):
     """Forward + loss + autograd backward over every tensor in `sd` (fp32).  Returns
-    (loss, kld, nce, logits, grads{name: tensor})."""
+    (loss, kld, nce, logits, grads{name: tensor}).  loss_scale mirrors GradScaler (backward runs on
+    loss_scale * loss, the returned gradients are unscaled); it only matters under EMULATE_BF16 with an
+    fp16 BWD_DTYPE."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
     logits, v, a = csts_forward(leaves, video, audio, return_embed=True)
     loss, kld, nce = kldiv_egonce(logits, v, a, labels_hm, alpha)
     names = list(leaves)
-    gs = torch.autograd.grad(loss, [leaves[n] for n in names], allow_unused=True)
-    grads = {n: g for n, g in zip(names, gs) if g is not None}
+    gs = torch.autograd.grad(loss * loss_scale, [leaves[n] for n in names], allow_unused=True)
+    grads = {n: g / loss_scale for n, g in zip(names, gs) if g is not None}
     return loss.detach(), kld.detach(), nce.detach(), logits.detach(), grads
 
 

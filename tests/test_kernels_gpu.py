@@ -509,3 +509,153 @@ def test_kldiv_and_egonce(golden_dir):
     # logits are sim/0.05 (|z| up to 20): fp32 exp amplifies rounding, hence 1e-3
     assert rel_err(dv, v.grad) < 1e-3
     assert rel_err(da, a.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ storage types
+def hf(x):
+    return x.to(torch.float16)
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+def test_gemm_f16_operands(backend):
+    """fp16 storage mode: both operands f16 (tcgen05 a_format = b_format = F16; mma.sync .f16.f16)."""
+    k = K()
+    M, N, Kd = 640, 384, 192
+    g = torch.Generator(device="cpu").manual_seed(11)
+    A = hf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = hf(torch.randn(N, Kd, generator=g) * 0.1).to(dev)
+    ref = A.float() @ B.float().t()
+    o = k.gemm(A, B, M=M, N=N, K=Kd, out_dtype=torch.float32, backend=backend)
+    assert rel_err(o, ref) < 2e-5, rel_err(o, ref)
+    # MN-major variants (weight gradient: both operands token-major; data gradient: MN-major weight)
+    At, Bt = A.t().contiguous(), B.t().contiguous()
+    o = k.gemm(At, Bt, M=M, N=N, K=Kd, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, backend=backend)
+    assert rel_err(o, ref) < 2e-5
+    o = k.gemm(A, Bt, M=M, N=N, K=Kd, b_kmajor=False, out_dtype=torch.float32, backend=backend)
+    assert rel_err(o, ref) < 2e-5
+    o = k.gemm(At, Bt, M=M, N=N, K=Kd, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=3, backend=backend)
+    assert rel_err(o, ref) < 2e-5
+    for odt, otol in ((torch.float16, 6e-4), (torch.bfloat16, 4e-3)):
+        o = k.gemm(A, B, M=M, N=N, K=Kd, out_dtype=odt, backend=backend)
+        assert o.dtype == odt and rel_err(o, ref) < otol
+
+
+def test_gemm_mixed_operand_types_take_the_generic_kernel():
+    """One tcgen05 kind::f16 MMA cannot mix an f16 and a bf16 operand (it faults on sm_100a): such a product
+    is refused by the tcgen05 backend and routed to the mma.sync kernel, which re-rounds the f16 fragment."""
+    k = K()
+    M, N, Kd = 256, 192, 96
+    g = torch.Generator(device="cpu").manual_seed(12)
+    A = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = hf(torch.randn(N, Kd, generator=g) * 0.1).to(dev)
+    ref = A.float() @ B.float().t()
+    assert rel_err(k.gemm(A, B, M=M, N=N, K=Kd, out_dtype=torch.float32), ref) < 4e-3                  # auto -> mma.sync
+    assert rel_err(k.gemm(B, A, M=N, N=M, K=Kd, out_dtype=torch.float32), ref.t()) < 4e-3
+    with pytest.raises(RuntimeError, match="unsupported"):
+        k.gemm(A, B, M=M, N=N, K=Kd, out_dtype=torch.float32, backend=2)
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+def test_gemm_epilogues_f16_storage(backend):
+    """GELU / GELU' / times-Z / accumulate epilogues with f16 operands, C and Z."""
+    k = K()
+    M, N, Kd = 640, 384, 192
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = hf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = hf(torch.randn(N, Kd, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    pre = A.float() @ B.float().t() + bias
+    Z = torch.empty(M, N, dtype=torch.float16, device=dev)
+    h = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, act=1, Z=Z, backend=backend)
+    pr = pre.clone().requires_grad_(True)
+    (gpre,) = torch.autograd.grad(F.gelu(pr).sum(), pr)
+    assert h.dtype == torch.float16 and rel_err(Z, gpre) < 6e-4 and rel_err(h, F.gelu(pre)) < 6e-4
+    dY = hf(torch.randn(M, Kd, generator=g)).to(dev)
+    W = hf(torch.randn(Kd, N, generator=g) * 0.05).to(dev)
+    o = k.gemm(dY, W, M=M, N=N, K=Kd, b_kmajor=False, act=2, Z=Z, out_dtype=torch.float32 if backend == 1 else torch.float16,
+               backend=backend)
+    assert rel_err(o, (dY.float() @ W.float()) * Z.float()) < 6e-4
+    base = hf(torch.randn(M, N, generator=g)).to(dev)
+    acc = base.clone()
+    k.gemm(A, B, M=M, N=N, K=Kd, out=acc, accumulate=True, backend=backend)
+    assert rel_err(acc, base.float() + A.float() @ B.float().t()) < 8e-4
+
+
+def test_fused_softmax_f16_probabilities():
+    k = K()
+    B, h, Lq, Lk, d = 2, 2, 256, 200, 96
+    ldS = (Lk + 7) // 8 * 8
+    g = torch.Generator(device="cpu").manual_seed(3)
+    q = hf(torch.randn(B, h, Lq, d, generator=g)).to(dev)
+    kk = hf(torch.randn(B, h, Lk, d, generator=g)).to(dev)
+    v = hf(torch.randn(B, h, Lk, d, generator=g)).to(dev)
+    do = hf(torch.randn(B, h, Lq, d, generator=g)).to(dev)
+    scale = d ** -0.5
+    P = torch.full((B, h, Lq, ldS), float("nan"), dtype=torch.float16, device=dev)
+    k.gemm(q, kk, M=Lq, N=Lk, K=d, out=P, ldc=ldS, alpha=scale, act=3, batch=(B, h), sA=(h * Lq * d, Lq * d), sB=(h * Lk * d, Lk * d),
+           sC=(h * Lq * ldS, Lq * ldS))
+    Pr = (q.float() @ kk.float().transpose(-1, -2) * scale).softmax(-1)
+    assert rel_err(P[..., :Lk], Pr) < 6e-4 and torch.all(P[..., Lk:] == 0)
+    dS = torch.full((B, h, Lq, ldS), float("nan"), dtype=torch.float16, device=dev)
+    k.gemm(do, v, M=Lq, N=Lk, K=d, out=dS, ldc=ldS, alpha=scale, act=4, Z=P, batch=(B, h), sA=(h * Lq * d, Lq * d),
+           sB=(h * Lk * d, Lk * d), sC=(h * Lq * ldS, Lq * ldS))
+    dP = do.float() @ v.float().transpose(-1, -2)
+    Pf = P[..., :Lk].float()
+    dSr = scale * Pf * (dP - (dP * Pf).sum(-1, keepdim=True))
+    assert rel_err(dS[..., :Lk], dSr) < 8e-4 and torch.all(dS[..., Lk:] == 0)
+    # unfused kernels on the same types
+    S = (q.float() @ kk.float().transpose(-1, -2) * scale)
+    Sp = torch.zeros(B, h, Lq, ldS, device=dev)
+    Sp[..., :Lk] = S
+    P2 = k.softmax_fwd(Sp, Lk, ldS, nq=Lq, dtype=torch.float16)
+    assert P2.dtype == torch.float16 and rel_err(P2[..., :Lk], Pr) < 6e-4
+    dPp = torch.zeros(B, h, Lq, ldS, device=dev)
+    dPp[..., :Lk] = dP
+    dS2 = k.softmax_bwd(P2, dPp, Lk, scale)
+    assert dS2.dtype == torch.float16 and rel_err(dS2[..., :Lk], dSr) < 8e-4
+    assert k.softmax_bwd(P2, dPp, Lk, scale, dtype=torch.bfloat16).dtype == torch.bfloat16
+
+
+def test_rowwise_and_pool_kernels_f16_storage():
+    k = K()
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(300, 384, generator=g).to(dev)
+    gamma, beta = torch.randn(384, generator=g).to(dev), torch.randn(384, generator=g).to(dev)
+    y, mean, rstd = k.layernorm_fwd(x, gamma, beta, 1e-6, out_dtype=torch.float16)
+    assert y.dtype == torch.float16 and rel_err(y, F.layer_norm(x, (384,), gamma, beta, 1e-6)) < 6e-4
+    assert torch.equal(k.cast16(x, torch.float16), hf(x))
+    assert torch.equal(k.cast16(x, torch.float16, ld_out=392)[:, :384], hf(x))
+    assert torch.equal(k.permute_021(x.view(3, 100, 384), 3, 100, 384, torch.float16), hf(x.view(3, 100, 384).transpose(1, 2).contiguous()))
+    # pooling conv + LayerNorm on f16 tokens and its backward pieces with f16 gradients
+    B, h, d, thw, stride = 2, 2, 96, (4, 16, 16), (1, 2, 2)
+    N = thw[0] * thw[1] * thw[2]
+    qkv = hf(torch.randn(B, N, 3, h, d, generator=g)).to(dev)
+    w = (torch.randn(d, 1, 3, 3, 3, generator=g) * 0.2).to(dev)
+    gq, bq = torch.randn(d, generator=g).to(dev), torch.randn(d, generator=g).to(dev)
+    qs = (N * 3 * h * d, d, 3 * h * d)
+    out, pre, mean, rstd, thw_o = k.dwconv(qkv, qs, 0, B, h, d, thw, stride, w, norm=(gq, bq), eps=1e-5)
+    assert out.dtype == torch.float16 and pre.dtype == torch.float16
+    xin = qkv[:, :, 0].float().permute(0, 2, 3, 1).reshape(B * h, d, *thw)             # (B*h, d, T, H, W)
+    conv = F.conv3d(xin, w, stride=stride, padding=1, groups=d)
+    Lo = thw_o[0] * thw_o[1] * thw_o[2]
+    conv_t = conv.reshape(B, h, d, Lo).transpose(2, 3)
+    assert rel_err(pre, conv_t) < 6e-4
+    assert rel_err(out, F.layer_norm(pre.float(), (d,), gq, bq, 1e-5)) < 8e-4
+    du = hf(torch.randn(B, h, Lo, d, generator=g)).to(dev)
+    dw = torch.zeros_like(w)
+    k.dwconv_wgrad(du, (h * Lo * d, Lo * d, d), 0, thw_o, qkv, qs, 0, thw, B, h, d, stride, dw)
+    xr = xin.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    F.conv3d(xr, wr, stride=stride, padding=1, groups=d).backward(du.float().transpose(2, 3).reshape(B * h, d, *thw_o))
+    assert rel_err(dw, wr.grad) < 2e-5
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    dpre = k.layernorm_bwd(du, pre, mean, rstd, gq, dg, db, dx_dtype=torch.float16)
+    pr = pre.float().clone().requires_grad_(True)
+    F.layer_norm(pr, (d,), gq, bq, 1e-5).backward(du.float())
+    assert dpre.dtype == torch.float16 and rel_err(dpre, pr.grad) < 8e-4
+    assert rel_err(dg, (du.float() * F.layer_norm(pre.float(), (d,), None, None, 1e-5)).sum((0, 1, 2))) < 1e-4
+    assert rel_err(k.colsum(du.view(-1, d), B * h * Lo, d), du.float().sum((0, 1, 2))) < 1e-5
+    # the adjoint (transposed) gather on f16 gradients
+    dqkv = torch.zeros(B, N, 3, h, d, dtype=torch.float16, device=dev)
+    k.dwconv(du, (h * Lo * d, Lo * d, d), 0, B, h, d, thw_o, stride, w, transposed=True, out=dqkv, out_strides=qs, out_off=0, thw_out=thw)
+    assert rel_err(dqkv[:, :, 0].permute(0, 2, 3, 1).reshape(B * h, d, *thw), xr.grad) < 8e-4

@@ -1,6 +1,9 @@
 """Block- and model-level parity (GPU) of csts_b200 against the oracle and the reference-generated
-golden fixtures.  Tolerances are BASELINE.json's: heat-map logits <= 1e-2 max-abs / 1e-3 mean-abs,
-loss <= 1e-3 relative, gradients <= 2e-2 relative (per tensor, L2) for the bf16 path."""
+golden fixtures.  Tolerances are BASELINE.json's: heat-maps <= 1e-2 max-abs / 1e-3 mean-abs,
+loss <= 1e-3 relative, gradients <= 2e-2 relative (L2).  Both precision modes are covered: the default
+bf16 storage and the fp16 storage selected by TRAIN.MIXED_PRECISION (the reference's fp16 autocast +
+GradScaler contract); the fp16 mode meets the gradient tolerance, the bf16 mode sits at ~3e-2 because of
+its 7-bit mantissa (DESIGN.md "Precision")."""
 import json
 import os
 
@@ -20,26 +23,39 @@ def rel_err(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
-def make_cfg(droppath=0.0):
+LOSS_SCALE = 4096.0      # fp16 mode: what GradScaler does in the training loop (power of two: exact)
+
+
+def make_cfg(droppath=0.0, mixed=False):
     from csts_b200.host.config import get_cfg
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfg = get_cfg()
     cfg.merge_from_file(os.path.join(root, "configs", "Ego4D", "CSTS_Ego4D_Gaze_Forecast.yaml"))
-    cfg.merge_from_list(["NUM_GPUS", 1, "MODEL.LOSS_FUNC", "kldiv+egonce", "MVIT.DROPPATH_RATE", droppath])
+    cfg.merge_from_list(["NUM_GPUS", 1, "MODEL.LOSS_FUNC", "kldiv+egonce", "MVIT.DROPPATH_RATE", droppath,
+                         "TRAIN.MIXED_PRECISION", mixed])
     return cfg
 
 
-@pytest.fixture(scope="module")
-def model_and_state(golden_dir):
+def _model_and_state(golden_dir, mixed):
     import csts_oracle as O
     from csts_b200.host.build import build_model
     shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
     sd = O.synthetic_state(shapes, seed=0, gain=1.0)
-    model = build_model(make_cfg())
+    model = build_model(make_cfg(mixed=mixed))
     model.load_state_dict(sd, strict=True)
     model.train()
     sd_gpu = {k: v.to(dev) for k, v in sd.items()}
     return model, sd_gpu
+
+
+@pytest.fixture(scope="module")
+def model_and_state(golden_dir):
+    return _model_and_state(golden_dir, False)
+
+
+@pytest.fixture(scope="module")
+def model_and_state_fp16(golden_dir):
+    return _model_and_state(golden_dir, True)
 
 
 BLOCK_CASES = [
@@ -54,6 +70,17 @@ BLOCK_CASES = [
 
 @pytest.mark.parametrize("name,B,thw", BLOCK_CASES)
 def test_block_forward_backward(model_and_state, name, B, thw):
+    _check_block(model_and_state, name, B, thw, tol_fwd=1e-2, tol_grad=2e-2)
+
+
+@pytest.mark.parametrize("name,B,thw", [c for c in BLOCK_CASES if c[0] in ("blocks.1", "blocks.2", "blocks.14", "spatial_fusion",
+                                                                             "temporal_fusion", "decode_block2")])
+def test_block_forward_backward_fp16_mode(model_and_state_fp16, name, B, thw):
+    """Same blocks under TRAIN.MIXED_PRECISION (fp16 activations and gradients): 8x finer rounding."""
+    _check_block(model_and_state_fp16, name, B, thw, tol_fwd=2e-3, tol_grad=4e-3)
+
+
+def _check_block(model_and_state, name, B, thw, tol_fwd, tol_grad):
     import csts_oracle as O
     model, sd = model_and_state
     spec = model.specs[name]
@@ -88,9 +115,9 @@ def test_block_forward_backward(model_and_state, name, B, thw):
     worst.sort(reverse=True)
     msg = f"{name}: fwd {e_fwd:.2e} dx {e_dx:.2e} worst param grads {[(f'{e:.2e}', n) for e, n in worst[:4]]}"
     print(msg)
-    assert e_fwd < 1e-2, msg
-    assert e_dx < 2e-2, msg
-    assert worst[0][0] < 2e-2, msg
+    assert e_fwd < tol_fwd, msg
+    assert e_dx < tol_grad, msg
+    assert worst[0][0] < tol_grad, msg
 
 
 def _train_step(model, video, audio, hm, alpha):
@@ -104,23 +131,29 @@ def _train_step(model, video, audio, hm, alpha):
     return loss, kld, nce, logits, v, a
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
 @pytest.mark.parametrize("fixture,gain", [("full_b2.pt", 1.0), ("full_b2_gain4.pt", 4.0)])
-def test_full_model_against_reference_golden(golden_dir, fixture, gain):
+def test_full_model_against_reference_golden(golden_dir, fixture, gain, mode):
     import csts_oracle as O
     from csts_b200.host.build import build_model
     rec = torch.load(os.path.join(golden_dir, fixture), weights_only=False)
     shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
     sd = O.synthetic_state(shapes, seed=rec["seed"], gain=rec["gain"])
-    model = build_model(make_cfg())
+    model = build_model(make_cfg(mixed=mode == "fp16"))
     model.load_state_dict(sd, strict=True)
     model.train()
     video, audio, hm = O.synthetic_batch(rec["B"], seed=rec["seed"] + 1)
     video, audio, hm = video.to(dev), audio.to(dev), hm.to(dev)
     loss, kld, nce, logits, v, a = _train_step(model, video, audio, hm, rec["alpha"])
-    loss.backward()
+    if mode == "fp16":          # scaler.scale(loss).backward(); scaler.unscale_(optimizer)
+        (loss * LOSS_SCALE).backward()
+        for p in model.parameters():
+            p.grad.div_(LOSS_SCALE)
+    else:
+        loss.backward()
     ref_logits = rec["logits"].to(dev)
     d = (logits - ref_logits).abs()
-    report = {"fixture": fixture, "logits_max_abs": d.max().item(), "logits_mean_abs": d.mean().item(),
+    report = {"fixture": fixture, "mode": mode, "logits_max_abs": d.max().item(), "logits_mean_abs": d.mean().item(),
               "loss": loss.item(), "ref_loss": rec["loss"].item(), "kld": kld.item(), "ref_kld": rec["kld"].item(),
               "nce": nce.item(), "ref_nce": rec["nce"].item(),
               "v_rel": rel_err(v, rec["v"].to(dev)), "a_rel": rel_err(a, rec["a"].to(dev))}
@@ -148,7 +181,7 @@ def test_full_model_against_reference_golden(golden_dir, fixture, gain):
     report["heatmap_mean_abs"] = (hm_got - hm_ref).abs().mean().item()
     report["logits_std"] = ref_logits.std().item()
     os.makedirs(OUT_DIR, exist_ok=True)
-    with open(os.path.join(OUT_DIR, f"parity_{fixture}.json"), "w") as f:
+    with open(os.path.join(OUT_DIR, f"parity_{fixture}.{mode}.json"), "w") as f:
         json.dump(report, f, indent=1)
     print(json.dumps(report, indent=1))
     # BASELINE.json tolerances.  "Output heat-maps" are the frame-softmaxed maps the loss and metrics
@@ -158,38 +191,51 @@ def test_full_model_against_reference_golden(golden_dir, fixture, gain):
     # (the gain-4 fixture scales every Linear weight by 4: attention logits grow 16x and amplify the
     #  rounding of the bf16 q/k operands, hence its looser bound)
     lim_max, lim_mean = (0.1, 0.03) if gain == 1.0 else (0.2, 0.06)
+    if mode == "fp16":
+        lim_max, lim_mean = lim_max / 4, lim_mean / 4
     assert report["logits_max_abs"] <= lim_max * report["logits_std"] and report["logits_mean_abs"] <= lim_mean * report["logits_std"], report
     assert abs(loss.item() - rec["loss"].item()) <= 1e-3 * abs(rec["loss"].item()), report
-    # gradients: 2e-2 relative on the whole gradient (L2 over all 188 M entries); individual tensors are
-    # reported in gpurun_out/parity_*.json and guarded loosely (deep, tiny tensors carry bf16 noise)
-    assert report["grad_global_rel"] <= (5e-2 if gain == 1.0 else 0.12), report
-    assert report["grad_median"] <= (6e-2 if gain == 1.0 else 0.15) and errs[0][0] <= 0.5, report
+    # gradients: relative L2 error of the whole gradient (all 188 M entries).  The fp16 mode meets BASELINE.json's
+    # 2e-2; the bf16 mode is bounded by its 7-bit mantissa (a plain-PyTorch bf16 emulation of the same storage
+    # policy is equally far from fp32, test below) and is held to 5e-2.  Individual tensors are reported in
+    # gpurun_out/parity_*.json and guarded loosely (deep, tiny tensors carry the rounding noise).
+    if mode == "fp16":
+        assert report["grad_global_rel"] <= (2e-2 if gain == 1.0 else 5e-2), report
+        assert report["grad_median"] <= (2e-2 if gain == 1.0 else 6e-2) and errs[0][0] <= 0.25, report
+    else:
+        assert report["grad_global_rel"] <= (5e-2 if gain == 1.0 else 0.12), report
+        assert report["grad_median"] <= (6e-2 if gain == 1.0 else 0.15) and errs[0][0] <= 0.5, report
     for n, g in rec.get("grads", {}).items():
         if g.norm() < 1e-6:
             continue
         assert rel_err(model.get_parameter(n).grad, g.to(dev)) <= 0.5, n
 
 
-def test_full_model_against_bf16_emulating_oracle(golden_dir):
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_full_model_against_storage_emulating_oracle(golden_dir, mode):
     """Implementation error vs rounding-policy error.  The oracle with EMULATE_BF16 rounds exactly the
-    tensors csts_b200 stores in bf16 (and nothing else); what remains between it and the CUDA path is
-    accumulation order, the transcendental implementations and a few double roundings."""
+    tensors csts_b200 stores in 16 bits (and nothing else) to the mode's storage type; what remains between
+    it and the CUDA path is accumulation order, the transcendental implementations and a few double roundings."""
     import csts_oracle as O
     from csts_b200.host.build import build_model
     shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
     sd = O.synthetic_state(shapes, seed=0, gain=1.0)
-    model = build_model(make_cfg())
+    model = build_model(make_cfg(mixed=mode == "fp16"))
     model.load_state_dict(sd, strict=True)
     model.train()
     video, audio, hm = (t.to(dev) for t in O.synthetic_batch(2, seed=1))
     loss, kld, nce, logits, v, a = _train_step(model, video, audio, hm, 0.05)
-    loss.backward()
+    scale = LOSS_SCALE if mode == "fp16" else 1.0
+    (loss * scale).backward()
+    for p in model.parameters():
+        p.grad.div_(scale)
     sd_gpu = {k: t.to(dev) for k, t in sd.items()}
-    O.EMULATE_BF16 = True
+    dt16 = torch.float16 if mode == "fp16" else torch.bfloat16
+    O.EMULATE_BF16, O.FWD_DTYPE, O.BWD_DTYPE = True, dt16, dt16
     try:
-        e_loss, _, _, e_logits, e_grads = O.loss_and_grads(sd_gpu, video, audio, hm, alpha=0.05)
+        e_loss, _, _, e_logits, e_grads = O.loss_and_grads(sd_gpu, video, audio, hm, alpha=0.05, loss_scale=scale)
     finally:
-        O.EMULATE_BF16 = False
+        O.EMULATE_BF16, O.FWD_DTYPE, O.BWD_DTYPE = False, torch.bfloat16, torch.bfloat16
     f_loss, _, _, f_logits, f_grads = O.loss_and_grads(sd_gpu, video, audio, hm, alpha=0.05)
 
     def global_rel(ga, gb):
@@ -210,15 +256,16 @@ def test_full_model_against_bf16_emulating_oracle(golden_dir):
         "grad_worst_vs_emulated": [(round(e, 5), n) for e, n in per[:8]],
     }
     os.makedirs(OUT_DIR, exist_ok=True)
-    with open(os.path.join(OUT_DIR, "parity_bf16_emulation.json"), "w") as f:
+    report["mode"] = mode
+    with open(os.path.join(OUT_DIR, f"parity_storage_emulation.{mode}.json"), "w") as f:
         json.dump(report, f, indent=1)
     print(json.dumps(report, indent=1))
-    # Forward: the CUDA path tracks the bf16-emulating oracle more closely than the fp32 one.
-    assert report["logits_mean_abs_vs_emulated"] <= 1e-3, report
+    # Forward: the CUDA path tracks the storage-emulating oracle more closely than the fp32 one.
+    assert report["logits_mean_abs_vs_emulated"] <= (1e-3 if mode == "bf16" else 2e-4), report
     assert report["logits_mean_abs_vs_emulated"] < report["logits_mean_abs_vs_fp32"], report
-    # Backward: rounding noise de-correlates between two bf16 implementations, so the meaningful
+    # Backward: rounding noise de-correlates between two 16-bit implementations, so the meaningful
     # statement is that the CUDA path is no further from fp32 than a plain-PyTorch implementation of
-    # the same rounding policy is (measured: 3.1e-2 vs 3.5e-2).
+    # the same rounding policy is (measured in bf16 mode: 3.1e-2 vs 3.5e-2).
     assert report["grad_global_rel_vs_fp32"] <= 1.25 * report["emulated_vs_fp32_grad_global_rel"], report
 
 
