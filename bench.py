@@ -153,6 +153,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the one JSON line and nothing else: library banners written to fd 1 (NCCL prints its version
+    # there on communicator creation) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -283,8 +288,8 @@ def run_gpu(args):
         cps, cores, times = cpu_train_step_clips_per_s(2, 2, 1)
         out["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
                                "sample": "2 timed fwd+loss+bwd steps at batch 2 of the same workload (oracle port, fp32)"}
-    print(json.dumps(out))
     sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         os._exit(0)
 
