@@ -3,6 +3,8 @@
 // They read and write the token-major layouts the GEMMs produce ((B, N, 3, heads, d) qkv slices,
 // (B, heads, L, d) pooled tensors, (B, N, C) residual streams) directly through element strides, so
 // the reference's permute+contiguous copies (attention.py:31,37) never happen.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "grid_ops.h"
 
@@ -184,6 +186,144 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
       }
     }
     if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; if (++to == p.To) { to = 0; if (++hd == p.heads) { hd = 0; ++b; } } } }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T-column variant for temporal stride 1 with Ti == To == TT (every pooling conv of the model except the
+// decoder's last, temporally up-sampling one).  A warp owns one (b, head, ho, wo) column and produces its
+// TT outputs together: each valid spatial tap loads and unpacks its TT input planes once and feeds up to
+// three outputs per plane, the three kt weights of the tap are read from shared memory once per column,
+// and the spatial tap geometry is decoded once per column instead of once per output.  The kernel is
+// instruction-issue bound (16-bit -> f32 unpacking + FMAs on L2-resident data), so this is what counts.
+//   regular   : ti = to + kt - 1  ->  to = ti - kt + 1
+//   transposed: ti = to + 1 - kt  ->  to = ti + kt - 1
+// ------------------------------------------------------------------------------------------------
+template <int D, bool TRANSPOSED, bool NORM, typename T, int TT>
+__global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int lh, int lw) {
+  pdl_wait();
+  constexpr int NJ = (D + 127) / 128;
+  __shared__ float s_w[27 * D];
+  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
+    int tap = i / D, c = i - tap * D;
+    s_w[i] = p.w[c * 27 + tap];               // parameter layout (d,1,3,3,3) -> [tap][c]
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int HWo = p.Ho * p.Wo;
+  const int64_t total = (int64_t)p.B * p.heads * HWo;                // columns
+  const T* in = reinterpret_cast<const T*>(p.in);
+  T* out = reinterpret_cast<T*>(p.out);
+  T* pre = reinterpret_cast<T*>(p.pre);
+  const int sW = (int)p.in_sP, sH = p.Wi * sW, sT = p.Hi * sH;      // input strides in elements (32-bit)
+  const int64_t oT = (int64_t)HWo * p.out_sP;                       // output stride between T planes
+
+  const int64_t nwarps = (int64_t)gridDim.x * wpb;
+  const int64_t per_warp = (total + nwarps - 1) / nwarps;
+  int64_t idx = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * per_warp;
+  const int64_t idx_end = idx + per_warp < total ? idx + per_warp : total;
+  int wo = 0, ho = 0, hd = 0, b = 0;
+  if (idx < idx_end) {
+    int o = (int)(idx % HWo);
+    int bh = (int)(idx / HWo);
+    hd = bh % p.heads; b = bh / p.heads;
+    wo = o % p.Wo; ho = o / p.Wo;
+  }
+  for (; idx < idx_end; ++idx) {
+    float acc[TT][NJ][4];
+#pragma unroll
+    for (int t = 0; t < TT; ++t)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[t][j][i] = 0.f;
+    int hi[3], wi[3];
+    bool vh[3], vw[3];
+    tap_coords<TRANSPOSED>(ho, lh, p.Hi, hi, vh);
+    tap_coords<TRANSPOSED>(wo, lw, p.Wi, wi, vw);
+    const T* pl = in + b * p.in_sB + hd * p.in_sH + 4 * lane;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      if (!vh[kh]) continue;                                       // warp-uniform
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        if (!vw[kw]) continue;
+        const T* src = pl + (hi[kh] * sH + wi[kw] * sW);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          if (4 * lane + 128 * j < D) {
+            float v[TT][4], w3[3][4];
+#pragma unroll
+            for (int ti = 0; ti < TT; ++ti) ld4(src + ti * sT + 128 * j, v[ti]);
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) ld4(s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane + 128 * j, w3[kt]);
+#pragma unroll
+            for (int ti = 0; ti < TT; ++ti)
+#pragma unroll
+              for (int kt = 0; kt < 3; ++kt) {
+                const int to = TRANSPOSED ? ti + kt - 1 : ti - kt + 1;
+                if (to < 0 || to >= TT) continue;                  // resolved at compile time
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[to][j][i] = fmaf(v[ti][i], w3[kt][i], acc[to][j][i]);
+              }
+          }
+        }
+      }
+    }
+    const int o_hw = ho * p.Wo + wo;
+    T* dst0 = out + b * p.out_sB + hd * p.out_sH + (int64_t)o_hw * p.out_sP;
+    const int64_t row0 = ((int64_t)(b * p.heads + hd) * TT) * HWo + o_hw;     // dense (B, heads, T*Ho*Wo) index of to = 0
+#pragma unroll
+    for (int to = 0; to < TT; ++to) {
+      T* dst = dst0 + to * oT;
+      if (!NORM) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          int c = 4 * lane + 128 * j;
+          if (c < D) st4(dst + c, acc[to][j]);
+        }
+      } else {
+        // statistics from the storage-rounded conv output (what backward re-reads), as in dwconv_kernel
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          int c = 4 * lane + 128 * j;
+          if (c < D) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { T r16; st_f(&r16, acc[to][j][i]); acc[to][j][i] = ld_f(&r16); sum += acc[to][j][i]; }
+          }
+        }
+        const float mean = warp_sum(sum) * (1.f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          int c = 4 * lane + 128 * j;
+          if (c < D) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float dlt = acc[to][j][i] - mean; q += dlt * dlt; }
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + p.eps);
+        const int64_t row = row0 + (int64_t)to * HWo;
+        if (lane == 0) { p.mean[row] = mean; p.rstd[row] = rstd; }
+        T* pdst = pre + row * D;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          int c = 4 * lane + 128 * j;
+          if (c < D) {
+            float g[4], be[4], y[4];
+            ld4(p.gamma + c, g);
+            ld4(p.beta + c, be);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = (acc[to][j][i] - mean) * rstd * g[i] + be[i];
+            st4(pdst + c, acc[to][j]);
+            st4(dst + c, y);
+          }
+        }
+      }
+    }
+    if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; if (++hd == p.heads) { hd = 0; ++b; } } }
   }
 }
 
@@ -476,6 +616,19 @@ int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   bool norm = p.gamma != nullptr;
   int lt = log2_exact(p.st), lh = log2_exact(p.sh), lw = log2_exact(p.sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv: strides must be powers of two (%d,%d,%d)", p.st, p.sh, p.sw);
+  static const bool no_tcol = getenv("CSTS_NO_TCOL") != nullptr;       // A/B tuning runs only
+  if (p.st == 1 && p.Ti == 4 && p.To == 4 && !no_tcol) {                // T-column kernel: one warp pass per (h, w) column
+    int64_t cols = (int64_t)p.B * p.heads * p.Ho * p.Wo;
+    int cgrid = grid_for(cols, 8);
+    if (p.transposed) {
+      if (norm) launch_pdl(dwconv_tcol_kernel<D, true, true, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      else launch_pdl(dwconv_tcol_kernel<D, true, false, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+    } else {
+      if (norm) launch_pdl(dwconv_tcol_kernel<D, false, true, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      else launch_pdl(dwconv_tcol_kernel<D, false, false, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+    }
+    return csts_check_launch("dwconv_tcol");
+  }
   if (p.transposed) {
     if (norm) launch_pdl(dwconv_kernel<D, true, true, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
     else launch_pdl(dwconv_kernel<D, true, false, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
