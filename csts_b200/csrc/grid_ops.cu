@@ -190,16 +190,17 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// T-column variant for temporal stride 1 with Ti == To == TT (every pooling conv of the model except the
-// decoder's last, temporally up-sampling one).  A warp owns one (b, head, ho, wo) column and produces its
-// TT outputs together: each valid spatial tap loads and unpacks its TT input planes once and feeds up to
-// three outputs per plane, the three kt weights of the tap are read from shared memory once per column,
+// T-column variant for compile-time temporal extents (TI input planes, TO output planes, temporal stride
+// ST): every pooling conv of the model has T = 4 with temporal stride 1, and the decoder's last
+// up-sampling conv goes 4 -> 8 planes with stride 2.  A warp owns one (b, head, ho, wo) column and produces
+// its TO outputs together: each valid spatial tap loads and unpacks its TI input planes once and feeds up
+// to three outputs per plane, the three kt weights of the tap are read from shared memory once per column,
 // and the spatial tap geometry is decoded once per column instead of once per output.  The kernel is
 // instruction-issue bound (16-bit -> f32 unpacking + FMAs on L2-resident data), so this is what counts.
-//   regular   : ti = to + kt - 1  ->  to = ti - kt + 1
-//   transposed: ti = to + 1 - kt  ->  to = ti + kt - 1
+//   regular   : ti = to * ST + kt - 1
+//   transposed: ti = (to + 1 - kt) / ST  <=>  to = ti * ST + kt - 1
 // ------------------------------------------------------------------------------------------------
-template <int D, bool TRANSPOSED, bool NORM, typename T, int TT>
+template <int D, bool TRANSPOSED, bool NORM, typename T, int TI, int TO, int ST>
 __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int lh, int lw) {
   pdl_wait();
   constexpr int NJ = (D + 127) / 128;
@@ -231,9 +232,9 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
     wo = o % p.Wo; ho = o / p.Wo;
   }
   for (; idx < idx_end; ++idx) {
-    float acc[TT][NJ][4];
+    float acc[TO][NJ][4];
 #pragma unroll
-    for (int t = 0; t < TT; ++t)
+    for (int t = 0; t < TO; ++t)
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -253,17 +254,19 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           if (4 * lane + 128 * j < D) {
-            float v[TT][4], w3[3][4];
+            float v[TI][4], w3[3][4];
 #pragma unroll
-            for (int ti = 0; ti < TT; ++ti) ld4(src + ti * sT + 128 * j, v[ti]);
+            for (int ti = 0; ti < TI; ++ti) ld4(src + ti * sT + 128 * j, v[ti]);
 #pragma unroll
             for (int kt = 0; kt < 3; ++kt) ld4(s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane + 128 * j, w3[kt]);
+            // (plane, kt) -> output pairing, resolved at compile time
 #pragma unroll
-            for (int ti = 0; ti < TT; ++ti)
+            for (int a = 0; a < (TRANSPOSED ? TI : TO); ++a)
 #pragma unroll
               for (int kt = 0; kt < 3; ++kt) {
-                const int to = TRANSPOSED ? ti + kt - 1 : ti - kt + 1;
-                if (to < 0 || to >= TT) continue;                  // resolved at compile time
+                const int other = a * ST + kt - 1;                 // transposed: a = ti, other = to;  regular: a = to, other = ti
+                if (other < 0 || other >= (TRANSPOSED ? TO : TI)) continue;
+                const int ti = TRANSPOSED ? a : other, to = TRANSPOSED ? other : a;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[to][j][i] = fmaf(v[ti][i], w3[kt][i], acc[to][j][i]);
               }
@@ -273,9 +276,9 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
     }
     const int o_hw = ho * p.Wo + wo;
     T* dst0 = out + b * p.out_sB + hd * p.out_sH + (int64_t)o_hw * p.out_sP;
-    const int64_t row0 = ((int64_t)(b * p.heads + hd) * TT) * HWo + o_hw;     // dense (B, heads, T*Ho*Wo) index of to = 0
+    const int64_t row0 = ((int64_t)(b * p.heads + hd) * TO) * HWo + o_hw;     // dense (B, heads, T*Ho*Wo) index of to = 0
 #pragma unroll
-    for (int to = 0; to < TT; ++to) {
+    for (int to = 0; to < TO; ++to) {
       T* dst = dst0 + to * oT;
       if (!NORM) {
 #pragma unroll
@@ -414,6 +417,87 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
 #pragma unroll
         for (int i = 0; i < 4; ++i) atomicAdd(p.dw + (c + i) * 27 + (kt * 3 + kh) * 3 + kw, acc[j][kw][i]);
     }
+  }
+}
+
+// T-column weight gradient (d = 96, compile-time temporal extents: TSM planes of `small`, TBG planes of `big`,
+// temporal stride ST).  A warp owns one (b, head, hs, ws) column of `small`: its TSM values are unpacked once,
+// each valid spatial tap unpacks its TBG planes of `big` once, and all 27 taps accumulate in registers
+// (27 x 4 channels per lane) — no operand is re-read by another warp, unlike the tap-row kernel above where
+// nine warps each re-load the same `small` row.  Warps of a block combine through shared memory, then one
+// global atomic per weight per block.
+template <typename TS, typename TB, int TSM, int TBG, int ST>
+__global__ void __launch_bounds__(128) dwconv_wgrad_tcol_kernel(csts_wgrad_args p, int lh, int lw, int cols_per_warp) {
+  pdl_wait();
+  constexpr int D = 96;
+  __shared__ float s_dw[27 * D];
+  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const bool active = 4 * lane < D;
+  const TS* small = reinterpret_cast<const TS*>(p.small);
+  const TB* big = reinterpret_cast<const TB*>(p.big);
+  const int HWs = p.Hs * p.Ws;
+  const int64_t total = (int64_t)p.B * p.heads * HWs;
+  const int ssP = (int)p.small_sP, bsP = (int)p.big_sP;
+  const int ssT = HWs * ssP, bsH = p.Wb * bsP, bsT = p.Hb * bsH;
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+  int64_t idx = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * cols_per_warp;
+  const int64_t idx_end = idx + cols_per_warp < total ? idx + cols_per_warp : total;
+  int ws = 0, hs = 0, hd = 0, b = 0;
+  if (idx < idx_end) {
+    int o = (int)(idx % HWs);
+    int bh = (int)(idx / HWs);
+    hd = bh % p.heads; b = bh / p.heads;
+    ws = o % p.Ws; hs = o / p.Ws;
+  }
+  for (; idx < idx_end; ++idx) {
+    if (active) {
+      const TS* sp = small + b * p.small_sB + hd * p.small_sH + (hs * p.Ws + ws) * ssP + 4 * lane;
+      const TB* bp = big + b * p.big_sB + hd * p.big_sH + 4 * lane;
+      float sv[TSM][4];
+#pragma unroll
+      for (int t = 0; t < TSM; ++t) ld4(sp + t * ssT, sv[t]);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hb = (hs << lh) + kh - 1;
+        if (hb < 0 || hb >= p.Hb) continue;                          // warp-uniform
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int wb = (ws << lw) + kw - 1;
+          if (wb < 0 || wb >= p.Wb) continue;
+          const TB* src = bp + hb * bsH + wb * bsP;
+          float bv[TBG][4];
+#pragma unroll
+          for (int t = 0; t < TBG; ++t) ld4(src + t * bsT, bv[t]);
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+            for (int ts = 0; ts < TSM; ++ts) {
+              const int tb = ts * ST + kt - 1;
+              if (tb < 0 || tb >= TBG) continue;                     // resolved at compile time
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[(kt * 3 + kh) * 3 + kw][i] = fmaf(sv[ts][i], bv[tb][i], acc[(kt * 3 + kh) * 3 + kw][i]);
+            }
+        }
+      }
+    }
+    if (++ws == p.Ws) { ws = 0; if (++hs == p.Hs) { hs = 0; if (++hd == p.heads) { hd = 0; ++b; } } }
+  }
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < 27; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[t * D + 4 * lane + i], acc[t][i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
+    int tap = i / D, c = i - tap * D;
+    atomicAdd(p.dw + c * 27 + tap, s_dw[i]);
   }
 }
 
@@ -617,17 +701,28 @@ int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   int lt = log2_exact(p.st), lh = log2_exact(p.sh), lw = log2_exact(p.sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv: strides must be powers of two (%d,%d,%d)", p.st, p.sh, p.sw);
   static const bool no_tcol = getenv("CSTS_NO_TCOL") != nullptr;       // A/B tuning runs only
-  if (p.st == 1 && p.Ti == 4 && p.To == 4 && !no_tcol) {                // T-column kernel: one warp pass per (h, w) column
-    int64_t cols = (int64_t)p.B * p.heads * p.Ho * p.Wo;
-    int cgrid = grid_for(cols, 8);
+  // T-column kernels: one warp pass per (h, w) column
+  const int64_t cols = (int64_t)p.B * p.heads * p.Ho * p.Wo;
+  const int cgrid = grid_for(cols, 8);
+  if (p.st == 1 && p.Ti == 4 && p.To == 4 && !no_tcol) {
     if (p.transposed) {
-      if (norm) launch_pdl(dwconv_tcol_kernel<D, true, true, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
-      else launch_pdl(dwconv_tcol_kernel<D, true, false, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      if (norm) launch_pdl(dwconv_tcol_kernel<D, true, true, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      else launch_pdl(dwconv_tcol_kernel<D, true, false, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
     } else {
-      if (norm) launch_pdl(dwconv_tcol_kernel<D, false, true, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
-      else launch_pdl(dwconv_tcol_kernel<D, false, false, T, 4>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      if (norm) launch_pdl(dwconv_tcol_kernel<D, false, true, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      else launch_pdl(dwconv_tcol_kernel<D, false, false, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
     }
     return csts_check_launch("dwconv_tcol");
+  }
+  if (D == 96 && p.st == 2 && !no_tcol) {                               // the decoder's temporal up-sampling conv and its adjoint
+    if (p.transposed && norm && p.Ti == 4 && p.To == 8) {
+      launch_pdl(dwconv_tcol_kernel<96, true, true, T, 4, 8, 2>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      return csts_check_launch("dwconv_tcol");
+    }
+    if (!p.transposed && !norm && p.Ti == 8 && p.To == 4) {
+      launch_pdl(dwconv_tcol_kernel<96, false, false, T, 8, 4, 2>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      return csts_check_launch("dwconv_tcol");
+    }
   }
   if (p.transposed) {
     if (norm) launch_pdl(dwconv_kernel<D, true, true, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
@@ -663,14 +758,32 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   if (total == 0) return 0;
   int lt = log2_exact(p->st), lh = log2_exact(p->sh), lw = log2_exact(p->sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv_wgrad: strides must be powers of two");
+  CSTS_REQUIRE((p->small_dtype == CSTS_BF16 || p->small_dtype == CSTS_F16) && (p->big_dtype == CSTS_BF16 || p->big_dtype == CSTS_F16),
+               "dwconv_wgrad: operand dtypes must be 1 (bf16) or 2 (f16)");
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool no_tcol = getenv("CSTS_NO_TCOL") != nullptr;       // A/B tuning runs only
+  if (p->d == 96 && p->small_dtype == p->big_dtype && !no_tcol &&
+      ((p->st == 1 && p->Ts == 4 && p->Tb == 4) || (p->st == 2 && p->Ts == 4 && p->Tb == 8))) {
+    // T-column kernel; every block ends with 27*d global atomics: at most 3 blocks (of 4 warps) per SM
+    const int64_t cols = (int64_t)p->B * p->heads * p->Hs * p->Ws;
+    int64_t warps = cols < (int64_t)csts_num_sms() * 12 ? cols : (int64_t)csts_num_sms() * 12;
+    int cols_per_warp = (int)((cols + warps - 1) / warps);
+    int cgrid = (int)((cols + (int64_t)cols_per_warp * 4 - 1) / ((int64_t)cols_per_warp * 4));
+#define WGRAD_TCOL(TS_, TB_)                                                                                          \
+  do {                                                                                                                \
+    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid), dim3(128), 0, st, *p, lh, lw, cols_per_warp); \
+    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid), dim3(128), 0, st, *p, lh, lw, cols_per_warp);            \
+  } while (0)
+    if (p->small_dtype == CSTS_F16) WGRAD_TCOL(f16, f16);
+    else WGRAD_TCOL(bf16, bf16);
+#undef WGRAD_TCOL
+    return csts_check_launch("dwconv_wgrad_tcol");
+  }
   // every block ends with 27*d global atomics: cap the grid at 4 blocks per SM
   const int64_t rows_total = (int64_t)p->B * p->heads * p->Ts * p->Hs;
   int grid = (int)(rows_total < csts_num_sms() * 4 ? rows_total : csts_num_sms() * 4);
   int rows_per_block = (int)((rows_total + grid - 1) / grid);
   grid = (int)((rows_total + rows_per_block - 1) / rows_per_block);
-  cudaStream_t st = (cudaStream_t)stream;
-  CSTS_REQUIRE((p->small_dtype == CSTS_BF16 || p->small_dtype == CSTS_F16) && (p->big_dtype == CSTS_BF16 || p->big_dtype == CSTS_F16),
-               "dwconv_wgrad: operand dtypes must be 1 (bf16) or 2 (f16)");
 #define WGRAD_T(D_, SW_, TS_, TB_) launch_pdl(dwconv_wgrad_kernel<D_, SW_, TS_, TB_>, dim3(grid), dim3(288), 0, st, *p, lt, lh, lw, rows_per_block)
 #define WGRAD(D_, SW_)                                                                        \
   do {                                                                                        \
