@@ -73,6 +73,14 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 
 // ---- device helpers ---------------------------------------------------------------------------
+// index decode in 32-bit arithmetic (a 64-bit division costs ~100 instructions): q <- q / d, returns q % d.
+// The host side guarantees that the flattened work-item count of such kernels stays below 2^32.
+__device__ __forceinline__ uint32_t divmod(uint32_t& q, uint32_t d) {
+  uint32_t n = q;
+  q = n / d;
+  return n - q * d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -509,12 +509,13 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
                                                           int B, int T, int H, int W, int C) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
-  const int64_t total = (int64_t)B * T * Ho * Wo * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4) * 4;
-    int64_t pos = i / C4;
-    int wo = (int)(pos % Wo), ho = (int)((pos / Wo) % Ho);
-    int64_t bt = pos / ((int64_t)Wo * Ho);
+  const uint32_t total = (uint32_t)B * T * Ho * Wo * C4;               // < 2^32, checked on the host
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C4) * 4;
+    const int64_t pos = q;
+    const int wo = (int)divmod(q, Wo), ho = (int)divmod(q, Ho);
+    const int64_t bt = q;
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int bi[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -541,12 +542,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
                                                           float* __restrict__ dx, int B, int T, int H, int W, int C) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
-  const int64_t total = (int64_t)B * T * H * W * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4) * 4;
-    int64_t pos = i / C4;
-    int wi = (int)(pos % W), hi = (int)((pos / W) % H);
-    int64_t bt = pos / ((int64_t)W * H);
+  const uint32_t total = (uint32_t)B * T * H * W * C4;                 // < 2^32, checked on the host
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C4) * 4;
+    const int64_t pos = q;
+    const int wi = (int)divmod(q, W), hi = (int)divmod(q, H);
+    const int64_t bt = q;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -592,12 +594,13 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restri
                                                            int C, int ft, int fh, int fw) {
   pdl_wait();
   const int To = T * ft, Ho = H * fh, Wo = W * fw, C4 = C / 4;
-  const int64_t total = (int64_t)B * To * Ho * Wo * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4) * 4;
-    int64_t pos = i / C4;
-    int wo = (int)(pos % Wo), ho = (int)((pos / Wo) % Ho), to = (int)((pos / ((int64_t)Wo * Ho)) % To);
-    int64_t b = pos / ((int64_t)Wo * Ho * To);
+  const uint32_t total = (uint32_t)B * To * Ho * Wo * C4;              // < 2^32, checked on the host
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C4) * 4;
+    const int64_t pos = q;
+    const int wo = (int)divmod(q, Wo), ho = (int)divmod(q, Ho), to = (int)divmod(q, To);
+    const int64_t b = q;
     int t0, t1, h0, h1, w0, w1;
     float lt, lh, lw;
     lin_coef(to, ft, T, t0, t1, lt);
@@ -643,12 +646,13 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
                                                            int C, int ft, int fh, int fw, int accumulate) {
   pdl_wait();
   const int To = T * ft, Ho = H * fh, Wo = W * fw, C4 = C / 4;
-  const int64_t total = (int64_t)B * T * H * W * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4) * 4;
-    int64_t pos = i / C4;
-    int wi = (int)(pos % W), hi = (int)((pos / W) % H), ti = (int)((pos / ((int64_t)W * H)) % T);
-    int64_t b = pos / ((int64_t)W * H * T);
+  const uint32_t total = (uint32_t)B * T * H * W * C4;                 // < 2^32, checked on the host
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C4) * 4;
+    const int64_t pos = q;
+    const int wi = (int)divmod(q, W), hi = (int)divmod(q, H), ti = (int)divmod(q, T);
+    const int64_t b = q;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int tlo = ft == 1 ? ti : max(ti * ft - ft, 0), thi = ft == 1 ? ti : min(ti * ft + 2 * ft - 1, To - 1);
     int hlo = fh == 1 ? hi : max(hi * fh - fh, 0), hhi = fh == 1 ? hi : min(hi * fh + 2 * fh - 1, Ho - 1);
@@ -803,12 +807,14 @@ int csts_maxpool_fwd(const float* x, float* y, void* arg, int B, int T, int H, i
   CSTS_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: C%%4, H%%2, W%%2 required");
   int64_t total = (int64_t)B * T * (H / 2) * (W / 2) * (C / 4);
   if (total == 0) return 0;
+  CSTS_REQUIRE(total < (1LL << 32), "maxpool_fwd: tensor too large for 32-bit indexing");
   launch_pdl(maxpool_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, (uint8_t*)arg, B, T, H, W, C);
   return csts_check_launch("maxpool_fwd");
 }
 int csts_maxpool_bwd(const float* dy, const void* arg, float* dx, int B, int T, int H, int W, int C, void* stream) {
   int64_t total = (int64_t)B * T * H * W * (C / 4);
   if (total == 0) return 0;
+  CSTS_REQUIRE(total < (1LL << 32), "maxpool_bwd: tensor too large for 32-bit indexing");
   launch_pdl(maxpool_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, (const uint8_t*)arg, dx, B, T, H, W, C);
   return csts_check_launch("maxpool_bwd");
 }
@@ -816,6 +822,7 @@ int csts_upsample_fwd(const float* x, float* y, int B, int T, int H, int W, int 
   CSTS_REQUIRE(C % 4 == 0 && ft >= 1 && fh >= 1 && fw >= 1, "upsample: bad arguments");
   int64_t total = (int64_t)B * T * ft * H * fh * W * fw * (C / 4);
   if (total == 0) return 0;
+  CSTS_REQUIRE(total < (1LL << 32), "upsample_fwd: tensor too large for 32-bit indexing");
   launch_pdl(upsample_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, B, T, H, W, C, ft, fh, fw);
   return csts_check_launch("upsample_fwd");
 }
@@ -823,6 +830,7 @@ int csts_upsample_bwd(const float* dy, float* dx, int B, int T, int H, int W, in
   CSTS_REQUIRE(C % 4 == 0 && ft >= 1 && fh >= 1 && fw >= 1, "upsample: bad arguments");
   int64_t total = (int64_t)B * T * H * W * (C / 4);
   if (total == 0) return 0;
+  CSTS_REQUIRE(total < (1LL << 32), "upsample_bwd: tensor too large for 32-bit indexing");
   launch_pdl(upsample_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, dx, B, T, H, W, C, ft, fh, fw, accumulate);
   return csts_check_launch("upsample_bwd");
 }

@@ -324,6 +324,53 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
   }
 }
 
+// 8 columns per thread (one 16-byte load for 16-bit inputs, two for f32).  A block covers GX column groups x
+// RY = 256 / GX row phases, so narrow matrices (N = 96 ... 288 with M = 131072 rows) still keep every thread
+// busy; four rows are in flight per thread.
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]) {
+  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 a = unpack2<T>(t.x), b = unpack2<T>(t.y), c = unpack2<T>(t.z), d = unpack2<T>(t.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) colsum8_kernel(const T* __restrict__ X, float* __restrict__ out, int64_t M, int N, int64_t ld,
+                                                      int rows_per_block, int GX) {
+  pdl_wait();
+  __shared__ float red[256 * 8];
+  const int tx = threadIdx.x % GX, ty = threadIdx.x / GX, RY = blockDim.x / GX;
+  const int col = (blockIdx.x * GX + tx) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (ty < RY && col < N) {
+    const T* base = X + col;
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += RY) {
+      float v[8];
+      ld8(base + r * ld, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  if (ty == 0 && col < N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+      for (int y = 0; y < RY; ++y) t += red[(y * GX + tx) * 8 + i];
+      atomicAdd(out + col + i, t);
+    }
+  }
+}
+
 int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
   int64_t cap = (int64_t)csts_num_sms() * 8;
@@ -465,15 +512,30 @@ int csts_scale_f32(const float* a, const float* device_scalar, float* out, int64
 int csts_colsum(const void* X, int x_dtype, float* out, int64_t M, int N, int64_t ld, void* stream) {
   if (M == 0 || N == 0) return 0;
   CSTS_REQUIRE(N % 4 == 0 && ld % 4 == 0, "colsum: N and ld must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int esz = x_dtype == 0 ? 4 : 2;
+  if (N % 8 == 0 && (ld * esz) % 16 == 0 && ((uintptr_t)X & 15) == 0) {
+    const int groups = N / 8;
+    const int bx = ceil_div(groups, 32), GX = ceil_div(groups, bx), RY = 256 / GX;
+    int want_y = csts_num_sms() * 4 / bx;
+    if (want_y < 1) want_y = 1;
+    int rows_per_block = (int)((M + want_y - 1) / want_y);
+    if (rows_per_block < 8 * RY) rows_per_block = 8 * RY;
+    dim3 grid(bx, ceil_div(M, rows_per_block));
+    if (x_dtype == 0) launch_pdl(colsum8_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)X, out, M, N, ld, rows_per_block, GX);
+    else if (x_dtype == CSTS_F16) launch_pdl(colsum8_kernel<f16>, dim3(grid), dim3(256), 0, st, (const f16*)X, out, M, N, ld, rows_per_block, GX);
+    else launch_pdl(colsum8_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)X, out, M, N, ld, rows_per_block, GX);
+    return csts_check_launch("colsum8");
+  }
   int bx = ceil_div(N, 128);
   int want_y = csts_num_sms() * 4 / bx;
   if (want_y < 1) want_y = 1;
   int rows_per_block = (int)((M + want_y - 1) / want_y);
   if (rows_per_block < 64) rows_per_block = 64;
   dim3 grid(bx, ceil_div(M, rows_per_block));
-  if (x_dtype == 0) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)X, out, M, N, ld, rows_per_block);
-  else if (x_dtype == CSTS_F16) launch_pdl(colsum_kernel<f16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const f16*)X, out, M, N, ld, rows_per_block);
-  else launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)X, out, M, N, ld, rows_per_block);
+  if (x_dtype == 0) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)X, out, M, N, ld, rows_per_block);
+  else if (x_dtype == CSTS_F16) launch_pdl(colsum_kernel<f16>, dim3(grid), dim3(256), 0, st, (const f16*)X, out, M, N, ld, rows_per_block);
+  else launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)X, out, M, N, ld, rows_per_block);
   return csts_check_launch("colsum");
 }
 

@@ -15,25 +15,36 @@ int grid_for(int64_t work_items, int per_block) {
 // x f32 (B, Cin, T, H, W) -> patches (bf16 / f16) [B*To*Ho*Wo, Kp], column = ((c*3 + kt)*7 + kh)*7 + kw,
 // columns >= Cin*147 are zero (Kp is the GEMM-friendly padded width).
 // ------------------------------------------------------------------------------------------------
+// One thread produces 8 consecutive columns of one patch row (a 16-byte store): the (c, kt, kh, kw) decode is
+// done once per chunk and advanced incrementally, all index arithmetic is 32-bit.
 template <typename TO>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, TO* __restrict__ out, int B, int Cin, int T, int H,
                                                      int W, int Kp) {
   pdl_wait();
   const int To = T / 2, Ho = H / 4, Wo = W / 4;
   const int K = Cin * 147;
-  const int64_t total = (int64_t)B * To * Ho * Wo * Kp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int col = (int)(i % Kp);
-    int64_t tok = i / Kp;
-    float v = 0.f;
-    if (col < K) {
-      int kw = col % 7, kh = (col / 7) % 7, kt = (col / 49) % 3, c = col / 147;
-      int wo = (int)(tok % Wo), ho = (int)((tok / Wo) % Ho), to = (int)((tok / ((int64_t)Wo * Ho)) % To);
-      int64_t b = tok / ((int64_t)Wo * Ho * To);
-      int ti = to * 2 + kt - 1, hi = ho * 4 + kh - 3, wi = wo * 4 + kw - 3;
-      if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((b * Cin + c) * T + ti) * H + hi) * W + wi];
+  const uint32_t chunks = Kp / 8;
+  const uint32_t total = (uint32_t)B * To * Ho * Wo * chunks;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int col0 = (int)divmod(q, chunks) * 8;
+    const uint32_t tok = q;
+    const int wo = (int)divmod(q, Wo), ho = (int)divmod(q, Ho), to = (int)divmod(q, To);
+    const int b = (int)q;
+    int kw = col0 % 7, kh = (col0 / 7) % 7, kt = (col0 / 49) % 3, c = col0 / 147;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = 0.f;
+      if (col0 + e < K) {
+        const int ti = to * 2 + kt - 1, hi = ho * 4 + kh - 3, wi = wo * 4 + kw - 3;
+        if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W)
+          v[e] = __ldg(x + ((((int64_t)b * Cin + c) * T + ti) * H + hi) * W + wi);
+      }
+      if (++kw == 7) { kw = 0; if (++kh == 7) { kh = 0; if (++kt == 3) { kt = 0; ++c; } } }
     }
-    st_f(out + i, v);
+    uint4 pk = make_uint4(pack2<TO>(v[0], v[1]), pack2<TO>(v[2], v[3]), pack2<TO>(v[4], v[5]), pack2<TO>(v[6], v[7]));
+    *reinterpret_cast<uint4*>(out + (int64_t)tok * Kp + col0) = pk;
   }
 }
 
@@ -237,12 +248,11 @@ __global__ void classifier_bwd_stem_kernel(const float* __restrict__ dlogits, co
                                            int Ti, int S, int C) {
   pdl_wait();
   const int To = 2 * Ti;
-  const int64_t total = (int64_t)B * Ti * S * C;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t r = i / C;
-    int s = (int)(r % S), ti = (int)((r / S) % Ti);
-    int64_t b = r / ((int64_t)S * Ti);
+  const uint32_t total = (uint32_t)B * Ti * S * C;                      // < 2^32, checked on the host
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C), s = (int)divmod(q, S), ti = (int)divmod(q, Ti);
+    const int64_t b = q;
     float acc = 0.f;
     for (int to = max(2 * ti - 2, 0); to <= min(2 * ti + 3, To - 1); ++to) {
       int i0, i1; float lam;
@@ -263,8 +273,9 @@ extern "C" {
 int csts_im2col_patch(const float* x, void* patches, int dtype, int B, int Cin, int T, int H, int W, int Kp, void* stream) {
   CSTS_REQUIRE(dtype == CSTS_BF16 || dtype == CSTS_F16, "im2col: patches must be bf16 or f16");
   CSTS_REQUIRE(T % 2 == 0 && H % 4 == 0 && W % 4 == 0 && Kp >= Cin * 147 && Kp % 8 == 0, "im2col: bad geometry");
-  int64_t total = (int64_t)B * (T / 2) * (H / 4) * (W / 4) * Kp;
+  int64_t total = (int64_t)B * (T / 2) * (H / 4) * (W / 4) * (Kp / 8);          // 16-byte chunks
   if (total == 0) return 0;
+  CSTS_REQUIRE(total < (1LL << 32) && ((uintptr_t)patches & 15) == 0, "im2col: too many patch chunks for 32-bit indexing / unaligned output");
   if (dtype == CSTS_F16) launch_pdl(im2col_kernel<f16>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (f16*)patches, B, Cin, T, H, W, Kp);
   else launch_pdl(im2col_kernel<bf16>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)patches, B, Cin, T, H, W, Kp);
   return csts_check_launch("im2col_patch");
@@ -316,6 +327,7 @@ int csts_classifier_bwd(const float* dlogits, const float* feat, const float* st
   launch_pdl(classifier_bwd_feat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dlogits, feat, stem, w, dfeat, dw, dbias, B, Ti, S, C);
   int rc = csts_check_launch("classifier_bwd_feat");
   if (rc) return rc;
+  CSTS_REQUIRE((int64_t)B * Ti * S * C < (1LL << 32), "classifier_bwd: tensor too large for 32-bit indexing");
   launch_pdl(classifier_bwd_stem_kernel, dim3(grid_for((int64_t)B * Ti * S * C, 256)), dim3(256), 0, (cudaStream_t)stream, dlogits, w, dstem, B, Ti, S, C);
   return csts_check_launch("classifier_bwd_stem");
 }

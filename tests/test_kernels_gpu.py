@@ -431,6 +431,13 @@ def test_permute_and_cast_and_colsum():
     assert rel_err(k.colsum(X, 3000, 288), X.float().sum(0)) < 1e-5
     Xf = torch.randn(777, 96, generator=g).to(dev)
     assert rel_err(k.colsum(Xf, 777, 96), Xf.sum(0)) < 1e-5
+    # wide (several column blocks), strided rows, a width that takes the 4-column kernel, tiny M, f16, accumulate-into
+    for M, N, ld, dt_ in [(5000, 3072, 3072, torch.bfloat16), (1234, 768, 2304, torch.bfloat16), (333, 100, 100, torch.float32),
+                          (3, 256, 256, torch.float32), (4097, 1536, 1536, torch.float16), (70000, 8, 8, torch.bfloat16)]:
+        Xs = torch.randn(M, ld, generator=g).to(dt_).to(dev)
+        out = torch.full((N,), 0.5, device=dev)
+        k.colsum(Xs, M, N, ld=ld, out=out)
+        assert rel_err(out, 0.5 + Xs[:, :N].float().sum(0)) < 2e-5, (M, N, ld, dt_)
     a, b = torch.randn(4096, generator=g).to(dev), torch.randn(4096, generator=g).to(dev)
     assert torch.equal(k.add_f32(a, b), a + b)
     s = torch.tensor([0.25], device=dev)
