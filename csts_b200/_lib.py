@@ -94,6 +94,8 @@ SIGNATURES = {
     "csts_sim_matrix_fwd": [_P, _P, _P, _P, _P, _I, _I, _F, _P],
     "csts_sim_matrix_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "csts_egonce": [_P, _P, _P, _P, _I, _F, _P],
+    "csts_grad_sqnorm": [_P, _P, _I, _P, _P],
+    "csts_clip_adamw_step": [_P, _P, _I, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _F, _F, _P],
 }
 
 _lib = None
@@ -115,6 +117,8 @@ def load():
         fn.restype = C.c_int
     lib.csts_gemm_backend.argtypes = [C.POINTER(GemmArgs)]
     lib.csts_gemm_backend.restype = C.c_int
+    lib.csts_mt_chunk_elems.argtypes = []
+    lib.csts_mt_chunk_elems.restype = C.c_int
     lib.csts_launch_count.argtypes = [C.c_int]
     lib.csts_launch_count.restype = C.c_longlong
     _lib = lib

@@ -349,9 +349,11 @@ class CSTS(nn.Module):
         if not video.is_cuda:
             raise RuntimeError("csts_b200.CSTS runs on CUDA (sm_100a) only; there is no CPU path")
         video, audio = video.float(), y.float()
+        wc = self._wc
         if self.training:
             self._draw_drop_path(video.shape[0], video.device)
-        wc = self._wc
+            if torch.is_grad_enabled():
+                wc.begin_training_step()
         x = PatchEmbedFn.apply(wc, video, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
                                self.pos_embed_spatial, self.pos_embed_temporal)
         y = PatchEmbedFn.apply(wc, audio, self.patch_embed_audio.proj.weight, self.patch_embed_audio.proj.bias,

@@ -10,7 +10,7 @@ from . import losses
 from .utils import frame_softmax, sim_matrix
 
 
-def construct_optimizer(model, cfg, capturable=False):
+def construct_optimizer(model, cfg, capturable=False, fused_clip=False):
     """Parameter grouping of slowfast/models/optimizer.py:11-108 for the AdamW case: weight decay on
     matrices / conv kernels / position embeddings, zero weight decay on 1-D parameters and biases
     (SOLVER.ZERO_WD_1D_PARAM) and on model.no_weight_decay()."""
@@ -34,6 +34,9 @@ def construct_optimizer(model, cfg, capturable=False):
     lr = cfg.SOLVER.BASE_LR
     if capturable:      # CUDA-graph replay: the learning rate must live on the device
         lr = torch.tensor(float(lr), dtype=torch.float32, device=decay[0].device)
+    if fused_clip:      # unscale + clip + AdamW + 16-bit weight refresh in one pass (host/optimizer.py); graph-capturable
+        from .optimizer import FusedClipAdamW
+        return FusedClipAdamW(groups, lr=lr, weight_decay=cfg.SOLVER.WEIGHT_DECAY, eps=1e-08, weight_cache=getattr(inner, "_wc", None))
     return torch.optim.AdamW(groups, lr=lr, eps=1e-08, weight_decay=cfg.SOLVER.WEIGHT_DECAY, fused=True, capturable=capturable)
 
 
@@ -86,6 +89,9 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, 
         root.backward()
         if grad_sync is not None:
             grad_sync()
+    if hasattr(optimizer, "clip_and_step"):          # FusedClipAdamW: lines 101-109 of the reference loop in two launches
+        optimizer.clip_and_step(cfg.SOLVER.CLIP_GRAD_L2NORM or 0.0, scaler if scaling else None)
+        return loss.detach()
     if scaling:
         scaler.unscale_(optimizer)
     if cfg.SOLVER.CLIP_GRAD_L2NORM:
@@ -135,7 +141,9 @@ class GraphedTrainStep:
                 train_step(cfg, model, optimizer, [self.video], self.audio, self.labels, grad_sync=self.grad_sync, scaler=self.scaler)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        inner._wc.clear()                        # the 16-bit weight casts must be part of the captured step
+        # The 16-bit weight copies: with torch's optimizer they are rebuilt at the top of every training forward
+        # (WeightCache.begin_training_step), so the casts become part of the captured step; with the fused
+        # optimizer the AdamW kernel itself rewrites them at the end of every step and no cast is captured.
         optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

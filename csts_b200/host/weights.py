@@ -35,10 +35,22 @@ class WeightCache:
     def __init__(self, precision=BF16):
         self._store = {}
         self.act, self.grad = precision
+        self._gen = 0            # training-step generation: copies made in an earlier step are not trusted
+        self._fresh = False      # set by the fused optimizer step, which rewrites the copies itself
+
+    def begin_training_step(self):
+        """Called at the top of every training forward.  A parameter's version counter is not a reliable
+        "changed" signal (torch's *fused* optimizers update parameters without bumping it), so in training the
+        copies are rebuilt once per step — unless the fused clip+AdamW step (host/optimizer.py) has just
+        rewritten them, which it announces through after_fused_step()."""
+        if self._fresh:
+            self._fresh = False
+        else:
+            self._gen += 1
 
     def _get(self, param, kind, make):
         key = (id(param), kind)
-        ver = (param.data_ptr(), param._version)
+        ver = (param.data_ptr(), param._version, self._gen)
         hit = self._store.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -61,6 +73,19 @@ class WeightCache:
         o, c = param.shape[0], param.shape[1]
         hw = param.shape[3] * param.shape[4]
         return self._get(param, "fpw", lambda p: K.permute_021(p.reshape(o, c, hw), o, c, hw, self.act).reshape(o, hw * c))
+
+    # ---- fused optimizer step (host/optimizer.py): the AdamW kernel writes the 16-bit copy itself -----------
+    def bound_copy(self, param):
+        """The live plain (N, K) copy of `param` (same element order as the parameter), or None."""
+        hit = self._store.get((id(param), "w"))
+        return hit[1] if hit is not None else None
+
+    def after_fused_step(self):
+        """The fused step updated the parameters in place behind autograd's back (no version bump): the plain
+        copies it refreshed stay valid, the re-laid-out ones (padded / permuted) must be rebuilt."""
+        for key in [k for k in self._store if k[1] != "w"]:
+            del self._store[key]
+        self._fresh = True
 
     def clear(self):
         self._store.clear()

@@ -179,6 +179,32 @@ int csts_sim_matrix_bwd(const float* a, const float* b, const float* sim, const 
 /* EgoNCE (slowfast/models/losses.py:157-170): loss and d loss / d sim; lse_scratch holds 2*n floats */
 int csts_egonce(const float* sim, float* loss, float* dsim, float* lse_scratch, int n, float temperature, void* stream);
 
+/* ---- optimizer step ------------------------------------------------------------------------------------
+ * The tail of the training step (tools/train_avgaze_net.py:101-109; slowfast/models/optimizer.py:98-104):
+ * scaler.unscale_ + clip_grad_norm_(max_norm) + AdamW (torch semantics: decoupled weight decay, eps outside
+ * the bias-corrected sqrt) + refresh of the 16-bit operand copy of each weight, as two multi-tensor launches.
+ * `tensors` is a DEVICE array describing every parameter; `chunks` a DEVICE array of (tensor index, chunk
+ * index) pairs, one per csts_mt_chunk_elems() elements of each tensor.  All state is f32.  When the gradient
+ * norm is not finite the step is skipped and *found_inf = 1 (GradScaler semantics).  *step is the number of
+ * steps already taken; the caller increments it afterwards (by 1 - *found_inf). */
+typedef struct csts_mt_tensor {
+  void* param;            /* f32, updated in place */
+  const void* grad;       /* f32, read only (left scaled / un-clipped) */
+  void* exp_avg;          /* f32 */
+  void* exp_avg_sq;       /* f32 */
+  void* w16;              /* bf16 / f16 copy of the updated parameter, same element order, or NULL */
+  int64_t numel;
+  float weight_decay;
+  int32_t group;          /* 0 / 1: which learning-rate scalar applies */
+  int32_t w16_dtype;      /* 1 bf16, 2 f16 */
+  int32_t pad_;
+} csts_mt_tensor;
+int csts_mt_chunk_elems(void);
+int csts_grad_sqnorm(const csts_mt_tensor* tensors, const int32_t* chunks, int n_chunks, double* out_sq, void* stream);
+int csts_clip_adamw_step(const csts_mt_tensor* tensors, const int32_t* chunks, int n_chunks, const double* total_sq, const float* grad_scale,
+                         float* found_inf, const float* step, const float* lr0, const float* lr1, double beta1, double beta2, float eps,
+                         float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

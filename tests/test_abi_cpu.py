@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_binding_matches_header():
     from csts_b200 import _lib
-    bound = set(_lib.SIGNATURES) | {"csts_launch_count", "csts_gemm_backend"}
+    bound = set(_lib.SIGNATURES) | {"csts_launch_count", "csts_gemm_backend", "csts_mt_chunk_elems"}
     assert bound == set(declared_symbols())
     _lib.load()
 

@@ -305,3 +305,46 @@ def test_droppath_statistics():
     assert torch.equal(y_plain, y_one)
     assert torch.equal(y_mix[0], x[0])                       # dropped sample: both branches vanish
     assert not torch.equal(y_mix[1], y_plain[1])
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_graphed_step_with_fused_optimizer_tracks_the_reference_loop(golden_dir, mode):
+    """GraphedTrainStep + FusedClipAdamW (one CUDA graph; unscale + clip + AdamW + weight refresh in two launches)
+    against the literal loop of tools/train_avgaze_net.py:70-109 (eager; GradScaler.unscale_, clip_grad_norm_,
+    torch AdamW) on the same kernels: same losses and same parameters after five steps."""
+    import csts_oracle as O
+    from csts_b200.host.build import build_model
+    from csts_b200.host.train_step import GraphedTrainStep, construct_optimizer, make_grad_scaler, train_step
+    shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
+    sd = O.synthetic_state(shapes, seed=3, gain=1.0)
+    video, audio, hm = (t.to(dev) for t in O.synthetic_batch(2, seed=4))
+    cfg = make_cfg(mixed=mode == "fp16")
+    cfg.SOLVER.BASE_LR = 1e-4
+
+    def fresh():
+        m = build_model(cfg)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        return m
+
+    ref_model = fresh()
+    ref_opt = construct_optimizer(ref_model, cfg)
+    ref_scaler = make_grad_scaler(cfg, init_scale=4096.0)
+    ref_losses = [train_step(cfg, ref_model, ref_opt, [video], audio, hm, scaler=ref_scaler).item() for _ in range(5)]
+
+    model = fresh()
+    opt = construct_optimizer(model, cfg, capturable=True, fused_clip=True)
+    scaler = make_grad_scaler(cfg, init_scale=4096.0)
+    step = GraphedTrainStep(cfg, model, opt, video, audio, hm, warmup=3, scaler=scaler)      # three eager steps, then capture
+    losses = [step(None, None, None).item() for _ in range(2)]
+    assert ref_losses[0] > ref_losses[-1]                                                   # it trains
+    for got, want in zip(losses, ref_losses[3:]):
+        assert abs(got - want) <= 1e-4 * abs(want), (losses, ref_losses)
+    # parameters: Adam moves every element by ~lr per step whatever the gradient's size, so elements whose gradient is
+    # rounding noise may legitimately step in opposite directions in two runs; compare in units of the travelled distance
+    num = sum((p - q).float().pow(2).sum().item() for p, q in zip(model.parameters(), ref_model.parameters()))
+    moved = sum((p - sd[n].to(dev)).float().pow(2).sum().item() for n, p in model.named_parameters())
+    assert moved > 0 and (num / moved) ** 0.5 < 0.05, (num, moved)
+    assert opt._step.item() == 5.0
+    if mode == "fp16":
+        assert scaler.get_scale() == ref_scaler.get_scale()
