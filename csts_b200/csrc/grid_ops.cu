@@ -421,19 +421,20 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
 }
 
 // T-column weight gradient (d = 96, compile-time temporal extents: TSM planes of `small`, TBG planes of `big`,
-// temporal stride ST).  A warp owns one (b, head, hs, ws) column of `small`: its TSM values are unpacked once,
-// each valid spatial tap unpacks its TBG planes of `big` once, and all 27 taps accumulate in registers
-// (27 x 4 channels per lane) — no operand is re-read by another warp, unlike the tap-row kernel above where
-// nine warps each re-load the same `small` row.  Warps of a block combine through shared memory, then one
-// global atomic per weight per block.
+// temporal stride ST).  Three warps share one (b, head, hs, ws) column of `small`, one per kernel row kh: a warp
+// issues its 4 + 3*TBG independent loads (the column of `small`, the kw = 0..2 columns of its `big` row) before
+// touching any of them, then accumulates its 9 taps (kt x kw) x 4 channels in registers.  The kernel is
+// latency-bound on L2-resident data, so what matters is loads in flight: ~16 per warp, 18 warps per SM.
+// Warps of a block combine through shared memory, then one global atomic per weight per block.
 template <typename TS, typename TB, int TSM, int TBG, int ST>
-__global__ void __launch_bounds__(128) dwconv_wgrad_tcol_kernel(csts_wgrad_args p, int lh, int lw, int cols_per_warp) {
+__global__ void __launch_bounds__(192) dwconv_wgrad_tcol_kernel(csts_wgrad_args p, int lh, int lw, int cols_per_slot) {
   pdl_wait();
   constexpr int D = 96;
   __shared__ float s_dw[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) s_dw[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kh = warp % 3, slot = warp / 3, slots = (blockDim.x >> 5) / 3;
   const bool active = 4 * lane < D;
   const TS* small = reinterpret_cast<const TS*>(p.small);
   const TB* big = reinterpret_cast<const TB*>(p.big);
@@ -441,13 +442,15 @@ __global__ void __launch_bounds__(128) dwconv_wgrad_tcol_kernel(csts_wgrad_args 
   const int64_t total = (int64_t)p.B * p.heads * HWs;
   const int ssP = (int)p.small_sP, bsP = (int)p.big_sP;
   const int ssT = HWs * ssP, bsH = p.Wb * bsP, bsT = p.Hb * bsH;
-  float acc[27][4];
+  float acc[3][3][4];                                                   // [kt][kw][channel]
 #pragma unroll
-  for (int t = 0; t < 27; ++t)
+  for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-  int64_t idx = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * cols_per_warp;
-  const int64_t idx_end = idx + cols_per_warp < total ? idx + cols_per_warp : total;
+    for (int b2 = 0; b2 < 3; ++b2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[a][b2][i] = 0.f;
+  int64_t idx = ((int64_t)blockIdx.x * slots + slot) * cols_per_slot;
+  const int64_t idx_end = idx + cols_per_slot < total ? idx + cols_per_slot : total;
   int ws = 0, hs = 0, hd = 0, b = 0;
   if (idx < idx_end) {
     int o = (int)(idx % HWs);
@@ -456,43 +459,54 @@ __global__ void __launch_bounds__(128) dwconv_wgrad_tcol_kernel(csts_wgrad_args 
     ws = o % p.Ws; hs = o / p.Ws;
   }
   for (; idx < idx_end; ++idx) {
-    if (active) {
+    const int hb = (hs << lh) + kh - 1;
+    if (active && hb >= 0 && hb < p.Hb) {                               // warp-uniform
       const TS* sp = small + b * p.small_sB + hd * p.small_sH + (hs * p.Ws + ws) * ssP + 4 * lane;
-      const TB* bp = big + b * p.big_sB + hd * p.big_sH + 4 * lane;
+      const TB* bp = big + b * p.big_sB + hd * p.big_sH + hb * bsH + 4 * lane;
+      uint2 sraw[TSM], braw[3][TBG];
+#pragma unroll
+      for (int t = 0; t < TSM; ++t) sraw[t] = __ldg(reinterpret_cast<const uint2*>(sp + t * ssT));
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wb = (ws << lw) + kw - 1;
+        const bool ok = wb >= 0 && wb < p.Wb;
+#pragma unroll
+        for (int t = 0; t < TBG; ++t) braw[kw][t] = ok ? __ldg(reinterpret_cast<const uint2*>(bp + wb * bsP + t * bsT)) : make_uint2(0u, 0u);
+      }
       float sv[TSM][4];
 #pragma unroll
-      for (int t = 0; t < TSM; ++t) ld4(sp + t * ssT, sv[t]);
+      for (int t = 0; t < TSM; ++t) {
+        float2 lo = unpack2<TS>(sraw[t].x), hi = unpack2<TS>(sraw[t].y);
+        sv[t][0] = lo.x; sv[t][1] = lo.y; sv[t][2] = hi.x; sv[t][3] = hi.y;
+      }
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int hb = (hs << lh) + kh - 1;
-        if (hb < 0 || hb >= p.Hb) continue;                          // warp-uniform
+      for (int kw = 0; kw < 3; ++kw) {
+        float bv[TBG][4];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int wb = (ws << lw) + kw - 1;
-          if (wb < 0 || wb >= p.Wb) continue;
-          const TB* src = bp + hb * bsH + wb * bsP;
-          float bv[TBG][4];
-#pragma unroll
-          for (int t = 0; t < TBG; ++t) ld4(src + t * bsT, bv[t]);
-#pragma unroll
-          for (int kt = 0; kt < 3; ++kt)
-#pragma unroll
-            for (int ts = 0; ts < TSM; ++ts) {
-              const int tb = ts * ST + kt - 1;
-              if (tb < 0 || tb >= TBG) continue;                     // resolved at compile time
-#pragma unroll
-              for (int i = 0; i < 4; ++i) acc[(kt * 3 + kh) * 3 + kw][i] = fmaf(sv[ts][i], bv[tb][i], acc[(kt * 3 + kh) * 3 + kw][i]);
-            }
+        for (int t = 0; t < TBG; ++t) {
+          float2 lo = unpack2<TB>(braw[kw][t].x), hi = unpack2<TB>(braw[kw][t].y);
+          bv[t][0] = lo.x; bv[t][1] = lo.y; bv[t][2] = hi.x; bv[t][3] = hi.y;
         }
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+          for (int ts = 0; ts < TSM; ++ts) {
+            const int tb = ts * ST + kt - 1;
+            if (tb < 0 || tb >= TBG) continue;                          // resolved at compile time
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[kt][kw][i] = fmaf(sv[ts][i], bv[tb][i], acc[kt][kw][i]);
+          }
       }
     }
     if (++ws == p.Ws) { ws = 0; if (++hs == p.Hs) { hs = 0; if (++hd == p.heads) { hd = 0; ++b; } } }
   }
   if (active) {
 #pragma unroll
-    for (int t = 0; t < 27; ++t)
+    for (int kt = 0; kt < 3; ++kt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[t * D + 4 * lane + i], acc[t][i]);
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[((kt * 3 + kh) * 3 + kw) * D + 4 * lane + i], acc[kt][kw][i]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
@@ -768,15 +782,16 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   static const bool no_tcol = getenv("CSTS_NO_TCOL") != nullptr;       // A/B tuning runs only
   if (p->d == 96 && p->small_dtype == p->big_dtype && !no_tcol &&
       ((p->st == 1 && p->Ts == 4 && p->Tb == 4) || (p->st == 2 && p->Ts == 4 && p->Tb == 8))) {
-    // T-column kernel; every block ends with 27*d global atomics: at most 3 blocks (of 4 warps) per SM
+    // T-column kernel: 2 column slots x 3 kernel rows per block; every block ends with 27*d global atomics, so at
+    // most 3 blocks per SM
     const int64_t cols = (int64_t)p->B * p->heads * p->Hs * p->Ws;
-    int64_t warps = cols < (int64_t)csts_num_sms() * 12 ? cols : (int64_t)csts_num_sms() * 12;
-    int cols_per_warp = (int)((cols + warps - 1) / warps);
-    int cgrid = (int)((cols + (int64_t)cols_per_warp * 4 - 1) / ((int64_t)cols_per_warp * 4));
+    int64_t nslots = cols < (int64_t)csts_num_sms() * 6 ? cols : (int64_t)csts_num_sms() * 6;
+    int cols_per_warp = (int)((cols + nslots - 1) / nslots);
+    int cgrid = (int)((cols + (int64_t)cols_per_warp * 2 - 1) / ((int64_t)cols_per_warp * 2));
 #define WGRAD_TCOL(TS_, TB_)                                                                                          \
   do {                                                                                                                \
-    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid), dim3(128), 0, st, *p, lh, lw, cols_per_warp); \
-    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid), dim3(128), 0, st, *p, lh, lw, cols_per_warp);            \
+    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid), dim3(192), 0, st, *p, lh, lw, cols_per_warp); \
+    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid), dim3(192), 0, st, *p, lh, lw, cols_per_warp);            \
   } while (0)
     if (p->small_dtype == CSTS_F16) WGRAD_TCOL(f16, f16);
     else WGRAD_TCOL(bf16, bf16);
