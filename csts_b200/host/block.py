@@ -155,8 +155,16 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     return y, thw_q, sv, attn
 
 
-def block_backward(spec, p, wc, sv, dy):
-    """dy: f32 (B, Lq, dim_out).  Returns (dx f32 (B,N,C), {param name: grad})."""
+def audio_rows(P, thw):
+    """Rows of the spatial-fusion attention that SpatialAttention turns into its audio-attention map
+    (av_attention.py:364-365): P[b, h, THW + t, HW*t : HW*(t+1)] for every frame t -> f32 (B, heads, T, HW)."""
+    T, HW = thw[0], thw[1] * thw[2]
+    return torch.stack([P[:, :, T * HW + t, HW * t: HW * (t + 1)] for t in range(T)], dim=2).float()
+
+
+def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
+    """dy: f32 (B, Lq, dim_out).  Returns (dx f32 (B,N,C), {param name: grad}).  d_audio_rows: gradient w.r.t.
+    audio_rows(P) (MVIT.SPATIAL_AUDIO_ATTN), folded into dP before the softmax backward."""
     x = sv["x"]
     B, N, C = x.shape
     h, d = spec.heads, spec.head_dim
@@ -242,6 +250,10 @@ def block_backward(spec, p, wc, sv, dy):
         dP = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=dev)
         K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP,
                b_off=v.off)
+        if d_audio_rows is not None:
+            T_, HW_ = thw[0], thw[1] * thw[2]
+            for t in range(T_):
+                dP[:, :, T_ * HW_ + t, HW_ * t: HW_ * (t + 1)] += d_audio_rows[:, :, t]
         dS = K.softmax_bwd(P, dP, Lk, d ** -0.5, dtype=wc.grad)
         del dP
     dq_t, tgt = grad_target(pooled_q, Lq, 0)
@@ -290,20 +302,28 @@ class BlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, x, *params):
-        spec, wc, thw, dp_scale, names = meta
+        spec, wc, thw, dp_scale, names = meta[:5]
+        extra = meta[5] if len(meta) > 5 else None       # {"want": "attn" | "audio_rows"}: optional attention outputs
         p = dict(zip(names, params))
         need = any(ctx.needs_input_grad)      # forward runs under no_grad: ask the node, not the mode
-        y, thw_q, sv, _ = block_forward(spec, p, wc, x.contiguous(), thw, dp_scale, save=need)
+        y, thw_q, sv, attn = block_forward(spec, p, wc, x.contiguous(), thw, dp_scale, save=need, want_attn=extra is not None)
         ctx.meta = meta
         ctx.sv = sv
         ctx.params = params
         ctx.thw_q = thw_q
+        if extra is not None and extra.get("want") == "audio_rows":
+            assert spec.kind == "spatial"
+            return y, audio_rows(attn, thw)              # second, differentiable output
+        if extra is not None:
+            extra["attn"] = attn                         # visualisation output (detached)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
-        spec, wc, thw, dp_scale, names = ctx.meta
+    def backward(ctx, dy, d_audio_rows=None):
+        spec, wc, thw, dp_scale, names = ctx.meta[:5]
         p = dict(zip(names, ctx.params))
-        dx, g = block_backward(spec, p, wc, ctx.sv, dy)
+        if dy is None:
+            dy = torch.zeros(ctx.sv["x"].shape[0], ctx.sv["Lq"], spec.dim_out, dtype=torch.float32, device=ctx.sv["x"].device)
+        dx, g = block_backward(spec, p, wc, ctx.sv, dy, d_audio_rows)
         ctx.sv = None
         return (None, dx) + tuple(g[n].view_as(p[n]) for n in names)

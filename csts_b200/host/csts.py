@@ -259,8 +259,6 @@ class CSTS(nn.Module):
         assert list(mv.PATCH_KERNEL) == [3, 7, 7] and list(mv.PATCH_STRIDE) == [2, 4, 4] and list(mv.PATCH_PADDING) == [1, 3, 3], \
             "the patch-embed kernel is specialised for k(3,7,7) s(2,4,4) p(1,3,3)"
         self.spatial_audio_attn = mv.SPATIAL_AUDIO_ATTN
-        if self.spatial_audio_attn:
-            raise NotImplementedError("MVIT.SPATIAL_AUDIO_ATTN=True is not part of the hot path yet (SURVEY.md §8f row 3)")
         norm_layer = partial(nn.LayerNorm, eps=1e-6)
         embed_dim = mv.EMBED_DIM
         self.patch_stride = list(mv.PATCH_STRIDE)
@@ -319,12 +317,12 @@ class CSTS(nn.Module):
         return {}
 
     # -----------------------------------------------------------------------------------------
-    def _run_block(self, blk, x, thw):
+    def _run_block(self, blk, x, thw, extra=None):
         spec = blk.spec
         dp_scale = None
         if self.training and spec.drop_path > 0.0:
             dp_scale = self._dp_scales[self._dp_site[id(blk)]]
-        meta = (spec, self._wc, tuple(thw), dp_scale, blk._names)
+        meta = (spec, self._wc, tuple(thw), dp_scale, blk._names) + ((extra,) if extra is not None else ())
         y = BlockFn.apply(meta, x, *blk.tensors())
         return y, spec.q_grid(thw)
 
@@ -343,8 +341,6 @@ class CSTS(nn.Module):
         self._dp_scales = torch.floor(u.add_(self._dp_keep)).div_(self._dp_keep)
 
     def forward(self, x, y, return_embed=False, return_spatial_attn=False, return_temporal_attn=False):
-        if return_spatial_attn or return_temporal_attn:
-            raise NotImplementedError("attention-map outputs are a visualisation path (SURVEY.md §8f row 3)")
         video = x[0] if isinstance(x, (list, tuple)) else x
         if not video.is_cuda:
             raise RuntimeError("csts_b200.CSTS runs on CUDA (sm_100a) only; there is no CPU path")
@@ -371,12 +367,24 @@ class CSTS(nn.Module):
         # spatial fusion (custom_multimodal_builder.py:414-432)
         n_vis = x.shape[1]
         y_sp = FramePoolFn.apply(wc, y, self.audio_pool.weight, self.audio_pool.bias)
-        av, _ = self._run_block(self.spatial_fusion, torch.cat([x, y_sp], dim=1), thw)
+        sp_extra = {"want": "audio_rows"} if self.spatial_audio_attn else ({"want": "attn"} if return_spatial_attn else None)
+        av, _ = self._run_block(self.spatial_fusion, torch.cat([x, y_sp], dim=1), thw, sp_extra)
+        x_tin = x
+        if self.spatial_audio_attn:
+            # audio-attention re-weighting of the temporal-fusion input (av_attention.py:360-370 and :438-440): min-max
+            # rescale of the audio token's attention over its frame, mean over heads.  Optional path (no shipped YAML
+            # enables it): the handful of small elementwise ops below run in torch, under autograd.
+            av, a_rows = av                                              # (B, heads, T, HW) rows of P, differentiable
+            amax = a_rows.max(dim=-1, keepdim=True)[0]
+            amin = a_rows.min(dim=-1, keepdim=True)[0]
+            w_a = ((a_rows - amin) / (amax - amin + 1e-8)).mean(dim=1).reshape(x.shape[0], -1, 1)
+            x_tin = x * w_a
         x_sp = av[:, :n_vis]
         # temporal fusion (:435-451)
-        x_t = FramePoolFn.apply(wc, x, self.vision_pool.weight, self.vision_pool.bias)
+        x_t = FramePoolFn.apply(wc, x_tin, self.vision_pool.weight, self.vision_pool.bias)
         y_t = FramePoolFn.apply(wc, y, self.audio_pool2.weight, self.audio_pool2.bias)
-        av_t, _ = self._run_block(self.temporal_fusion, torch.cat([x_t, y_t], dim=1), (2, 2, 2))
+        tm_extra = {"want": "attn"} if return_temporal_attn else None
+        av_t, _ = self._run_block(self.temporal_fusion, torch.cat([x_t, y_t], dim=1), (2, 2, 2), tm_extra)
         # re-weight (:454-461)
         T = thw[0]
         Cn = x.shape[2]
@@ -389,6 +397,16 @@ class CSTS(nn.Module):
                 f = AddFn.apply(f, skips[3 - i][0])
         stem, thw0 = skips[0]
         logits = HeadFn.apply(f, stem, self.classifier.weight, self.classifier.bias, thw0)
+        if not return_embed and (return_spatial_attn or return_temporal_attn):           # :485-491, visualisation outputs
+            out = [logits]
+            if return_spatial_attn:
+                if self.spatial_audio_attn:
+                    raise ValueError("return_spatial_attn is undefined under MVIT.SPATIAL_AUDIO_ATTN (as in the reference, "
+                                     "custom_multimodal_builder.py:425-430)")
+                out.append(sp_extra["attn"])
+            if return_temporal_attn:
+                out.append(tm_extra["attn"])
+            return out
         if not return_embed:
             return logits
         yw = ReweightFn.apply(y, av_t, T * Cn, T)

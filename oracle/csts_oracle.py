@@ -337,11 +337,26 @@ def frame_pool(sd, name, tok, thw):
     return y.squeeze(-1).squeeze(-1).permute(0, 2, 1)
 
 
-def csts_forward(sd, video, audio, return_embed=False, return_intermediates=False):
-    """CSTS.forward.  ref: custom_multimodal_builder.py:343-498 (default flags:
-    SPATIAL_AUDIO_ATTN False, CLS_EMBED_ON False, SEP_POS_EMBED True, dropout 0).
+def audio_rescale(p, thw):
+    """SpatialAttention's audio-attention map (ref av_attention.py:360-370): the attention of audio token t over
+    the H*W visual tokens of frame t, min-max rescaled per (b, head, t).  p (B,h,THW+T,THW+T) -> (B,h,T,H,W)."""
+    T, H, W = thw
+    HW, THW = H * W, T * H * W
+    a = torch.stack([p[:, :, THW + t, HW * t: HW * (t + 1)] for t in range(T)], dim=2)
+    amax = a.max(dim=-1, keepdim=True)[0]
+    amin = a.min(dim=-1, keepdim=True)[0]
+    a = (a - amin) / (amax - amin + 1e-8)
+    return a.reshape(a.shape[0], a.shape[1], T, H, W)
+
+
+def csts_forward(sd, video, audio, return_embed=False, return_intermediates=False, spatial_audio_attn=False,
+                 return_spatial_attn=False, return_temporal_attn=False):
+    """CSTS.forward.  ref: custom_multimodal_builder.py:343-498 (CLS_EMBED_ON False, SEP_POS_EMBED True,
+    dropout 0; `spatial_audio_attn` = MVIT.SPATIAL_AUDIO_ATTN, default False in every shipped YAML).
 
     video (B,3,8,256,256), audio (B,1,8,256,256) -> logits (B,1,8,64,64) [, v (B,256), a (B,256)]
+    With return_spatial_attn / return_temporal_attn (and no return_embed): [logits, spatial_attn?, temporal_attn?]
+    (ref :483-491), the attention probabilities of the two fusion blocks.
     """
     inter = {}
     x = patch_embed(sd, "patch_embed", video)
@@ -364,12 +379,16 @@ def csts_forward(sd, video, audio, return_embed=False, return_intermediates=Fals
     inter["enc_video"], inter["enc_audio"] = x, y
     # spatial fusion, ref :414-432
     y_sp = frame_pool(sd, "audio_pool", y, thw_a)
-    av, _ = block(sd, "spatial_fusion", torch.cat([x, y_sp], dim=1), thw)
+    av, _, p_sp = block(sd, "spatial_fusion", torch.cat([x, y_sp], dim=1), thw, want_attn=True)
     x_sp = av[:, : x.shape[1]]
     # temporal fusion, ref :435-451
-    x_t = frame_pool(sd, "vision_pool", x, thw)
+    x_in = x
+    if spatial_audio_attn:                                  # ref :438-440: x_temporal * mean_heads(audio_rescale)
+        w_a = audio_rescale(p_sp, thw).mean(dim=1).reshape(B, -1, 1)
+        x_in = x * w_a
+    x_t = frame_pool(sd, "vision_pool", x_in, thw)
     y_t = frame_pool(sd, "audio_pool2", y, thw_a)
-    av_t, _ = block(sd, "temporal_fusion", torch.cat([x_t, y_t], dim=1), (2, 2, 2))
+    av_t, _, p_tm = block(sd, "temporal_fusion", torch.cat([x_t, y_t], dim=1), (2, 2, 2), want_attn=True)
     # re-weight, ref :454-461
     C = x.shape[2]
     nt = x_t.shape[1]
@@ -394,6 +413,8 @@ def csts_forward(sd, video, audio, return_embed=False, return_intermediates=Fals
         out.append(rnd_b(F.linear(rnd_f(yw.mean(dim=1)), rnd_f(sd["audio_proj.weight"]), sd["audio_proj.bias"])))
     if return_intermediates:
         return out, inter
+    if not return_embed and (return_spatial_attn or return_temporal_attn):               # ref :485-491
+        return [logits] + ([p_sp] if return_spatial_attn else []) + ([p_tm] if return_temporal_attn else [])
     return out if return_embed else logits
 
 

@@ -11,6 +11,9 @@ Fixtures written:
   full_b2.pt          full CSTS fwd + kldiv+egonce + backward at B=2 on synthetic_state(seed 0):
                       logits, embeddings, loss terms, all 524 per-tensor gradient norms and a few
                       small gradients in full.
+  optional_b1.pt      the config-reachable optional paths at B=1 (python oracle/make_golden.py --only-optional):
+                      MVIT.SPATIAL_AUDIO_ATTN=True (logits, loss, gradient norms) and the
+                      return_spatial_attn / return_temporal_attn attention maps of the default model.
 """
 import argparse
 import json
@@ -115,12 +118,47 @@ def full(B=2, seed=0, gain=1.0, tag="full_b2"):
                 grads={n: grads[n].clone() for n in keep}), shapes
 
 
+def optional_paths(B=1, seed=7):
+    """custom_multimodal_builder.py:425-440,448-451,483-491 and av_attention.py:356-370 on the unmodified reference."""
+    rec = dict(B=B, seed=seed)
+    video, audio, hm = O.synthetic_batch(B, seed=seed + 1)
+    # (1) MVIT.SPATIAL_AUDIO_ATTN = True: audio attention re-weights the temporal-fusion input
+    model, cfg = ref_shim.reference_model(seed=0, overrides=["MVIT.SPATIAL_AUDIO_ATTN", True])
+    shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+    sd = O.synthetic_state(shapes, seed=seed, gain=2.0)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    logits, v, a = model([video], audio, return_embed=True)
+    p = torch.softmax(logits.reshape(B, 1, 8, -1) / 2, dim=-1).reshape(logits.shape)
+    from slowfast.models import losses as ref_losses
+    kld = ref_losses.get_loss_func("kldiv")()(p, hm)
+    kld.backward()
+    rec["saa_logits"], rec["saa_v"], rec["saa_kld"] = logits.detach(), v.detach(), kld.detach()
+    rec["saa_grad_norms"] = {n: q.grad.norm().item() for n, q in model.named_parameters() if q.grad is not None}
+    rec["saa_grads"] = {n: model.get_parameter(n).grad.clone() for n in ("spatial_fusion.attn.qkv.bias", "spatial_fusion.norm1.weight",
+                                                                        "vision_pool.bias", "blocks.15.norm2.bias")}
+    # (2) attention maps of the default model (visualisation outputs)
+    model, cfg = ref_shim.reference_model(seed=0)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        out = model([video], audio, return_spatial_attn=True, return_temporal_attn=True)
+    rec["attn_logits"], rec["temporal_attn"] = out[0], out[2]
+    rec["spatial_attn_rows"] = out[1][:, :, ::13, :].clone()          # every 13th query row of (B, 8, 260, 260), all keys
+    rec["spatial_attn_rowsum"] = out[1].sum(-1)
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-full", action="store_true")
+    ap.add_argument("--only-optional", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if args.only_optional:
+        torch.save(optional_paths(), os.path.join(OUT, "optional_b1.pt"))
+        return
     torch.save(unit_blocks(), os.path.join(OUT, "unit_blocks.pt"))
     torch.save(losses(), os.path.join(OUT, "losses.pt"))
     if not args.skip_full:
@@ -131,6 +169,7 @@ def main():
         rec4, _ = full(B=2, seed=5, gain=4.0, tag="full_b2_gain4")
         rec4.pop("grads")
         torch.save(rec4, os.path.join(OUT, "full_b2_gain4.pt"))
+    torch.save(optional_paths(), os.path.join(OUT, "optional_b1.pt"))
 
 
 if __name__ == "__main__":

@@ -348,3 +348,49 @@ def test_graphed_step_with_fused_optimizer_tracks_the_reference_loop(golden_dir,
     assert opt._step.item() == 5.0
     if mode == "fp16":
         assert scaler.get_scale() == ref_scaler.get_scale()
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_optional_paths_against_reference_golden(golden_dir, mode):
+    """MVIT.SPATIAL_AUDIO_ATTN=True (audio attention re-weights the temporal-fusion input; gradients flow back into
+    the spatial-fusion attention) and the return_spatial_attn / return_temporal_attn outputs, against outputs of the
+    unmodified reference (tests/golden/optional_b1.pt; custom_multimodal_builder.py:425-440,448-451,483-491)."""
+    import csts_oracle as O
+    from csts_b200.host.build import build_model
+    rec = torch.load(os.path.join(golden_dir, "optional_b1.pt"), weights_only=False)
+    shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
+    sd = O.synthetic_state(shapes, seed=rec["seed"], gain=2.0)
+    video, audio, hm = (t.to(dev) for t in O.synthetic_batch(rec["B"], seed=rec["seed"] + 1))
+    tol = 1.0 if mode == "bf16" else 0.25
+    cfg = make_cfg(mixed=mode == "fp16")
+    cfg.MVIT.SPATIAL_AUDIO_ATTN = True
+    model = build_model(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    from csts_b200.host import losses
+    from csts_b200.host.utils import frame_softmax
+    logits, v, a = model([video], audio, return_embed=True)
+    ref = rec["saa_logits"].to(dev)
+    d = (logits - ref).abs()
+    assert d.max() <= 0.1 * tol * ref.std() and d.mean() <= 0.03 * tol * ref.std(), (d.max().item(), d.mean().item(), ref.std().item())
+    kld = losses.get_loss_func("kldiv")()(frame_softmax(logits, temperature=2), hm)
+    assert abs(kld.item() - rec["saa_kld"].item()) <= 1e-3 * abs(rec["saa_kld"].item())
+    scale = LOSS_SCALE if mode == "fp16" else 1.0
+    (kld * scale).backward()
+    for n, g in rec["saa_grads"].items():                      # includes tensors reached only through the audio-attention branch
+        got = model.get_parameter(n).grad / scale
+        assert rel_err(got, g.to(dev)) <= 0.15 * tol, (n, rel_err(got, g.to(dev)))
+    # without the flag the network computes something else (the fixture is not vacuous)
+    cfg2 = make_cfg(mixed=mode == "fp16")
+    plain = build_model(cfg2)
+    plain.load_state_dict(sd, strict=True)
+    plain.eval()
+    with torch.no_grad():
+        out = plain([video], audio, return_spatial_attn=True, return_temporal_attn=True)
+        assert (plain([video], audio) - ref).abs().max() > 1e-3
+        only_t = plain([video], audio, return_temporal_attn=True)
+    assert len(out) == 3 and out[1].shape == (1, 8, 260, 260) and out[2].shape == (1, 8, 8, 8) and len(only_t) == 2
+    assert (out[2] - rec["temporal_attn"].to(dev)).abs().max() <= 2e-2 * tol
+    assert (out[1][:, :, ::13, :] - rec["spatial_attn_rows"].to(dev)).abs().max() <= 2e-2 * tol
+    assert (out[1].sum(-1) - 1).abs().max() <= 1e-2
+    assert (only_t[1] - out[2]).abs().max() <= 1e-3       # split-K atomics: not bit-reproducible run to run

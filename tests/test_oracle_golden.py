@@ -90,3 +90,33 @@ def test_oracle_against_live_reference_forward():
         got = O.csts_forward(sd, video, audio, return_embed=True)
     for r, g in zip(ref, got):
         torch.testing.assert_close(g, r, rtol=1e-4, atol=2e-5)
+
+
+def test_optional_paths_against_reference_golden(golden_dir):
+    """MVIT.SPATIAL_AUDIO_ATTN=True and the return_spatial_attn / return_temporal_attn outputs
+    (custom_multimodal_builder.py:425-440,448-451,483-491; av_attention.py:356-370), B=1."""
+    rec = _load(golden_dir, "optional_b1.pt")
+    shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
+    sd = O.synthetic_state(shapes, seed=rec["seed"], gain=2.0)
+    video, audio, hm = O.synthetic_batch(rec["B"], seed=rec["seed"] + 1)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits, v, a = O.csts_forward(leaves, video, audio, return_embed=True, spatial_audio_attn=True)
+    assert (logits - rec["saa_logits"]).abs().max() < 2e-4
+    assert (v - rec["saa_v"]).abs().max() < 2e-4
+    kld = O.kldiv(O.frame_softmax(logits, 2.0), hm)
+    assert abs(kld.item() - rec["saa_kld"].item()) < 1e-5 * abs(rec["saa_kld"].item())
+    kld.backward()
+    for n, g in rec["saa_grads"].items():
+        assert ((leaves[n].grad - g).norm() / g.norm()).item() < 2e-3, n
+    worst = max(abs(leaves[n].grad.norm().item() - gn) / gn for n, gn in rec["saa_grad_norms"].items() if gn > 1e-6)
+    assert worst < 5e-3, worst
+    # the flag changes the result (the fixture is not vacuous)
+    assert (O.csts_forward(sd, video, audio) - rec["saa_logits"]).abs().max() > 1e-3
+    with torch.no_grad():
+        out = O.csts_forward(sd, video, audio, return_spatial_attn=True, return_temporal_attn=True)
+    assert len(out) == 3 and out[1].shape == (1, 8, 260, 260) and out[2].shape == (1, 8, 8, 8)
+    assert (out[0] - rec["attn_logits"]).abs().max() < 2e-4
+    assert (out[2] - rec["temporal_attn"]).abs().max() < 1e-5
+    assert (out[1][:, :, ::13, :] - rec["spatial_attn_rows"]).abs().max() < 1e-5
+    assert (out[1].sum(-1) - rec["spatial_attn_rowsum"]).abs().max() < 1e-5
+    assert len(O.csts_forward(sd, video, audio, return_temporal_attn=True)) == 2
