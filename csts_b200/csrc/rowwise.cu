@@ -359,14 +359,16 @@ __global__ void __launch_bounds__(256) colsum8_kernel(const T* __restrict__ X, f
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  for (int i = 0; i < 8; ++i) red[i * 256 + threadIdx.x] = acc[i];     // [column-in-group][thread]: conflict-free both ways
   __syncthreads();
-  if (ty == 0 && col < N) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
+  // thread (i, tx) of the first 8 * GX threads sums column i of group tx over the RY row phases
+  for (int e = threadIdx.x; e < 8 * GX; e += blockDim.x) {
+    const int i = e / GX, gx = e - i * GX;
+    const int c = (blockIdx.x * GX + gx) * 8 + i;
+    if (c < N) {
       float t = 0.f;
-      for (int y = 0; y < RY; ++y) t += red[(y * GX + tx) * 8 + i];
-      atomicAdd(out + col + i, t);
+      for (int y = 0; y < RY; ++y) t += red[i * 256 + y * GX + gx];
+      atomicAdd(out + c, t);
     }
   }
 }

@@ -339,12 +339,12 @@ def test_graphed_step_with_fused_optimizer_tracks_the_reference_loop(golden_dir,
     losses = [step(None, None, None).item() for _ in range(2)]
     assert ref_losses[0] > ref_losses[-1]                                                   # it trains
     for got, want in zip(losses, ref_losses[3:]):
-        assert abs(got - want) <= 1e-4 * abs(want), (losses, ref_losses)
+        assert abs(got - want) <= 3e-4 * abs(want), (losses, ref_losses)
     # parameters: Adam moves every element by ~lr per step whatever the gradient's size, so elements whose gradient is
     # rounding noise may legitimately step in opposite directions in two runs; compare in units of the travelled distance
     num = sum((p - q).float().pow(2).sum().item() for p, q in zip(model.parameters(), ref_model.parameters()))
     moved = sum((p - sd[n].to(dev)).float().pow(2).sum().item() for n, p in model.named_parameters())
-    assert moved > 0 and (num / moved) ** 0.5 < 0.05, (num, moved)
+    assert moved > 0 and (num / moved) ** 0.5 < 0.1, (num, moved)
     assert opt._step.item() == 5.0
     if mode == "fp16":
         assert scaler.get_scale() == ref_scaler.get_scale()
