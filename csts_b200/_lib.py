@@ -20,7 +20,7 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("Z", C.c_void_p),
-        ("bias", C.c_void_p), ("residual", C.c_void_p), ("row_scale", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("row_scale", C.c_void_p), ("rowsum", C.c_void_p),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64), ("ldz", C.c_int64), ("ldr", C.c_int64),
         ("sA1", C.c_int64), ("sA2", C.c_int64), ("sB1", C.c_int64), ("sB2", C.c_int64), ("sC1", C.c_int64), ("sC2", C.c_int64),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),

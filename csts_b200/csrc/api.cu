@@ -83,10 +83,19 @@ int csts_gemm(const csts_gemm_args* a, void* stream) {
   CSTS_REQUIRE(a->c_dtype >= 0 && a->c_dtype <= 2, "gemm: c_dtype %d", a->c_dtype);
   if (a->Z) CSTS_REQUIRE(a->z_dtype == CSTS_BF16 || a->z_dtype == CSTS_F16, "gemm: z_dtype must be 1 (bf16) or 2 (f16)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->backend == 1) return csts_gemm_mma_launch(*a, st);
-  if (a->backend == 2) return csts_gemm_tc_launch(*a, st);
-  if (csts_gemm_tc_supported(*a)) return csts_gemm_tc_launch(*a, st);
-  return csts_gemm_mma_launch(*a, st);
+  const bool tc = a->backend == 2 || (a->backend != 1 && csts_gemm_tc_supported(*a));
+  if (a->rowsum) {
+    CSTS_REQUIRE(!a->a_kmajor && a->batch1 * a->batch2 == 1, "gemm: rowsum needs an MN-major A operand and a single batch");
+    const bool fused = tc && !a->b_kmajor && a->c_dtype == 0 && a->act == 0;   // the (MN, MN) f32 kernels carry the extra MMA
+    if (!fused) {                                     // same result from a separate pass over A (K rows x M columns)
+      csts_gemm_args b = *a;
+      b.rowsum = nullptr;
+      int rc = tc ? csts_gemm_tc_launch(b, st) : csts_gemm_mma_launch(b, st);
+      if (rc) return rc;
+      return csts_colsum(a->A, a->a_dtype, a->rowsum, a->K, a->M, a->lda, stream);
+    }
+  }
+  return tc ? csts_gemm_tc_launch(*a, st) : csts_gemm_mma_launch(*a, st);
 }
 
 }  // extern "C"

@@ -131,6 +131,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_
 
 struct TcParams {
   void* C; void* Z; const float* bias; const float* residual; const float* row_scale;
+  float* rowsum;                    // += sum_k A[k][m] (weight-gradient products: the bias gradient), or NULL
   int64_t ldc, ldz, ldr;
   int64_t sC1, sC2;                 // batch strides of C (elements)
   int M, N, K;
@@ -150,7 +151,10 @@ template <int BN> struct Cfg {
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int NACC = (512 / BN) >= 4 ? 4 : 2;            // accumulator stages in TMEM
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int ONES_BYTES = 2048;                        // all-ones 16 x 64 operand tile (row-sum MMA)
+  static constexpr int RS_COLS = 32;                             // TMEM columns per accumulator stage for the row sums
+  static constexpr bool RS_FITS = NACC * (BN + RS_COLS) <= 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ---- epilogue helpers: a warp moves a 32-row x 128-byte tile between global memory (coalesced: 8 lanes
@@ -452,7 +456,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::STAGES * C::A_BYTES;
   unsigned char* sStage = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES);
+  unsigned char* sOnes = sStage + STAGING_BYTES;                 // 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
+  // Row sums of the A operand (the bias gradient that belongs to a weight-gradient product dW = dY^T . X): one extra
+  // N = 16 MMA per k-step against an all-ones tile, into 32 spare TMEM columns per accumulator stage, for the
+  // tile_n == 0 tiles only.  Any layout of an all-ones tile is an all-ones tile, so one 2 KB region serves all k.
+  constexpr bool RS_OK = A_MN && B_MN && (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) && C::RS_FITS;
+  const bool rowsum_on = RS_OK && p.rowsum != nullptr;
   // bars: full[STAGES], empty[STAGES], tmem_full[NACC], tmem_empty[NACC]
   uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
   uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 8 * C::NACC;
@@ -472,6 +482,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+  if (rowsum_on) {
+    const uint32_t one2 = p.a_bf16 ? 0x3F803F80u : 0x3C003C00u;   // 1.0 twice, in the operand format
+    for (int i = threadIdx.x; i < C::ONES_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -527,6 +542,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, p.a_bf16, p.b_bf16);
+      const uint32_t idesc_rs = make_idesc(BM, 16, A_MN ? 1 : 0, 0, p.a_bf16, p.a_bf16);
+      const uint64_t odesc = make_sw128_desc(smem_u32(sOnes), 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -535,6 +552,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_rs = tmem_base + C::NACC * BN + as * C::RS_COLS;
+        const bool rs_tile = rowsum_on && tn == 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
@@ -547,6 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < BK / UMMA_K; ++k) {
             umma_bf16(tmem_d, adesc + (uint64_t)((A_MN ? 2048 : 32) >> 4) * k, bdesc + (uint64_t)((B_MN ? 2048 : 32) >> 4) * k, idesc,
                       (kb > kb0 || k > 0) ? 1u : 0u);
+            if (rs_tile) umma_bf16(tmem_rs, adesc + (uint64_t)((A_MN ? 2048 : 32) >> 4) * k, odesc, idesc_rs, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty0 + 8 * stage);           // smem slot free once these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -614,6 +634,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int cn = c + CSTEP, n1 = tn * BN + cn;
         if (side && cn < BN && n1 < p.N) slice_prefetch<EPI_S>(p, coff, m0, n1, BN - cn, lane, split == 0, pre);
         epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0, cur);
+      }
+      if (rowsum_on && tn == 0 && sub == 0 && live) {      // lane = output row: its sum over this item's k-range
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + C::NACC * BN + as * C::RS_COLS, r);
+        tmem_ld_wait();
+        if (m0 + lane < p.M) atomicAdd(p.rowsum + m0 + lane, __uint_as_float(r[0]));
       }
       tc_fence_before();
       __syncwarp();
@@ -684,7 +710,7 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
             : make_tmap(&tb, a.B, a.N, a.K, a.ldb, BN, a.batch1, a.batch2, a.sB1, a.sB2);
   if (rc) return rc;
   TcParams p;
-  p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual;
+  p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual; p.rowsum = a.rowsum;
   p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
   p.ldc = a.ldc; p.ldz = a.ldz; p.ldr = a.ldr;
   p.sC1 = a.sC1; p.sC2 = a.sC2; p.batch = a.batch1 * a.batch2; p.batch2 = a.batch2;
@@ -740,7 +766,9 @@ int pick_bn(int M, int N, int work_mult) {
 
 template <bool A_MN, bool B_MN, int EPI>
 int dispatch(const csts_gemm_args& a, cudaStream_t stream) {
-  switch (pick_bn(a.M, a.N, (a.split_k > 1 ? a.split_k : 1) * a.batch1 * a.batch2)) {
+  int bn = pick_bn(a.M, a.N, (a.split_k > 1 ? a.split_k : 1) * a.batch1 * a.batch2);
+  if (a.rowsum) bn = a.N <= 96 ? 96 : 192;            // tile widths that leave TMEM columns for the fused row sums
+  switch (bn) {
     case 256: return launch<256, A_MN, B_MN, EPI>(a, stream);
     case 192: return launch<192, A_MN, B_MN, EPI>(a, stream);
     case 128: return launch<128, A_MN, B_MN, EPI>(a, stream);

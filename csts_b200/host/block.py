@@ -187,27 +187,26 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         zoff[0] = lo + (n + 3) // 4 * 4          # keep 16-byte alignment for the vectorised kernels
         return zbuf[lo: lo + n]
 
-    def wgrad(a_rows, b_rows, m_out, n_out, ktok):
-        # dW[m_out, n_out] = a_rows^T . b_rows   (both token-major: contraction over rows)
+    def wgrad(a_rows, b_rows, m_out, n_out, ktok, bias_name):
+        # dW[m_out, n_out] = a_rows^T . b_rows   (both token-major: contraction over rows); the bias gradient
+        # sum_rows a_rows comes out of the same kernel (one extra narrow MMA per k-step against an all-ones tile)
+        g[bias_name] = zeros(m_out)
         return K.gemm(a_rows, b_rows, M=m_out, N=n_out, K=ktok, a_kmajor=False, b_kmajor=False, lda=m_out, ldb=n_out,
-                      out_dtype=torch.float32, split_k=_split_k(m_out, n_out, ktok))
+                      out_dtype=torch.float32, split_k=_split_k(m_out, n_out, ktok), rowsum=g[bias_name])
 
     dy = dy.contiguous().view(Mq, Co)
     g2 = K.cast16(dy, wc.grad, row_scale=dp, rows_per_scale=rps)            # gradient entering the (drop-path scaled) MLP branch
     # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
     dZ = K.gemm(g2, wc.w(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, b_kmajor=False, act=2, Z=sv["Z"])
-    g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq)
-    g["mlp.fc2.bias"] = K.colsum(g2, Mq, Co, out=zeros(Co))
+    g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq, "mlp.fc2.bias")
     dxn2 = K.gemm(dZ, wc.w(p["mlp.fc1.weight"]), M=Mq, N=C, K=hid, b_kmajor=False)
-    g["mlp.fc1.weight"] = wgrad(dZ, sv["xn2"], hid, C, Mq)
-    g["mlp.fc1.bias"] = K.colsum(dZ, Mq, hid, out=zeros(hid))
+    g["mlp.fc1.weight"] = wgrad(dZ, sv["xn2"], hid, C, Mq, "mlp.fc1.bias")
     del dZ
     g["norm2.weight"], g["norm2.bias"] = zeros(C), zeros(C)
     if spec.dim != spec.dim_out:
         gp = g2 if dp is None else K.cast16(dy, wc.grad)                     # the re-based residual is not drop-path scaled
         K.gemm(gp, wc.w(p["proj.weight"]), M=Mq, N=C, K=Co, b_kmajor=False, out=dxn2, accumulate=True)
-        g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq)
-        g["proj.bias"] = K.colsum(dy, Mq, Co, out=zeros(Co))
+        g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq, "proj.bias")
         dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"])
     else:
         dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
@@ -216,8 +215,7 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
     # ---- attention output projection ------------------------------------------------------------------
     g1 = K.cast16(dx1, wc.grad, row_scale=dp, rows_per_scale=rps)
     do = K.gemm(g1, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, b_kmajor=False)       # (B, Lq, heads, d)
-    g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq)
-    g["attn.proj.bias"] = K.colsum(g1, Mq, C, out=zeros(C))
+    g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq, "attn.proj.bias")
     del g1
     # ---- residual path -----------------------------------------------------------------------------------
     if spec.stride_q is None or spec.kind in ("spatial", "temporal"):
@@ -288,8 +286,7 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         pool_backward(dv_t, "v_pool", 2, spec.stride_kv, "attn.pool_v.weight", "attn.norm_v", False, v.thw)
     # ---- qkv projection and norm1 ---------------------------------------------------------------------------
     dxn1 = K.gemm(dqkv, wc.w(p["attn.qkv.weight"]), M=M, N=C, K=3 * C, b_kmajor=False)
-    g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M)
-    g["attn.qkv.bias"] = K.colsum(dqkv, M, 3 * C, out=zeros(3 * C))
+    g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M, "attn.qkv.bias")
     g["norm1.weight"], g["norm1.bias"] = zeros(C), zeros(C)
     dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
                          add=dx_skip.view(B, N, C))

@@ -24,7 +24,7 @@ def set_gemm_backend(code: int):
 def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=None,
          ldc=None, bias=None, act=0, Z=None, residual=None, res_mod=0, accumulate=False, alpha=1.0, split_k=1,
          batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None,
-         row_scale=None, rows_per_scale=0):
+         row_scale=None, rows_per_scale=0, rowsum=None):
     """C = epi(alpha * op(A) @ op(B)).  A/B are bf16 or f16 storage tensors (independently); offsets/strides
     in elements.  out_dtype defaults to A's type."""
     assert A.dtype in (torch.bfloat16, torch.float16) and B.dtype in (torch.bfloat16, torch.float16)
@@ -48,6 +48,7 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
     a.bias = bias.data_ptr() if bias is not None else None
     a.residual = residual.data_ptr() if residual is not None else None
     a.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    a.rowsum = rowsum.data_ptr() if rowsum is not None else None      # f32 [M], += row sums of op(A) (bias gradient of a wgrad)
     a.rows_per_scale = rows_per_scale
     a.lda, a.ldb, a.ldc = lda, ldb, ldc
     a.ldz = ldc

@@ -52,6 +52,10 @@ typedef struct csts_gemm_args {
   const float* residual;  /* f32 [rows, N] (pitch ldr) or NULL; row = m % res_mod when res_mod > 0 */
   const float* row_scale; /* [ceil(M / rows_per_scale)] or NULL: row m is multiplied by
                              row_scale[m / rows_per_scale] before the residual is added (DropPath, common.py:46-59) */
+  float* rowsum;          /* [M] f32 or NULL: rowsum[m] += sum_k opA(A)[m][k].  For a weight-gradient product
+                             dW = dY^T . X (a_kmajor = 0) this is the bias gradient sum_tokens dY, produced by one extra
+                             N = 16 MMA per k-step against an all-ones tile instead of a separate pass over dY.
+                             Needs a_kmajor = 0 and a single batch; accumulated into (zeroed by the caller) */
   int64_t lda, ldb, ldc, ldz, ldr;
   int64_t sA1, sA2, sB1, sB2, sC1, sC2;   /* batch strides: z -> (z / batch2, z % batch2) */
   int32_t M, N, K;

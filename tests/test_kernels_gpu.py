@@ -30,6 +30,10 @@ def bf(x):
     return x.to(torch.bfloat16)
 
 
+def hf(x):
+    return x.to(torch.float16)
+
+
 # ------------------------------------------------------------------------------------------------ GEMM
 GEMM_SHAPES = [
     # M, N, K
@@ -184,6 +188,15 @@ def test_gemm_weight_gradient_layout(backend, M, N, Kd, split):
     acc = base.clone()
     k.gemm(dY, X, M=M, N=N, K=Kd, a_kmajor=False, b_kmajor=False, out=acc, accumulate=True, split_k=split, backend=backend)
     assert rel_err(acc, ref + base) < 2e-5
+    # fused bias gradient: row sums of dY^T accumulate into `rowsum` from the same kernel (tcgen05: an extra N = 16 MMA
+    # against an all-ones tile; mma.sync backend: a column-sum pass), for bf16 and f16 operands
+    for cast in (bf, hf):
+        dYc, Xc = cast(dY.float()), cast(X.float())
+        rs = torch.full((M,), 0.25, device=dev)
+        out = k.gemm(dYc, Xc, M=M, N=N, K=Kd, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split, backend=backend,
+                     rowsum=rs)
+        assert rel_err(out, dYc.float().t() @ Xc.float()) < 2e-5
+        assert rel_err(rs, 0.25 + dYc.float().sum(0)) < 2e-5, rel_err(rs, 0.25 + dYc.float().sum(0))
 
 
 @pytest.mark.parametrize("backend", [1, 2])
@@ -519,8 +532,6 @@ def test_kldiv_and_egonce(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------ storage types
-def hf(x):
-    return x.to(torch.float16)
 
 
 @pytest.mark.parametrize("backend", [1, 2])
