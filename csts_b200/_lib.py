@@ -67,7 +67,7 @@ SIGNATURES = {
     "csts_check_device": [],
     "csts_gemm": [C.POINTER(GemmArgs), _P],
     "csts_layernorm_fwd": [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _F, _P],
-    "csts_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P],
+    "csts_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P, _I, _P, _I, _P],
     "csts_softmax_fwd": [_P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "csts_softmax_bwd": [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P],
     "csts_cast16": [_P, _P, _I, _L, _I, _I, _P, _I, _P],

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ add,
                                                             TDX* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows, int width) {
+                                                            float* __restrict__ dbeta, int rows, int width, void* __restrict__ dx16,
+                                                            int dx16_half, const float* __restrict__ row_scale, int rows_per_scale) {
   pdl_wait();
   __shared__ float s_dg[768], s_db[768];
   for (int i = threadIdx.x; i < width; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
@@ -144,6 +145,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = rs[u] * (gd[j][i] - s1 - xh[j][i] * s2) + av[u][j][i];
           st4(dxr + c, o);
+          if (dx16) {                                  // 16-bit (row-scaled) copy: the operand of the next backward GEMM
+            const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] *= sc;
+            if (dx16_half) st4(reinterpret_cast<f16*>(dx16) + (int64_t)row * width + c, o);
+            else st4(reinterpret_cast<bf16*>(dx16) + (int64_t)row * width + c, o);
+          }
         }
       }
     }
@@ -412,14 +420,17 @@ int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const f
 
 int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                        const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
-                       int width, void* stream) {
+                       int width, void* dx16, int dx16_dtype, const float* row_scale, int rows_per_scale, void* stream) {
   CSTS_REQUIRE(width % 4 == 0 && width <= LN_MAX_WIDTH, "layernorm_bwd: width %d unsupported", width);
+  if (dx16) CSTS_REQUIRE(dx16_dtype == CSTS_BF16 || dx16_dtype == CSTS_F16, "layernorm_bwd: dx16 must be bf16 or f16");
+  if (dx16 && row_scale) CSTS_REQUIRE(rows_per_scale > 0, "layernorm_bwd: rows_per_scale must be positive");
+  const int dx16_half = dx16_dtype == CSTS_F16;
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int64_t blocks = (rows + 31) / 32;       // >= 4 rows per warp so the column atomics amortise
   int grid = (int)(blocks < csts_num_sms() * 8 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 8);
 #define LN_BWD_J(TX, TDY, TDX, J) \
-  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, J>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width)
+  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, J>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width, dx16, dx16_half, row_scale, rows_per_scale)
 #define LN_BWD(TX, TDY, TDX)                             \
   do {                                                   \
     if (width <= 128) LN_BWD_J(TX, TDY, TDX, 1);         \

@@ -207,13 +207,13 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         gp = g2 if dp is None else K.cast16(dy, wc.grad)                     # the re-based residual is not drop-path scaled
         K.gemm(gp, wc.w(p["proj.weight"]), M=Mq, N=C, K=Co, b_kmajor=False, out=dxn2, accumulate=True)
         g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq, "proj.bias")
-        dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"])
+        dx1, g1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
+                                  copy16=wc.grad, row_scale=dp, rows_per_scale=rps)
     else:
-        dx1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
-                              add=dy)
+        dx1, g1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
+                                  add=dy, copy16=wc.grad, row_scale=dp, rows_per_scale=rps)
     del dxn2, g2
-    # ---- attention output projection ------------------------------------------------------------------
-    g1 = K.cast16(dx1, wc.grad, row_scale=dp, rows_per_scale=rps)
+    # ---- attention output projection (g1 = drop-path scaled 16-bit copy of dx1, written by the LayerNorm backward) ------
     do = K.gemm(g1, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, b_kmajor=False)       # (B, Lq, heads, d)
     g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq, "attn.proj.bias")
     del g1

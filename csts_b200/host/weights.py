@@ -67,13 +67,6 @@ class WeightCache:
         """Conv weight (N, ...) f32 -> 16-bit (N, kp), zero padded columns (patch embed)."""
         return self._get(param, ("pad", kp), lambda p: K.cast16(p.reshape(p.shape[0], -1), self.act, ld_out=kp))
 
-    def frame_pool_w(self, param):
-        """Conv3d(C, C, (1,8,8)) weight (O, C, 1, 8, 8) -> 16-bit (O, 64*C) with columns ordered
-        (hw, c) to match the token-major activation layout."""
-        o, c = param.shape[0], param.shape[1]
-        hw = param.shape[3] * param.shape[4]
-        return self._get(param, "fpw", lambda p: K.permute_021(p.reshape(o, c, hw), o, c, hw, self.act).reshape(o, hw * c))
-
     # ---- fused optimizer step (host/optimizer.py): the AdamW kernel writes the 16-bit copy itself -----------
     def bound_copy(self, param):
         """The live plain (N, K) copy of `param` (same element order as the parameter), or None."""

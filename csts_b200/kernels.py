@@ -96,14 +96,17 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype=torch.bfloat16, want_stats=True
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, add=None, dx_dtype=torch.float32):
-    """dgamma/dbeta (f32, zero-initialised by the caller) are accumulated into."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, add=None, dx_dtype=torch.float32, copy16=None, row_scale=None,
+                  rows_per_scale=0):
+    """dgamma/dbeta (f32, zero-initialised by the caller) are accumulated into.  copy16 (a 16-bit dtype): also
+    return a 16-bit copy of dx whose row m is scaled by row_scale[m // rows_per_scale] (written in the same pass)."""
     width = x.shape[-1]
     rows = x.numel() // width
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    dx16 = torch.empty(x.shape, dtype=copy16, device=x.device) if copy16 is not None else None
     call("csts_layernorm_bwd", ptr(dy), dt(dy), ptr(x), dt(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(add), ptr(dx), dt(dx),
-         ptr(dgamma), ptr(dbeta), rows, width)
-    return dx
+         ptr(dgamma), ptr(dbeta), rows, width, ptr(dx16), dt(dx16) if dx16 is not None else 0, ptr(row_scale), rows_per_scale)
+    return dx if copy16 is None else (dx, dx16)
 
 
 def softmax_fwd(S, n, ldp, nq, mask_hw=0, mask_t=0, dtype=torch.bfloat16):

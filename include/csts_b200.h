@@ -81,10 +81,12 @@ int csts_gemm_backend(const csts_gemm_args* a);  /* 2 = tcgen05, 1 = mma.sync fo
 /* ---- LayerNorm: nn.LayerNorm (attention.py:239,243 norm1/norm2 eps 1e-6; :42-43 norm_q/k/v eps 1e-5) --- */
 int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,
                        float* rstd, int64_t rows, int width, float eps, void* stream);
-/* dx = [add +] LN'(dy); dgamma/dbeta (f32, zeroed by the caller) are accumulated into */
+/* dx = [add +] LN'(dy); dgamma/dbeta (f32, zeroed by the caller) are accumulated into.  dx16 (optional): a second,
+ * 16-bit copy of dx with row m multiplied by row_scale[m / rows_per_scale] (the DropPath-scaled operand of the next
+ * backward GEMM), written in the same pass */
 int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                        const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
-                       int width, void* stream);
+                       int width, void* dx16, int dx16_dtype, const float* row_scale, int rows_per_scale, void* stream);
 
 /* ---- attention softmax: attn.softmax(dim=-1) (attention.py:155), with the in-frame mask of
  * SpatialAttention (av_attention.py:336-348) when mask_hw > 0.  P is bf16 / f16 (p_dtype), pad columns

