@@ -43,6 +43,8 @@ class PoolArgs(C.Structure):
         ("To", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("transposed", C.c_int32), ("eps", C.c_float), ("dtype", C.c_int32),
+        ("in2", C.c_void_p), ("out2", C.c_void_p), ("w2", C.c_void_p), ("gamma2", C.c_void_p), ("beta2", C.c_void_p),
+        ("pre2", C.c_void_p), ("mean2", C.c_void_p), ("rstd2", C.c_void_p),
     ]
 
 
@@ -56,6 +58,7 @@ class WgradArgs(C.Structure):
         ("Tb", C.c_int32), ("Hb", C.c_int32), ("Wb", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("small_dtype", C.c_int32), ("big_dtype", C.c_int32),
+        ("small2", C.c_void_p), ("big2", C.c_void_p), ("dw2", C.c_void_p),
     ]
 
 

@@ -37,6 +37,9 @@ __device__ __forceinline__ void tap_coords(int o, int shift, int n_in, int (&idx
 template <int D, bool TRANSPOSED, bool NORM, typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, int lh, int lw) {
   pdl_wait();
+  if (blockIdx.y == 1) {                           // second problem of the launch (same geometry, other tensors)
+    p.in = p.in2; p.out = p.out2; p.w = p.w2; p.gamma = p.gamma2; p.beta = p.beta2; p.pre = p.pre2; p.mean = p.mean2; p.rstd = p.rstd2;
+  }
   constexpr int NJ = (D + 127) / 128;
   __shared__ float s_w[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
@@ -203,6 +206,9 @@ __global__ void __launch_bounds__(256) dwconv_kernel(csts_pool_args p, int lt, i
 template <int D, bool TRANSPOSED, bool NORM, typename T, int TI, int TO, int ST>
 __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int lh, int lw) {
   pdl_wait();
+  if (blockIdx.y == 1) {                           // second problem of the launch (same geometry, other tensors)
+    p.in = p.in2; p.out = p.out2; p.w = p.w2; p.gamma = p.gamma2; p.beta = p.beta2; p.pre = p.pre2; p.mean = p.mean2; p.rstd = p.rstd2;
+  }
   constexpr int NJ = (D + 127) / 128;
   __shared__ float s_w[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
@@ -341,6 +347,7 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
 template <int D, int SW, typename TS, typename TB>
 __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, int lt, int lh, int lw, int rows_per_block) {
   pdl_wait();
+  if (blockIdx.y == 1) { p.small = p.small2; p.big = p.big2; p.dw = p.dw2; }   // second problem of the launch
   constexpr int NJ = (D + 127) / 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kt = warp / 3, kh = warp % 3;
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
 template <typename TS, typename TB, int TSM, int TBG, int ST>
 __global__ void __launch_bounds__(192) dwconv_wgrad_tcol_kernel(csts_wgrad_args p, int lh, int lw, int cols_per_slot) {
   pdl_wait();
+  if (blockIdx.y == 1) { p.small = p.small2; p.big = p.big2; p.dw = p.dw2; }   // second problem of the launch
   constexpr int D = 96;
   __shared__ float s_dw[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) s_dw[i] = 0.f;
@@ -716,6 +724,7 @@ int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   int64_t total = (int64_t)p.B * p.heads * p.To * p.Ho * p.Wo;
   int grid = grid_for(total, 8);
   bool norm = p.gamma != nullptr;
+  const int ny = p.in2 ? 2 : 1;
   int lt = log2_exact(p.st), lh = log2_exact(p.sh), lw = log2_exact(p.sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv: strides must be powers of two (%d,%d,%d)", p.st, p.sh, p.sw);
   static const bool no_tcol = getenv("CSTS_NO_TCOL") != nullptr;       // A/B tuning runs only
@@ -724,30 +733,30 @@ int launch_dwconv(const csts_pool_args& p, cudaStream_t st) {
   const int cgrid = grid_for(cols, 8);
   if (p.st == 1 && p.Ti == 4 && p.To == 4 && !no_tcol) {
     if (p.transposed) {
-      if (norm) launch_pdl(dwconv_tcol_kernel<D, true, true, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
-      else launch_pdl(dwconv_tcol_kernel<D, true, false, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      if (norm) launch_pdl(dwconv_tcol_kernel<D, true, true, T, 4, 4, 1>, dim3(cgrid, ny), dim3(256), 0, st, p, lh, lw);
+      else launch_pdl(dwconv_tcol_kernel<D, true, false, T, 4, 4, 1>, dim3(cgrid, ny), dim3(256), 0, st, p, lh, lw);
     } else {
-      if (norm) launch_pdl(dwconv_tcol_kernel<D, false, true, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
-      else launch_pdl(dwconv_tcol_kernel<D, false, false, T, 4, 4, 1>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      if (norm) launch_pdl(dwconv_tcol_kernel<D, false, true, T, 4, 4, 1>, dim3(cgrid, ny), dim3(256), 0, st, p, lh, lw);
+      else launch_pdl(dwconv_tcol_kernel<D, false, false, T, 4, 4, 1>, dim3(cgrid, ny), dim3(256), 0, st, p, lh, lw);
     }
     return csts_check_launch("dwconv_tcol");
   }
   if (D == 96 && p.st == 2 && !no_tcol) {                               // the decoder's temporal up-sampling conv and its adjoint
     if (p.transposed && norm && p.Ti == 4 && p.To == 8) {
-      launch_pdl(dwconv_tcol_kernel<96, true, true, T, 4, 8, 2>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      launch_pdl(dwconv_tcol_kernel<96, true, true, T, 4, 8, 2>, dim3(cgrid, ny), dim3(256), 0, st, p, lh, lw);
       return csts_check_launch("dwconv_tcol");
     }
     if (!p.transposed && !norm && p.Ti == 8 && p.To == 4) {
-      launch_pdl(dwconv_tcol_kernel<96, false, false, T, 8, 4, 2>, dim3(cgrid), dim3(256), 0, st, p, lh, lw);
+      launch_pdl(dwconv_tcol_kernel<96, false, false, T, 8, 4, 2>, dim3(cgrid, ny), dim3(256), 0, st, p, lh, lw);
       return csts_check_launch("dwconv_tcol");
     }
   }
   if (p.transposed) {
-    if (norm) launch_pdl(dwconv_kernel<D, true, true, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
-    else launch_pdl(dwconv_kernel<D, true, false, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    if (norm) launch_pdl(dwconv_kernel<D, true, true, T>, dim3(grid, ny), dim3(256), 0, st, p, lt, lh, lw);
+    else launch_pdl(dwconv_kernel<D, true, false, T>, dim3(grid, ny), dim3(256), 0, st, p, lt, lh, lw);
   } else {
-    if (norm) launch_pdl(dwconv_kernel<D, false, true, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
-    else launch_pdl(dwconv_kernel<D, false, false, T>, dim3(grid), dim3(256), 0, st, p, lt, lh, lw);
+    if (norm) launch_pdl(dwconv_kernel<D, false, true, T>, dim3(grid, ny), dim3(256), 0, st, p, lt, lh, lw);
+    else launch_pdl(dwconv_kernel<D, false, false, T>, dim3(grid, ny), dim3(256), 0, st, p, lt, lh, lw);
   }
   return csts_check_launch("dwconv");
 }
@@ -762,6 +771,10 @@ int csts_dwconv(const csts_pool_args* p, void* stream) {
                    p->out_sP % 4 == 0, "dwconv: strides must be multiples of 4 elements");
   CSTS_REQUIRE(((uintptr_t)p->in & 7) == 0 && ((uintptr_t)p->out & 7) == 0, "dwconv: in/out must be 8-byte aligned");
   if (p->gamma) CSTS_REQUIRE(p->beta && p->pre && p->mean && p->rstd, "dwconv: norm epilogue needs beta/pre/mean/rstd");
+  if (p->in2) {
+    CSTS_REQUIRE(p->out2 && p->w2 && ((uintptr_t)p->in2 & 7) == 0 && ((uintptr_t)p->out2 & 7) == 0, "dwconv: second problem needs in2/out2/w2 (8-byte aligned)");
+    if (p->gamma) CSTS_REQUIRE(p->gamma2 && p->beta2 && p->pre2 && p->mean2 && p->rstd2, "dwconv: second problem needs its own norm tensors");
+  }
   if ((int64_t)p->B * p->heads * p->To * p->Ho * p->Wo == 0) return 0;
   CSTS_REQUIRE((int64_t)p->Ti * p->Hi * p->Wi * p->in_sP < (1LL << 31), "dwconv: one (batch, head) slab must stay below 2^31 elements");
   CSTS_REQUIRE(p->dtype == CSTS_BF16 || p->dtype == CSTS_F16, "dwconv: dtype must be 1 (bf16) or 2 (f16)");
@@ -774,6 +787,7 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   CSTS_REQUIRE(p->d == 96 || p->d == 192, "dwconv_wgrad: head_dim %d unsupported", p->d);
   int64_t total = (int64_t)p->B * p->heads * p->Ts * p->Hs * p->Ws;
   if (total == 0) return 0;
+  if (p->small2) CSTS_REQUIRE(p->big2 && p->dw2, "dwconv_wgrad: second problem needs small2/big2/dw2");
   int lt = log2_exact(p->st), lh = log2_exact(p->sh), lw = log2_exact(p->sw);
   CSTS_REQUIRE(lt >= 0 && lh >= 0 && lw >= 0, "dwconv_wgrad: strides must be powers of two");
   CSTS_REQUIRE((p->small_dtype == CSTS_BF16 || p->small_dtype == CSTS_F16) && (p->big_dtype == CSTS_BF16 || p->big_dtype == CSTS_F16),
@@ -790,8 +804,8 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
     int cgrid = (int)((cols + (int64_t)cols_per_warp * 2 - 1) / ((int64_t)cols_per_warp * 2));
 #define WGRAD_TCOL(TS_, TB_)                                                                                          \
   do {                                                                                                                \
-    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid), dim3(192), 0, st, *p, lh, lw, cols_per_warp); \
-    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid), dim3(192), 0, st, *p, lh, lw, cols_per_warp);            \
+    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid, p->small2 ? 2 : 1), dim3(192), 0, st, *p, lh, lw, cols_per_warp); \
+    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid, p->small2 ? 2 : 1), dim3(192), 0, st, *p, lh, lw, cols_per_warp);            \
   } while (0)
     if (p->small_dtype == CSTS_F16) WGRAD_TCOL(f16, f16);
     else WGRAD_TCOL(bf16, bf16);
@@ -803,7 +817,7 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
   int grid = (int)(rows_total < csts_num_sms() * 4 ? rows_total : csts_num_sms() * 4);
   int rows_per_block = (int)((rows_total + grid - 1) / grid);
   grid = (int)((rows_total + rows_per_block - 1) / rows_per_block);
-#define WGRAD_T(D_, SW_, TS_, TB_) launch_pdl(dwconv_wgrad_kernel<D_, SW_, TS_, TB_>, dim3(grid), dim3(288), 0, st, *p, lt, lh, lw, rows_per_block)
+#define WGRAD_T(D_, SW_, TS_, TB_) launch_pdl(dwconv_wgrad_kernel<D_, SW_, TS_, TB_>, dim3(grid, p->small2 ? 2 : 1), dim3(288), 0, st, *p, lt, lh, lw, rows_per_block)
 #define WGRAD(D_, SW_)                                                                        \
   do {                                                                                        \
     if (p->small_dtype == CSTS_BF16 && p->big_dtype == CSTS_F16) WGRAD_T(D_, SW_, bf16, f16); \

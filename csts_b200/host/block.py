@@ -86,10 +86,10 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
         thw_q, Lq = tuple(thw), N
         q = _Ref(qkv, 0, *qs, N, thw_q)
     if spec.stride_kv is not None:
-        kt, k_pre, k_mean, k_rstd, thw_k = K.dwconv(qkv, qs, C, B, h, d, thw, spec.stride_kv, p["attn.pool_k.weight"],
-                                                    norm=(p["attn.norm_k.weight"], p["attn.norm_k.bias"]), eps=EPS_POOL)
-        vt, v_pre, v_mean, v_rstd, _ = K.dwconv(qkv, qs, 2 * C, B, h, d, thw, spec.stride_kv, p["attn.pool_v.weight"],
-                                                norm=(p["attn.norm_v.weight"], p["attn.norm_v.bias"]), eps=EPS_POOL)
+        # pool_k and pool_v share their geometry: one launch (grid.y = 2)
+        (kt, k_pre, k_mean, k_rstd, thw_k), (vt, v_pre, v_mean, v_rstd, _) = K.dwconv(
+            qkv, qs, C, B, h, d, thw, spec.stride_kv, p["attn.pool_k.weight"], norm=(p["attn.norm_k.weight"], p["attn.norm_k.bias"]),
+            eps=EPS_POOL, second=dict(in_off=2 * C, w=p["attn.pool_v.weight"], norm=(p["attn.norm_v.weight"], p["attn.norm_v.bias"])))
         Lk = thw_k[0] * thw_k[1] * thw_k[2]
         k = _dense_ref(kt, B, h, Lk, d, thw_k)
         v = _dense_ref(vt, B, h, Lk, d, thw_k)
@@ -261,29 +261,40 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
            b_off=q.off, **tgt)
     del dS
 
-    def pool_backward(dt, key, slot, stride, wname, nname, transposed, grid_out):
+    def pool_ln_backward(dt, key, nname):
         pre, mean, rstd = sv[key]
-        L = grid_out[0] * grid_out[1] * grid_out[2]
         g[nname + ".weight"], g[nname + ".bias"] = zeros(d), zeros(d)
-        du = K.layernorm_bwd(dt, pre, mean, rstd, p[nname + ".weight"], g[nname + ".weight"], g[nname + ".bias"],
-                             dx_dtype=wc.grad)
+        return K.layernorm_bwd(dt, pre, mean, rstd, p[nname + ".weight"], g[nname + ".weight"], g[nname + ".bias"], dx_dtype=wc.grad)
+
+    def pool_backward(items, stride, transposed, grid_out):
+        """items: [(du, slot, weight name)] — one pool, or the k and v pools of the block in a single launch each for the
+        data gradient (adjoint gather written straight into the qkv-gradient slice) and the weight gradient."""
+        L = grid_out[0] * grid_out[1] * grid_out[2]
         dense = (h * L * d, L * d, d)
-        # data gradient: the adjoint gather of the forward conv, written straight into the qkv-gradient slice
+        (du, slot, wname) = items[0]
+        sec = None
+        if len(items) == 2:
+            du2, slot2, wname2 = items[1]
+            sec = dict(inp=du2, in_off=0, w=p[wname2], out=dqkv, out_off=slot2 * C)
         K.dwconv(du, dense, 0, B, h, d, grid_out, stride, p[wname], transposed=not transposed, out=dqkv, out_strides=qs,
-                 out_off=slot * C, thw_out=thw)
-        dw = zeros(27 * d).view_as(p[wname])
+                 out_off=slot * C, thw_out=thw, second=sec)
+        for _, _, wn in items:
+            g[wn] = zeros(27 * d).view_as(p[wn])
         if transposed:
-            K.dwconv_wgrad(sv["qkv"], qs, slot * C, thw, du, dense, 0, grid_out, B, h, d, stride, dw)
+            assert len(items) == 1
+            K.dwconv_wgrad(sv["qkv"], qs, slot * C, thw, du, dense, 0, grid_out, B, h, d, stride, g[wname])
         else:
-            K.dwconv_wgrad(du, dense, 0, grid_out, sv["qkv"], qs, slot * C, thw, B, h, d, stride, dw)
-        g[wname] = dw
+            sec = None
+            if len(items) == 2:
+                sec = dict(small=du2, small_off=0, big=sv["qkv"], big_off=slot2 * C, dw=g[wname2])
+            K.dwconv_wgrad(du, dense, 0, grid_out, sv["qkv"], qs, slot * C, thw, B, h, d, stride, g[wname], second=sec)
 
     if pooled_q:
-        pool_backward(dq_t, "q_pool", 0, spec.stride_q, "attn.upsample_q.weight" if dec else "attn.pool_q.weight", "attn.norm_q",
-                      dec, thw_q)
+        qname = "attn.upsample_q.weight" if dec else "attn.pool_q.weight"
+        pool_backward([(pool_ln_backward(dq_t, "q_pool", "attn.norm_q"), 0, qname)], spec.stride_q, dec, thw_q)
     if pooled_kv:
-        pool_backward(dk_t, "k_pool", 1, spec.stride_kv, "attn.pool_k.weight", "attn.norm_k", False, k.thw)
-        pool_backward(dv_t, "v_pool", 2, spec.stride_kv, "attn.pool_v.weight", "attn.norm_v", False, v.thw)
+        pool_backward([(pool_ln_backward(dk_t, "k_pool", "attn.norm_k"), 1, "attn.pool_k.weight"),
+                       (pool_ln_backward(dv_t, "v_pool", "attn.norm_v"), 2, "attn.pool_v.weight")], spec.stride_kv, False, k.thw)
     # ---- qkv projection and norm1 ---------------------------------------------------------------------------
     dxn1 = K.gemm(dqkv, wc.w(p["attn.qkv.weight"]), M=M, N=C, K=3 * C, b_kmajor=False)
     g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M, "attn.qkv.bias")

@@ -175,32 +175,45 @@ def _out_grid(thw, stride, transposed):
 
 
 def dwconv(inp, in_strides, in_off, B, heads, d, thw_in, stride, w, *, transposed=False, norm=None, eps=1e-5,
-           out=None, out_strides=None, out_off=0, thw_out=None):
+           out=None, out_strides=None, out_off=0, thw_out=None, second=None):
     """Depthwise 3x3x3 (transposed) conv over a token grid; optional fused LayerNorm(d).
 
     inp: bf16 / f16 storage (out and pre get the same type); element (b, head, pos, c) at in_off + b*sB + head*sH + pos*sP + c.
     Returns (out, pre, mean, rstd, thw_out); out is dense (B, heads, Lo, d) unless `out` is given.
+
+    second = dict(inp=, in_off=, w=, norm=, out=, out_off=): a second problem of identical geometry and strides (the k
+    and v pools of a block) executed by the same launch; the call then returns (first results, second results).
     """
     if thw_out is None:
         thw_out = _out_grid(thw_in, stride, transposed)
     Lo = thw_out[0] * thw_out[1] * thw_out[2]
-    if out is None:
-        out = torch.empty((B, heads, Lo, d), dtype=inp.dtype, device=inp.device)
-        out_strides = (heads * Lo * d, Lo * d, d)
-    assert out.dtype == inp.dtype
+    dense = out is None
     a = PoolArgs()
     a.dtype = dt(inp)
-    a.inp = inp.data_ptr() + in_off * 2
-    a.out = out.data_ptr() + out_off * 2
-    a.w = w.data_ptr()
-    pre = mean = rstd = None
-    if norm is not None:
-        gamma, beta = norm
-        pre = torch.empty((B, heads, Lo, d), dtype=inp.dtype, device=inp.device)
-        mean = torch.empty(B * heads * Lo, dtype=torch.float32, device=inp.device)
-        rstd = torch.empty_like(mean)
-        a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
-        a.pre, a.mean, a.rstd = pre.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+
+    def one(inp_, in_off_, w_, norm_, out_, out_off_):
+        if dense:
+            out_ = torch.empty((B, heads, Lo, d), dtype=inp_.dtype, device=inp_.device)
+        assert out_.dtype == inp_.dtype == inp.dtype
+        pre = mean = rstd = None
+        gamma = beta = None
+        if norm_ is not None:
+            gamma, beta = norm_
+            pre = torch.empty((B, heads, Lo, d), dtype=inp_.dtype, device=inp_.device)
+            mean = torch.empty(B * heads * Lo, dtype=torch.float32, device=inp_.device)
+            rstd = torch.empty_like(mean)
+        ptrs = (inp_.data_ptr() + in_off_ * 2, out_.data_ptr() + out_off_ * 2, w_.data_ptr(), ptr(gamma), ptr(beta), ptr(pre), ptr(mean), ptr(rstd))
+        return ptrs, (out_, pre, mean, rstd, thw_out)
+
+    p1, r1 = one(inp, in_off, w, norm, out, out_off)
+    a.inp, a.out, a.w, a.gamma, a.beta, a.pre, a.mean, a.rstd = p1
+    r2 = None
+    if second is not None:
+        assert (second.get("norm") is None) == (norm is None)
+        p2, r2 = one(second.get("inp", inp), second["in_off"], second["w"], second.get("norm"), second.get("out"), second.get("out_off", 0))
+        a.in2, a.out2, a.w2, a.gamma2, a.beta2, a.pre2, a.mean2, a.rstd2 = p2
+    if dense:
+        out_strides = (heads * Lo * d, Lo * d, d)
     a.in_sB, a.in_sH, a.in_sP = in_strides
     a.out_sB, a.out_sH, a.out_sP = out_strides
     a.B, a.heads, a.d = B, heads, d
@@ -210,11 +223,18 @@ def dwconv(inp, in_strides, in_off, B, heads, d, thw_in, stride, w, *, transpose
     a.transposed = int(transposed)
     a.eps = eps
     call("csts_dwconv", C.byref(a))
-    return out, pre, mean, rstd, thw_out
+    return r1 if second is None else (r1, r2)
 
 
-def dwconv_wgrad(small, small_strides, small_off, thw_small, big, big_strides, big_off, thw_big, B, heads, d, stride, dw):
+def dwconv_wgrad(small, small_strides, small_off, thw_small, big, big_strides, big_off, thw_big, B, heads, d, stride, dw, second=None):
+    """second = dict(small=, small_off=, big=, big_off=, dw=): a second problem of identical geometry in the same launch."""
     a = WgradArgs()
+    if second is not None:
+        s2, b2 = second["small"], second["big"]
+        assert s2.dtype == small.dtype and b2.dtype == big.dtype
+        a.small2 = s2.data_ptr() + second["small_off"] * 2
+        a.big2 = b2.data_ptr() + second["big_off"] * 2
+        a.dw2 = second["dw"].data_ptr()
     a.small = small.data_ptr() + small_off * 2
     a.big = big.data_ptr() + big_off * 2
     a.dw = dw.data_ptr()

@@ -127,6 +127,16 @@ typedef struct csts_pool_args {
   int32_t transposed;     /* 0: out[o] = sum_tap w[tap] in[o*s+tap-1]; 1: out[o] = sum_tap w[tap] in[(o+1-tap)/s] */
   float eps;
   int32_t dtype;          /* 1 bf16, 2 f16: type of in / out / pre */
+  /* optional second problem of identical geometry run by the same launch (the k and v pools of a block share
+   * everything but their tensors): used when in2 != NULL */
+  const void* in2;
+  void* out2;
+  const float* w2;
+  const float* gamma2;
+  const float* beta2;
+  void* pre2;
+  float* mean2;
+  float* rstd2;
 } csts_pool_args;
 int csts_dwconv(const csts_pool_args* p, void* stream);
 
@@ -142,6 +152,10 @@ typedef struct csts_wgrad_args {
   int32_t Tb, Hb, Wb;
   int32_t st, sh, sw;
   int32_t small_dtype, big_dtype;
+  /* optional second problem of identical geometry in the same launch (used when small2 != NULL) */
+  const void* small2;
+  const void* big2;
+  float* dw2;
 } csts_wgrad_args;
 int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream);
 

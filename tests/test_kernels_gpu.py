@@ -685,3 +685,39 @@ def test_rowwise_and_pool_kernels_f16_storage():
     dqkv = torch.zeros(B, N, 3, h, d, dtype=torch.float16, device=dev)
     k.dwconv(du, (h * Lo * d, Lo * d, d), 0, B, h, d, thw_o, stride, w, transposed=True, out=dqkv, out_strides=qs, out_off=0, thw_out=thw)
     assert rel_err(dqkv[:, :, 0].permute(0, 2, 3, 1).reshape(B * h, d, *thw), xr.grad) < 8e-4
+
+
+@pytest.mark.parametrize("thw,stride", [((4, 16, 16), (1, 2, 2)), ((2, 8, 8), (1, 1, 1))])
+def test_paired_pool_launch_equals_two_single_launches(thw, stride):
+    """The k and v pools of a block run as one launch (grid.y = 2): forward (+LayerNorm), adjoint gather and weight
+    gradient must equal the single-problem launches bit for bit."""
+    k = K()
+    B, h, d = 2, 2, 96
+    N = thw[0] * thw[1] * thw[2]
+    Cn = h * d
+    g = torch.Generator(device="cpu").manual_seed(31)
+    qkv = bf(torch.randn(B, N, 3, h, d, generator=g)).to(dev)
+    wk, wv = ((torch.randn(d, 1, 3, 3, 3, generator=g) * 0.2).to(dev) for _ in range(2))
+    nk, nv = ((torch.randn(d, generator=g).to(dev), torch.randn(d, generator=g).to(dev)) for _ in range(2))
+    qs = (N * 3 * Cn, d, 3 * Cn)
+    rk = k.dwconv(qkv, qs, Cn, B, h, d, thw, stride, wk, norm=nk)
+    rv = k.dwconv(qkv, qs, 2 * Cn, B, h, d, thw, stride, wv, norm=nv)
+    pk, pv = k.dwconv(qkv, qs, Cn, B, h, d, thw, stride, wk, norm=nk, second=dict(in_off=2 * Cn, w=wv, norm=nv))
+    for a, b in zip(rk[:4] + rv[:4], pk[:4] + pv[:4]):
+        assert torch.equal(a, b)
+    thw_o = rk[4]
+    Lo = thw_o[0] * thw_o[1] * thw_o[2]
+    dense = (h * Lo * d, Lo * d, d)
+    duk, duv = (bf(torch.randn(B, h, Lo, d, generator=g)).to(dev) for _ in range(2))
+    one, two = torch.zeros_like(qkv), torch.zeros_like(qkv)
+    k.dwconv(duk, dense, 0, B, h, d, thw_o, stride, wk, transposed=True, out=one, out_strides=qs, out_off=Cn, thw_out=thw)
+    k.dwconv(duv, dense, 0, B, h, d, thw_o, stride, wv, transposed=True, out=one, out_strides=qs, out_off=2 * Cn, thw_out=thw)
+    k.dwconv(duk, dense, 0, B, h, d, thw_o, stride, wk, transposed=True, out=two, out_strides=qs, out_off=Cn, thw_out=thw,
+             second=dict(inp=duv, in_off=0, w=wv, out=two, out_off=2 * Cn))
+    assert torch.equal(one, two) and one[:, :, 1].abs().sum() > 0 and torch.all(one[:, :, 0] == 0)
+    dwk1, dwv1, dwk2, dwv2 = (torch.zeros_like(wk) for _ in range(4))
+    k.dwconv_wgrad(duk, dense, 0, thw_o, qkv, qs, Cn, thw, B, h, d, stride, dwk1)
+    k.dwconv_wgrad(duv, dense, 0, thw_o, qkv, qs, 2 * Cn, thw, B, h, d, stride, dwv1)
+    k.dwconv_wgrad(duk, dense, 0, thw_o, qkv, qs, Cn, thw, B, h, d, stride, dwk2,
+                   second=dict(small=duv, small_off=0, big=qkv, big_off=2 * Cn, dw=dwv2))
+    assert rel_err(dwk2, dwk1) < 1e-5 and rel_err(dwv2, dwv1) < 1e-5 and dwv1.abs().sum() > 0     # atomics: order differs
