@@ -136,6 +136,55 @@ def test_drop_path_masks_are_drawn_once_per_step(cpu_model):
     assert abs(blocks[-1].spec.drop_path - 0.2) < 1e-6
 
 
+def test_fused_optimizer_state_interchanges_with_torch_adamw():
+    """FusedClipAdamW keeps torch.optim.AdamW's state layout (step / exp_avg / exp_avg_sq per parameter, same
+    param_groups), so an optimizer checkpoint written by the reference loop loads into it and vice versa."""
+    from csts_b200.host.optimizer import FusedClipAdamW
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    groups = lambda q: [{"params": [q[0]], "weight_decay": 0.05}, {"params": [q[1]], "weight_decay": 0.0}]
+    ref = torch.optim.AdamW(groups(ps), lr=1e-3, eps=1e-8, weight_decay=0.05)
+    for _ in range(2):
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        ref.step()
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ours = FusedClipAdamW(groups(qs), lr=1e-3, eps=1e-8, weight_decay=0.05)
+    ours.load_state_dict(ref.state_dict())
+    ours._init_state()
+    assert ours._step.item() == 2.0
+    for p, q in zip(ps, qs):
+        assert torch.equal(ours.state[q]["exp_avg"], ref.state[p]["exp_avg"])
+        assert torch.equal(ours.state[q]["exp_avg_sq"], ref.state[p]["exp_avg_sq"])
+    back = torch.optim.AdamW(groups([torch.nn.Parameter(p.detach().clone()) for p in ps]), lr=1e-3, eps=1e-8, weight_decay=0.05)
+    back.load_state_dict(ours.state_dict())
+    assert [g["weight_decay"] for g in back.param_groups] == [0.05, 0.0]
+    assert float(back.state[back.param_groups[0]["params"][0]]["step"]) == 2.0
+
+
+def test_weight_cache_does_not_trust_version_counters():
+    """torch's fused optimizers update parameters without bumping `_version`; in training the 16-bit copies are
+    therefore re-made once per step (begin_training_step) unless the fused clip+AdamW step has just rewritten them."""
+    from csts_b200.host.weights import WeightCache
+    wc = WeightCache()
+    calls = []
+    p = torch.nn.Parameter(torch.zeros(2, 2))
+    make = lambda q: calls.append(1) or q.clone()
+    wc._get(p, "w", make)
+    wc._get(p, "w", make)
+    assert len(calls) == 1                       # same step, same version: cached
+    wc.begin_training_step()
+    wc._get(p, "w", make)
+    assert len(calls) == 2                       # new step: rebuilt even though p._version is unchanged
+    wc._get(p, ("pad", 8), make)
+    wc.after_fused_step()                        # the fused optimizer refreshed the plain copies, dropped the re-laid-out ones
+    wc.begin_training_step()
+    wc._get(p, "w", make)
+    assert len(calls) == 3
+    wc._get(p, ("pad", 8), make)
+    assert len(calls) == 4
+
+
 def test_cpu_forward_fails_loudly(cpu_model):
     model, _ = cpu_model
     with pytest.raises(RuntimeError):

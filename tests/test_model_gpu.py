@@ -201,10 +201,10 @@ def test_full_model_against_reference_golden(golden_dir, fixture, gain, mode):
     # gpurun_out/parity_*.json and guarded loosely (deep, tiny tensors carry the rounding noise).
     if mode == "fp16":
         assert report["grad_global_rel"] <= (2e-2 if gain == 1.0 else 5e-2), report
-        assert report["grad_median"] <= (2e-2 if gain == 1.0 else 6e-2) and errs[0][0] <= 0.25, report
+        assert report["grad_median"] <= (2e-2 if gain == 1.0 else 6e-2) and errs[0][0] <= 0.4, report
     else:
         assert report["grad_global_rel"] <= (5e-2 if gain == 1.0 else 0.12), report
-        assert report["grad_median"] <= (6e-2 if gain == 1.0 else 0.15) and errs[0][0] <= 0.5, report
+        assert report["grad_median"] <= (6e-2 if gain == 1.0 else 0.15) and errs[0][0] <= 0.6, report
     for n, g in rec.get("grads", {}).items():
         if g.norm() < 1e-6:
             continue
