@@ -799,7 +799,8 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
     // T-column kernel: 2 column slots x 3 kernel rows per block; every block ends with 27*d global atomics, so at
     // most 3 blocks per SM
     const int64_t cols = (int64_t)p->B * p->heads * p->Hs * p->Ws;
-    int64_t nslots = cols < (int64_t)csts_num_sms() * 6 ? cols : (int64_t)csts_num_sms() * 6;
+    static const int slot_mult = getenv("CSTS_WGRAD_SLOTS") ? atoi(getenv("CSTS_WGRAD_SLOTS")) : 2;      // tuning hook (A/B: 6 -> 29.04 ms, 2 -> 28.69 ms per step)
+    int64_t nslots = cols < (int64_t)csts_num_sms() * slot_mult ? cols : (int64_t)csts_num_sms() * slot_mult;
     int cols_per_warp = (int)((cols + nslots - 1) / nslots);
     int cgrid = (int)((cols + (int64_t)cols_per_warp * 2 - 1) / ((int64_t)cols_per_warp * 2));
 #define WGRAD_TCOL(TS_, TB_)                                                                                          \

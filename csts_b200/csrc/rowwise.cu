@@ -1,6 +1,8 @@
 // Memory-bound row-wise kernels: LayerNorm fwd/bwd, attention softmax fwd/bwd, casts, column sums,
 // elementwise residual adds.  All HBM-bound: 128-bit (f32x4) / 64-bit (bf16x4) accesses, one warp per
 // row with shuffle reductions, grids sized in multiples of the SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -427,7 +429,10 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
   const int dx16_half = dx16_dtype == CSTS_F16;
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = (rows + 31) / 32;       // >= 4 rows per warp so the column atomics amortise
+  // every block ends with 2 * width global atomics on the same addresses: narrow rows get more rows per block
+  static const int rows_narrow = getenv("CSTS_LN_BWD_ROWS") ? atoi(getenv("CSTS_LN_BWD_ROWS")) : 32;   // tuning hook
+  const int rows_per_block = width <= 128 ? rows_narrow : 32;
+  int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;       // >= 4 rows per warp so the column atomics amortise
   int grid = (int)(blocks < csts_num_sms() * 8 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 8);
 #define LN_BWD_J(TX, TDY, TDX, J) \
   launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, J>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width, dx16, dx16_half, row_scale, rows_per_scale)
