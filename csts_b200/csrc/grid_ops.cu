@@ -679,20 +679,49 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
     int tlo = ft == 1 ? ti : max(ti * ft - ft, 0), thi = ft == 1 ? ti : min(ti * ft + 2 * ft - 1, To - 1);
     int hlo = fh == 1 ? hi : max(hi * fh - fh, 0), hhi = fh == 1 ? hi : min(hi * fh + 2 * fh - 1, Ho - 1);
     int wlo = fw == 1 ? wi : max(wi * fw - fw, 0), whi = fw == 1 ? wi : min(wi * fw + 2 * fw - 1, Wo - 1);
-    for (int to = tlo; to <= thi; ++to) {
-      float ct = lin_adj(ti, to, ft, T);
-      if (ct == 0.f) continue;
-      for (int ho = hlo; ho <= hhi; ++ho) {
-        float ch = lin_adj(hi, ho, fh, H);
-        if (ch == 0.f) continue;
-        for (int wo = wlo; wo <= whi; ++wo) {
-          float cw = lin_adj(wi, wo, fw, W);
-          if (cw == 0.f) continue;
-          float v[4];
-          ld4(dy + (((b * To + to) * Ho + ho) * Wo + wo) * C + c, v);
-          float wgt = ct * ch * cw;
+    // the adjoint weights depend on one axis each: evaluate them once per axis (<= 3 f candidates, f <= 2 on the path),
+    // not once per (to, ho, wo) triple
+    constexpr int MAXC = 6;
+    if (hhi - hlo < MAXC && whi - wlo < MAXC) {
+      float chv[MAXC], cwv[MAXC];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+      for (int k = 0; k < MAXC; ++k) {
+        chv[k] = (hlo + k <= hhi) ? lin_adj(hi, hlo + k, fh, H) : 0.f;
+        cwv[k] = (wlo + k <= whi) ? lin_adj(wi, wlo + k, fw, W) : 0.f;
+      }
+      for (int to = tlo; to <= thi; ++to) {
+        const float ct = lin_adj(ti, to, ft, T);
+        if (ct == 0.f) continue;
+#pragma unroll
+        for (int kh = 0; kh < MAXC; ++kh) {
+          if (chv[kh] == 0.f) continue;
+#pragma unroll
+          for (int kw = 0; kw < MAXC; ++kw) {
+            if (cwv[kw] == 0.f) continue;
+            float v[4];
+            ld4(dy + (((b * To + to) * Ho + (hlo + kh)) * Wo + (wlo + kw)) * C + c, v);
+            const float wgt = ct * chv[kh] * cwv[kw];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+          }
+        }
+      }
+    } else {
+      for (int to = tlo; to <= thi; ++to) {
+        float ct = lin_adj(ti, to, ft, T);
+        if (ct == 0.f) continue;
+        for (int ho = hlo; ho <= hhi; ++ho) {
+          float ch = lin_adj(hi, ho, fh, H);
+          if (ch == 0.f) continue;
+          for (int wo = wlo; wo <= whi; ++wo) {
+            float cw = lin_adj(wi, wo, fw, W);
+            if (cw == 0.f) continue;
+            float v[4];
+            ld4(dy + (((b * To + to) * Ho + ho) * Wo + wo) * C + c, v);
+            float wgt = ct * ch * cw;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+          }
         }
       }
     }

@@ -244,14 +244,17 @@ __global__ void __launch_bounds__(256) classifier_bwd_feat_kernel(const float* _
   if (threadIdx.x == 0) atomicAdd(dbias, s_db);
 }
 // dstem[b][ti][s][c] = w[c] * sum_{to} coef(to -> ti) * dlogit[b][to][s]
-__global__ void classifier_bwd_stem_kernel(const float* __restrict__ dlogits, const float* __restrict__ w, float* __restrict__ dstem, int B,
-                                           int Ti, int S, int C) {
+// One warp per (b, ti, s) token: the interpolation-adjoint sum is a per-token scalar (evaluated once, not once per
+// channel), then the C channels are written as coalesced rows.
+__global__ void __launch_bounds__(256) classifier_bwd_stem_kernel(const float* __restrict__ dlogits, const float* __restrict__ w,
+                                                                  float* __restrict__ dstem, int B, int Ti, int S, int C) {
   pdl_wait();
   const int To = 2 * Ti;
-  const uint32_t total = (uint32_t)B * Ti * S * C;                      // < 2^32, checked on the host
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    uint32_t q = i;
-    const int c = (int)divmod(q, C), s = (int)divmod(q, S), ti = (int)divmod(q, Ti);
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const uint32_t total = (uint32_t)B * Ti * S;
+  for (uint32_t tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < total; tok += gridDim.x * wpb) {
+    uint32_t q = tok;
+    const int s = (int)divmod(q, S), ti = (int)divmod(q, Ti);
     const int64_t b = q;
     float acc = 0.f;
     for (int to = max(2 * ti - 2, 0); to <= min(2 * ti + 3, To - 1); ++to) {
@@ -260,9 +263,10 @@ __global__ void classifier_bwd_stem_kernel(const float* __restrict__ dlogits, co
       float cf = 0.f;
       if (i0 == ti) cf += 1.f - lam;
       if (i1 == ti) cf += lam;
-      if (cf != 0.f) acc += cf * dlogits[(b * To + to) * S + s];
+      if (cf != 0.f) acc += cf * __ldg(dlogits + (b * To + to) * S + s);
     }
-    dstem[i] = acc * w[c];
+    float* d = dstem + (int64_t)tok * C;
+    for (int c = lane; c < C; c += 32) d[c] = acc * w[c];
   }
 }
 
@@ -328,7 +332,7 @@ int csts_classifier_bwd(const float* dlogits, const float* feat, const float* st
   int rc = csts_check_launch("classifier_bwd_feat");
   if (rc) return rc;
   CSTS_REQUIRE((int64_t)B * Ti * S * C < (1LL << 32), "classifier_bwd: tensor too large for 32-bit indexing");
-  launch_pdl(classifier_bwd_stem_kernel, dim3(grid_for((int64_t)B * Ti * S * C, 256)), dim3(256), 0, (cudaStream_t)stream, dlogits, w, dstem, B, Ti, S, C);
+  launch_pdl(classifier_bwd_stem_kernel, dim3(grid_for((int64_t)B * Ti * S, 8)), dim3(256), 0, (cudaStream_t)stream, dlogits, w, dstem, B, Ti, S, C);
   return csts_check_launch("classifier_bwd_stem");
 }
 
