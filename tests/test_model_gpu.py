@@ -397,3 +397,30 @@ def test_optional_paths_against_reference_golden(golden_dir, mode):
     assert e_t <= 2e-2 * tol and e_s <= 2e-2 * tol and e_1 <= 1e-2, (e_t, e_s, e_1)
     # split-K f32 atomics make two forwards differ in the last bits; one flipped 16-bit rounding moves a probability by ~1e-3
     assert (only_t[1] - out[2]).abs().max() <= 1e-2 * tol
+
+
+def test_prefetched_inputs_reach_the_graphed_step(golden_dir):
+    """GraphedTrainStep.prefetch / step_prefetched (host->device copy of the next batch on a copy stream while the current
+    step computes) feeds the step the same data as the synchronous call.  lr = 0 keeps the weights fixed, so the loss
+    identifies the batch."""
+    import csts_oracle as O
+    from csts_b200.host.build import build_model
+    from csts_b200.host.train_step import GraphedTrainStep, construct_optimizer
+    shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
+    cfg = make_cfg()
+    cfg.SOLVER.BASE_LR = 0.0
+    model = build_model(cfg)
+    model.load_state_dict(O.synthetic_state(shapes, seed=3, gain=1.0), strict=True)
+    model.train()
+    batches = [tuple(t.pin_memory() for t in O.synthetic_batch(2, seed=s)) for s in (11, 12)]
+    opt = construct_optimizer(model, cfg, capturable=True, fused_clip=True)
+    step = GraphedTrainStep(cfg, model, opt, *(t.to(dev) for t in batches[0]), warmup=2)
+    want = [step([v], a, h).item() for v, a, h in batches]
+    assert abs(want[0] - want[1]) > 1e-4                       # the two batches are distinguishable
+    step.prefetch([batches[0][0]], batches[0][1], batches[0][2])
+    got = []
+    for nxt in (1, 0, 1):
+        loss = step.step_prefetched()
+        step.prefetch([batches[nxt][0]], batches[nxt][1], batches[nxt][2])
+        got.append(loss.item())
+    assert all(abs(g - w) <= 2e-5 * abs(w) for g, w in zip(got, [want[0], want[1], want[0]])), (got, want)
