@@ -85,45 +85,61 @@ def make_cfg(n_gpus, precision="bf16"):
     return assert_and_infer_cfg(cfg)
 
 
-# --------------------------------------------------------------------------------------------- CPU arm
-def cpu_train_step_clips_per_s(batch, steps, warmup):
-    """Oracle (fp32 torch restatement of the reference, oracle/csts_oracle.py) fwd + loss + bwd on the
-    host cores: the reference's CPU path (NUM_GPUS=0).  AdamW/clip are omitted on this arm: they are
-    <1 % of a CPU step."""
+# --------------------------------------------------------------------------------------------- reference arms
+def reference_clips_per_s(device, batch, steps, warmup, autocast_dtype=None):
+    """The reference's own training step (tools/train_avgaze_net.py:70-109: forward, kldiv+egonce, backward,
+    clip_grad_norm_, AdamW) — the UNMODIFIED `slowfast` package imported from baseline/_ref (or /root/reference)
+    through oracle/ref_shim.py, or the oracle port when no reference tree is importable — on `device`."""
     import torch
-    import csts_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    with open(os.path.join(ROOT, "tests", "golden", "param_shapes.json")) as f:
-        shapes = json.load(f)
-    sd = O.synthetic_state(shapes, seed=0)
-    video, audio, hm = O.synthetic_batch(batch, seed=1)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.loss_and_grads(sd, video, audio, hm, alpha=0.05)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return batch / statistics.median(times), torch.get_num_threads(), times
+    import ref_train
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    st = ref_train.ReferenceStepper(device, autocast_dtype=autocast_dtype, droppath=0.2, seed=0)
+    cps, times = ref_train.time_steps(st, batch, steps, warmup)
+    return cps, times, st.kind, torch.get_num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 2
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)                      # the reference prints while it builds its optimizer; stdout carries the JSON line only
+    batch = BATCH_PER_GPU
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
-    cps, cores, times = cpu_train_step_clips_per_s(batch, steps, warmup=1)
-    sample = f"{steps} timed fwd+loss+bwd steps at batch {batch} (of the batch-{BATCH_PER_GPU} workload), oracle port, fp32, {cores} threads"
-    print(json.dumps({
+    cps, times, kind, cores = reference_clips_per_s("cpu", batch, steps, warmup=1)
+    sample = (f"{steps} timed full training steps (fwd + kldiv+egonce + bwd + clip_grad_norm_ + AdamW) at batch {batch}, "
+              f"{'unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port'}, fp32, NUM_GPUS=0, {cores} threads")
+    os.write(json_fd, (json.dumps({
         "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
         "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample, "global_batch": batch, "droppath": 0.2,
+                   "optimizer": "clip_grad_norm_ 1.0 + AdamW (torch)"},
+        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
-    }))
+    }) + "\n").encode())
+
+
+def gpu_reference(dev, steps=5, warmup=2):
+    """The bar SURVEY.md §8(d) names: the reference's stock PyTorch-eager step on the SAME B200, same batch, same
+    synthetic inputs — fp32 (stock flags) and under torch.autocast(bfloat16)."""
+    import torch
+    out = {}
+    for name, dtype in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            cps, times, kind, _ = reference_clips_per_s(dev, BATCH_PER_GPU, steps, warmup, autocast_dtype=dtype)
+            out[name] = {"value": cps, "unit": "clips/s", "ms_per_step": 1e3 * statistics.median(times), "kind": kind}
+        except Exception as e:          # report, never fail the bench line
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    out["what"] = (f"{steps} timed full training steps at batch {BATCH_PER_GPU} after {warmup} warm-ups, CUDA events; "
+                   "unmodified reference modules (baseline/_ref) in stock PyTorch eager on this GPU, DROPPATH 0.2, torch AdamW; "
+                   f"matmul.allow_tf32={torch.backends.cuda.matmul.allow_tf32}, cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}")
+    return out
 
 
 def ncu_traffic(prefix):
@@ -139,6 +155,71 @@ def ncu_traffic(prefix):
     n = sum(v["launches"] for k, v in d.items() if k.startswith(prefix))
     b = sum(v["dram_bytes"] for k, v in d.items() if k.startswith(prefix))
     return (b / n if n else None), os.path.relpath(files[-1], ROOT) + f" (ncu dram__bytes_read+write.sum over {n} launches of one step)"
+
+
+def dp_check(dev, rank, world, precision):
+    """Data-parallel correctness, checked on the machine the numbers come from (untimed, before the timed region):
+    the gradient left by one replay of the GRAPHED data-parallel step (captured NCE all-gather + captured bucketed NCCL
+    all-reduces on the side stream, local batch 2, DROPPATH 0, lr 0 so the parameters stay put) against the gradient of
+    the single-process step over the concatenated global batch on the same parameters, plus bit-equality of the
+    reduced gradient across ranks."""
+    import torch
+    import torch.distributed as dist
+    import csts_oracle as O
+    from csts_b200.host import losses
+    from csts_b200.host.build import build_model
+    from csts_b200.host.train_step import GraphedTrainStep, construct_optimizer, make_grad_scaler
+    from csts_b200.host.utils import frame_softmax, sim_matrix
+    cfg = make_cfg(world, precision)
+    cfg.MVIT.DROPPATH_RATE = 0.0
+    cfg.SOLVER.BASE_LR = 0.0
+    torch.manual_seed(7)
+    model = build_model(cfg, ddp=False)
+    model.train()
+    opt = construct_optimizer(model, cfg, capturable=True, fused_clip=True)
+    bl = 2
+    batches = [O.synthetic_batch(bl, seed=500 + r) for r in range(world)]
+    v, a, h = (t.to(dev) for t in batches[rank])
+    scaler = make_grad_scaler(cfg, init_scale=1024.0, growth_interval=10 ** 9)
+    g = GraphedTrainStep(cfg, model, opt, v, a, h, scaler=scaler)
+    g(None, None, None)
+    torch.cuda.synchronize()
+    arena = model._wc.arena
+    got = arena.flat.clone()
+    if scaler.is_enabled():
+        got /= scaler.get_scale()
+    # cross-rank equality of the reduced gradient
+    ref0 = got.clone()
+    dist.broadcast(ref0, src=0)
+    diff = (got - ref0).abs().max().reshape(1)
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    # single-process global batch on the same parameters (no collectives: the model and loss functions directly)
+    gv, ga, gh = (torch.cat([b[i] for b in batches]).to(dev) for i in range(3))
+    opt.zero_grad(set_to_none=True)
+    preds, ve, ae = model([gv], ga, return_embed=True)
+    loss = losses.get_loss_func("kldiv")()(frame_softmax(preds, temperature=2), gh) + \
+        cfg.MODEL.LOSS_ALPHA * losses.get_loss_func("egonce")()(sim_matrix(ve, ae))
+    (scaler.scale(loss) if scaler.is_enabled() else loss).backward()
+    torch.cuda.synchronize()
+    want = torch.zeros_like(got)
+    for p in model.parameters():
+        lo, n = arena.slot[id(p)]
+        want[lo: lo + n] = p.grad.reshape(-1)
+    if scaler.is_enabled():
+        want /= scaler.get_scale()
+    rel = ((got - want).norm() / want.norm()).reshape(1)
+    worst = torch.zeros(1, device=dev)
+    for p in model.parameters():
+        lo, n = arena.slot[id(p)]
+        wn = want[lo: lo + n].norm()
+        if wn > 1e-7:
+            worst = torch.maximum(worst, ((got[lo: lo + n] - want[lo: lo + n]).norm() / wn).reshape(1))
+    dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    del g
+    return {"rel": rel.item(), "worst_tensor_rel": worst.item(), "ranks_equal": diff.item() == 0.0, "max_rank_diff": diff.item(),
+            "what": f"graphed DP step (local batch {bl}, {world} ranks) vs single-process global batch {bl * world}, same parameters; "
+                    "global relative L2 over all 188 M gradient entries, worst per-tensor relative L2, and bit-equality across ranks"}
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -163,6 +244,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    dpc = dp_check(dev, rank, world, args.precision) if world > 1 and args.graph else None
     cfg = make_cfg(world, args.precision)
     torch.manual_seed(cfg.RNG_SEED)
     use_graph = args.graph
@@ -215,6 +297,7 @@ def run_gpu(args):
         # Park the GPU behind a ~70 ms spin kernel so the host can enqueue the whole eager step first: the
         # per-launch CUDA events then bracket kernels that run back to back (no host-side gaps inside the deltas).
         torch.cuda._sleep(int(0.07 * 1.9e9))
+        graphed.model._wc.fork_backward = False      # serial launches: each event pair then brackets one kernel running alone
         return train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync, scaler=scaler)
 
     def timed(fn, steps, profile=False):
@@ -250,6 +333,7 @@ def run_gpu(args):
         # per-kernel CUDA-event timing needs un-captured launches: same kernels, eager, right after the timed region
         _, _, prof = timed(eager_profile_step, args.steps, profile=(rank == 0))
     if graphed is not None:
+        graphed.model._wc.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
         graphed.prefetch([video_h], audio_h, hm_h)
     for _ in range(2):
         e2e_step()
@@ -293,10 +377,20 @@ def run_gpu(args):
                      "share_of_step": tc_ms / total_ms, "all_gemm_ms_per_step": all_ms / args.steps,
                      "timing": "CUDA events around every launch" + (" (eager replay of the same step; the timed region itself is one CUDA-graph launch per step)" if graphed is not None else "")},
     }
+    if dpc is not None:
+        out["dp_check"] = dpc
+    if args.gpu_reference and world == 1:
+        torch.cuda.empty_cache()
+        out["gpu_reference"] = gpu_reference(dev)
+        for k in ("fp32", "bf16_autocast"):
+            if "value" in out["gpu_reference"].get(k, {}):
+                out["gpu_reference"][k]["speedup_value"] = out["value"] / out["gpu_reference"][k]["value"]
+                out["gpu_reference"][k]["speedup_e2e"] = out["e2e"]["value"] / out["gpu_reference"][k]["value"]
     if args.cpu_baseline:
-        cps, cores, times = cpu_train_step_clips_per_s(2, 2, 1)
-        out["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
-                               "sample": "2 timed fwd+loss+bwd steps at batch 2 of the same workload (oracle port, fp32)"}
+        cps, times, kind, cores = reference_clips_per_s("cpu", BATCH_PER_GPU, 2, 1)
+        out["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": kind,
+                               "sample": f"2 timed full training steps (fwd + loss + bwd + clip + AdamW) at batch {BATCH_PER_GPU} of the same "
+                                         f"workload ({'unmodified reference, baseline/_ref' if kind == 'reference' else 'oracle port'}, fp32, NUM_GPUS=0)"}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
@@ -314,6 +408,8 @@ def main():
     ap.add_argument("--torch-optimizer", dest="fused_optimizer", action="store_false",
                     help="clip_grad_norm_ + torch's fused AdamW instead of the library's fused clip+AdamW step")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-gpu-reference", dest="gpu_reference", action="store_false",
+                    help="skip timing the reference's stock PyTorch-eager step on the same GPU")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -20,7 +20,11 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -675,8 +679,8 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 [batch1][batch2][rows][cols] tensor, row pitch ld, batch strides s1 / s2 (elements);
 // box = [1, 1, box_rows, 64 cols], 128B swizzle, out-of-bounds elements read as zero
-int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
-              int64_t s1, int64_t s2) {
+int encode_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
+                int64_t s1, int64_t s2) {
   EncodeTiledFn fn = get_encode_fn();
   CSTS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
   cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch2, (cuuint64_t)batch1};
@@ -692,13 +696,52 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
   return 0;
 }
 
+// A descriptor is a pure function of (base, extents, strides, box): the training step presents the same few hundred
+// tensors every iteration (the caching allocator hands back the same blocks), so encoded maps are kept, keyed by those
+// values.  The cache is bounded (cleared when full) and guarded by a mutex: autograd's backward thread and the forward
+// thread both launch GEMMs.
+struct TmapKey {
+  const void* base; int64_t rows, cols, ld, s1, s2; int box_rows, batch1, batch2;
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed word-wise");
+
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
+              int64_t s1, int64_t s2) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.base = base; key.rows = rows; key.cols = cols; key.ld = ld; key.s1 = batch1 > 1 ? s1 : 0; key.s2 = batch2 > 1 ? s2 : 0;
+  key.box_rows = box_rows; key.batch1 = batch1; key.batch2 = batch2;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return 0; }
+  }
+  int rc = encode_tmap(map, base, rows, cols, ld, box_rows, batch1, batch2, s1, s2);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() >= 8192) cache.clear();
+  cache.emplace(key, *map);
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch(const csts_gemm_args& a, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set{false};      // set from the forward thread and from autograd's backward thread
+  if (!attr_set.load(std::memory_order_acquire)) {
     CSTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   CUtensorMap ta, tb;
   // K-major operand X[mn][k]: tensor [mn rows, K cols], box [tile rows, 64 k].

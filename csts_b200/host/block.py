@@ -65,8 +65,11 @@ def _dense_ref(t, B, h, L, d, thw):
 
 
 def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False):
-    """x: f32 (B, N, C).  p: {name: f32 parameter}.  wc: WeightCache.  Returns (y, thw_q, saved, attn)."""
+    """x: f32 (B, N, C).  p: {name: f32 parameter}.  wc: WeightCache.  Returns (y, thw_q, saved, attn).
+    dp_scale: None or f32 (2, B) — the per-sample DropPath scales (0 or 1/keep) of the attention branch (row 0)
+    and of the MLP branch (row 1): the reference draws them independently (attention.py:242 and :247)."""
     B, N, C = x.shape
+    dp_a, dp_m = (dp_scale[0], dp_scale[1]) if dp_scale is not None else (None, None)
     h, d = spec.heads, spec.head_dim
     M = B * N
     dec = spec.kind == "dec"
@@ -132,7 +135,7 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
         x_res, arg = K.maxpool_fwd(x, B, thw, C, want_arg=save)
     rps = Lq if dp_scale is not None else 0
     x1 = K.gemm(o, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, bias=p["attn.proj.bias"], residual=x_res.view(Mq, C),
-                out_dtype=torch.float32, row_scale=dp_scale, rows_per_scale=rps)
+                out_dtype=torch.float32, row_scale=dp_a, rows_per_scale=rps)
     # ---- MLP (attention.py:243-247) -----------------------------------------------------------------
     xn2, mean2, rstd2 = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], EPS_BLOCK, out_dtype=wc.act)
     hid = spec.hidden
@@ -144,7 +147,7 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     else:
         base = x1
     x2 = K.gemm(hdn, wc.w(p["mlp.fc2.weight"]), M=Mq, N=spec.dim_out, K=hid, bias=p["mlp.fc2.bias"], residual=base,
-                out_dtype=torch.float32, row_scale=dp_scale, rows_per_scale=rps)
+                out_dtype=torch.float32, row_scale=dp_m, rows_per_scale=rps)
     y = x2.view(B, Lq, spec.dim_out)
     attn = P[..., :Lk].float() if want_attn else None
     if not save:
@@ -162,6 +165,66 @@ def audio_rows(P, thw):
     return torch.stack([P[:, :, T * HW + t, HW * t: HW * (t + 1)] for t in range(T)], dim=2).float()
 
 
+class _GradOut:
+    """Where the parameter gradients of one block are written.
+
+    With a GradArena (host/grad_arena.py) every gradient is a view of the block's contiguous slice of the arena,
+    zeroed by ONE memset (the accumulate-into ones — norm affine, biases, pool kernels — and the split-K weight
+    gradients alike).  Without one (stand-alone use of the block in tests, or a parameter that already holds a
+    gradient that autograd has to accumulate into) the small gradients share one zeroed scratch buffer and the
+    matrices are allocated by the GEMM."""
+
+    def __init__(self, p, wc, dev, scratch_elems):
+        arena = getattr(wc, "arena", None)
+        ts = list(p.values())
+        self.arena = arena if arena is not None and all(arena.has(t) and t.grad is None for t in ts) else None
+        if self.arena is not None:
+            self.arena.span(ts).zero_()
+        else:
+            self.zbuf = torch.zeros(scratch_elems, dtype=torch.float32, device=dev)
+            self.zoff = 0
+
+    def small(self, param, n):
+        """zeroed f32 [n] for an accumulate-into gradient"""
+        if self.arena is not None:
+            return self.arena.view(param).view(-1)
+        lo = self.zoff
+        self.zoff = lo + (n + 3) // 4 * 4          # keep 16-byte alignment for the vectorised kernels
+        return self.zbuf[lo: lo + n]
+
+    def matrix(self, param):
+        """(zeroed output tensor, or None when the GEMM should allocate its own)"""
+        return self.arena.view(param) if self.arena is not None else None
+
+
+class _Fork:
+    """Weight-gradient work of a block runs on a second stream: it is off the dX critical path, and two thirds of
+    the step's GEMMs fill at most one wave of SMs, so the two streams share the machine.  Inside the captured
+    step the fork becomes a parallel branch of the CUDA graph.  Every tensor the side stream reads is kept alive
+    in `hold` until join() — the caching allocator is not told about the second stream."""
+
+    def __init__(self, stream):
+        self.side = stream
+        self.main = torch.cuda.current_stream() if stream is not None else None
+        self.hold = []
+        self.used = False
+
+    def run(self, fn, *keep):
+        if self.side is None:
+            return fn()
+        self.hold.extend(keep)
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            r = fn()
+        self.used = True
+        return r
+
+    def join(self):
+        if self.used:
+            self.main.wait_stream(self.side)
+        self.hold.clear()
+
+
 def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
     """dy: f32 (B, Lq, dim_out).  Returns (dx f32 (B,N,C), {param name: grad}).  d_audio_rows: gradient w.r.t.
     audio_rows(P) (MVIT.SPATIAL_AUDIO_ATTN), folded into dP before the softmax backward."""
@@ -172,50 +235,53 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
     Lq, Lk, ldS, thw, thw_q = sv["Lq"], sv["Lk"], sv["ldS"], sv["thw"], sv["thw_q"]
     M, Mq, hid, Co = B * N, B * Lq, spec.hidden, spec.dim_out
     dp = sv["dp"]
+    dp_a, dp_m = (dp[0], dp[1]) if dp is not None else (None, None)
     rps = Lq if dp is not None else 0
     dev = x.device
     g = {}
 
-    # one memset for every accumulate-into gradient buffer of the block (norm affine, biases, pool kernels)
     n_pool = 3 if spec.stride_q is not None and spec.stride_kv is not None else (2 if spec.stride_kv is not None else
                                                                                (1 if spec.stride_q is not None else 0))
-    zbuf = torch.zeros(4 * C + 3 * C + C + hid + 2 * Co + n_pool * 29 * d + 64, dtype=torch.float32, device=dev)
-    zoff = [0]
+    go = _GradOut(p, wc, dev, 4 * C + 3 * C + C + hid + 2 * Co + n_pool * 29 * d + 64)
+    # the second stream needs gradient storage that outlives the block (the arena); see _Fork
+    fork = _Fork(wc.side_stream() if go.arena is not None and hasattr(wc, "side_stream") else None)
 
-    def zeros(n):
-        lo = zoff[0]
-        zoff[0] = lo + (n + 3) // 4 * 4          # keep 16-byte alignment for the vectorised kernels
-        return zbuf[lo: lo + n]
+    def zeros(name, n):
+        return go.small(p[name], n)
 
-    def wgrad(a_rows, b_rows, m_out, n_out, ktok, bias_name):
+    def wgrad(a_rows, b_rows, wname, m_out, n_out, ktok, bias_name):
         # dW[m_out, n_out] = a_rows^T . b_rows   (both token-major: contraction over rows); the bias gradient
         # sum_rows a_rows comes out of the same kernel (one extra narrow MMA per k-step against an all-ones tile)
-        g[bias_name] = zeros(m_out)
-        return K.gemm(a_rows, b_rows, M=m_out, N=n_out, K=ktok, a_kmajor=False, b_kmajor=False, lda=m_out, ldb=n_out,
-                      out_dtype=torch.float32, split_k=_split_k(m_out, n_out, ktok), rowsum=g[bias_name])
+        g[bias_name] = zeros(bias_name, m_out)
+        out = go.matrix(p[wname])
+        sk = _split_k(m_out, n_out, ktok)
+        g[wname] = fork.run(lambda: K.gemm(a_rows, b_rows, M=m_out, N=n_out, K=ktok, a_kmajor=False, b_kmajor=False, lda=m_out,
+                                           ldb=n_out, out=None if out is None else out.view(m_out, n_out), out_dtype=torch.float32,
+                                           accumulate=out is not None and sk > 1, split_k=sk, rowsum=g[bias_name]),
+                            a_rows, b_rows)
 
     dy = dy.contiguous().view(Mq, Co)
-    g2 = K.cast16(dy, wc.grad, row_scale=dp, rows_per_scale=rps)            # gradient entering the (drop-path scaled) MLP branch
+    g2 = K.cast16(dy, wc.grad, row_scale=dp_m, rows_per_scale=rps)            # gradient entering the (drop-path scaled) MLP branch
     # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
+    wgrad(g2, sv["hdn"], "mlp.fc2.weight", Co, hid, Mq, "mlp.fc2.bias")
     dZ = K.gemm(g2, wc.w(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, b_kmajor=False, act=2, Z=sv["Z"])
-    g["mlp.fc2.weight"] = wgrad(g2, sv["hdn"], Co, hid, Mq, "mlp.fc2.bias")
+    wgrad(dZ, sv["xn2"], "mlp.fc1.weight", hid, C, Mq, "mlp.fc1.bias")
     dxn2 = K.gemm(dZ, wc.w(p["mlp.fc1.weight"]), M=Mq, N=C, K=hid, b_kmajor=False)
-    g["mlp.fc1.weight"] = wgrad(dZ, sv["xn2"], hid, C, Mq, "mlp.fc1.bias")
     del dZ
-    g["norm2.weight"], g["norm2.bias"] = zeros(C), zeros(C)
+    g["norm2.weight"], g["norm2.bias"] = zeros("norm2.weight", C), zeros("norm2.bias", C)
     if spec.dim != spec.dim_out:
         gp = g2 if dp is None else K.cast16(dy, wc.grad)                     # the re-based residual is not drop-path scaled
+        wgrad(gp, sv["xn2"], "proj.weight", Co, C, Mq, "proj.bias")
         K.gemm(gp, wc.w(p["proj.weight"]), M=Mq, N=C, K=Co, b_kmajor=False, out=dxn2, accumulate=True)
-        g["proj.weight"] = wgrad(gp, sv["xn2"], Co, C, Mq, "proj.bias")
         dx1, g1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
-                                  copy16=wc.grad, row_scale=dp, rows_per_scale=rps)
+                                  copy16=wc.grad, row_scale=dp_a, rows_per_scale=rps)
     else:
         dx1, g1 = K.layernorm_bwd(dxn2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], g["norm2.weight"], g["norm2.bias"],
-                                  add=dy, copy16=wc.grad, row_scale=dp, rows_per_scale=rps)
+                                  add=dy, copy16=wc.grad, row_scale=dp_a, rows_per_scale=rps)
     del dxn2, g2
     # ---- attention output projection (g1 = drop-path scaled 16-bit copy of dx1, written by the LayerNorm backward) ------
+    wgrad(g1, sv["o"], "attn.proj.weight", C, C, Mq, "attn.proj.bias")
     do = K.gemm(g1, wc.w(p["attn.proj.weight"]), M=Mq, N=C, K=C, b_kmajor=False)       # (B, Lq, heads, d)
-    g["attn.proj.weight"] = wgrad(g1, sv["o"], C, C, Mq, "attn.proj.bias")
     del g1
     # ---- residual path -----------------------------------------------------------------------------------
     if spec.stride_q is None or spec.kind in ("spatial", "temporal"):
@@ -263,7 +329,7 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
 
     def pool_ln_backward(dt, key, nname):
         pre, mean, rstd = sv[key]
-        g[nname + ".weight"], g[nname + ".bias"] = zeros(d), zeros(d)
+        g[nname + ".weight"], g[nname + ".bias"] = zeros(nname + ".weight", d), zeros(nname + ".bias", d)
         return K.layernorm_bwd(dt, pre, mean, rstd, p[nname + ".weight"], g[nname + ".weight"], g[nname + ".bias"], dx_dtype=wc.grad)
 
     def pool_backward(items, stride, transposed, grid_out):
@@ -272,22 +338,28 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         L = grid_out[0] * grid_out[1] * grid_out[2]
         dense = (h * L * d, L * d, d)
         (du, slot, wname) = items[0]
-        sec = None
+        du2 = slot2 = wname2 = None
+        for _, _, wn in items:
+            g[wn] = zeros(wn, 27 * d).view_as(p[wn])
         if len(items) == 2:
             du2, slot2, wname2 = items[1]
+
+        def weight_grads():
+            if transposed:
+                assert len(items) == 1
+                K.dwconv_wgrad(sv["qkv"], qs, slot * C, thw, du, dense, 0, grid_out, B, h, d, stride, g[wname])
+            else:
+                sec = None
+                if len(items) == 2:
+                    sec = dict(small=du2, small_off=0, big=sv["qkv"], big_off=slot2 * C, dw=g[wname2])
+                K.dwconv_wgrad(du, dense, 0, grid_out, sv["qkv"], qs, slot * C, thw, B, h, d, stride, g[wname], second=sec)
+
+        fork.run(weight_grads, du, du2)
+        sec = None
+        if len(items) == 2:
             sec = dict(inp=du2, in_off=0, w=p[wname2], out=dqkv, out_off=slot2 * C)
         K.dwconv(du, dense, 0, B, h, d, grid_out, stride, p[wname], transposed=not transposed, out=dqkv, out_strides=qs,
                  out_off=slot * C, thw_out=thw, second=sec)
-        for _, _, wn in items:
-            g[wn] = zeros(27 * d).view_as(p[wn])
-        if transposed:
-            assert len(items) == 1
-            K.dwconv_wgrad(sv["qkv"], qs, slot * C, thw, du, dense, 0, grid_out, B, h, d, stride, g[wname])
-        else:
-            sec = None
-            if len(items) == 2:
-                sec = dict(small=du2, small_off=0, big=sv["qkv"], big_off=slot2 * C, dw=g[wname2])
-            K.dwconv_wgrad(du, dense, 0, grid_out, sv["qkv"], qs, slot * C, thw, B, h, d, stride, g[wname], second=sec)
 
     if pooled_q:
         qname = "attn.upsample_q.weight" if dec else "attn.pool_q.weight"
@@ -296,11 +368,12 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         pool_backward([(pool_ln_backward(dk_t, "k_pool", "attn.norm_k"), 1, "attn.pool_k.weight"),
                        (pool_ln_backward(dv_t, "v_pool", "attn.norm_v"), 2, "attn.pool_v.weight")], spec.stride_kv, False, k.thw)
     # ---- qkv projection and norm1 ---------------------------------------------------------------------------
+    wgrad(dqkv, sv["xn1"].view(M, C), "attn.qkv.weight", 3 * C, C, M, "attn.qkv.bias")
     dxn1 = K.gemm(dqkv, wc.w(p["attn.qkv.weight"]), M=M, N=C, K=3 * C, b_kmajor=False)
-    g["attn.qkv.weight"] = wgrad(dqkv, sv["xn1"].view(M, C), 3 * C, C, M, "attn.qkv.bias")
-    g["norm1.weight"], g["norm1.bias"] = zeros(C), zeros(C)
+    g["norm1.weight"], g["norm1.bias"] = zeros("norm1.weight", C), zeros("norm1.bias", C)
     dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
                          add=dx_skip.view(B, N, C))
+    fork.join()
     return dx, g
 
 

@@ -9,6 +9,7 @@ are *parameter holders only*: their ``forward`` is never called — every operat
 hand-written CUDA through ``csts_b200.kernels``; there is no PyTorch or CPU fallback.
 """
 import math
+import os
 from functools import partial
 
 import torch
@@ -18,6 +19,7 @@ from torch.nn.init import trunc_normal_
 from .. import kernels as K
 from .block import BlockFn, block_forward, block_param_names
 from .build import MODEL_REGISTRY
+from .grad_arena import GradArena, grad_slot
 from .plan import build_plan
 from .weights import WeightCache, precision_of
 
@@ -159,8 +161,9 @@ class FramePoolFn(torch.autograd.Function):
         dtok_t = K.gemm(g, ctx.wc.w(weight), M=B * T, N=Kd, K=O, b_kmajor=False, ldb=Kd, out_dtype=torch.float32)   # (B*T, c, hw)
         dtok = K.permute_021(dtok_t, B * T, Cn, 64, torch.float32)                                                  # -> (B*T, hw, c)
         db = torch.zeros(O, dtype=torch.float32, device=dout.device)
+        slot = grad_slot(ctx.wc, weight)          # 151 MB: written straight into the gradient arena
         dw = K.gemm(g, a.view(B * T, Kd), M=O, N=Kd, K=B * T, a_kmajor=False, b_kmajor=False, lda=O, ldb=Kd, out_dtype=torch.float32,
-                    rowsum=db)
+                    out=None if slot is None else slot.view(O, Kd), rowsum=db)
         return None, dtok.view(B, N, Cn), dw.view(weight.shape), db
 
 
@@ -331,17 +334,26 @@ class CSTS(nn.Module):
 
     def _draw_drop_path(self, batch, device):
         """DropPath (common.py:46-59): per-sample keep mask scaled by 1/keep_prob, floor(keep + U[0,1)) / keep.
-        The masks of every block of the step are drawn in one shot (three launches instead of four per block)."""
+        A block applies it twice with independent draws — to the attention branch and to the MLP branch
+        (attention.py:242 and :247) — so every block gets two rows.  The masks of all blocks of the step are drawn in
+        one shot (three launches instead of four per DropPath call)."""
         if self._dp_site is None:
             blks = [m for m in self.modules() if isinstance(m, Block) and m.spec.drop_path > 0.0]
             self._dp_site = {id(b): i for i, b in enumerate(blks)}
-            self._dp_keep = torch.tensor([[1.0 - b.spec.drop_path] for b in blks], dtype=torch.float32)
+            self._dp_keep = torch.tensor([[[1.0 - b.spec.drop_path]] for b in blks], dtype=torch.float32)
         if not self._dp_site:
             return
         if self._dp_keep.device != device:
             self._dp_keep = self._dp_keep.to(device)
-        u = torch.rand(len(self._dp_site), batch, dtype=torch.float32, device=device)
-        self._dp_scales = torch.floor(u.add_(self._dp_keep)).div_(self._dp_keep)
+        u = torch.rand(len(self._dp_site), 2, batch, dtype=torch.float32, device=device)
+        self._dp_scales = torch.floor(u.add_(self._dp_keep)).div_(self._dp_keep)        # (blocks, 2 branches, B)
+
+    def _ensure_arena(self):
+        """Gradient arena of the replica (host/grad_arena.py), (re)built when the parameters moved."""
+        wc = self._wc
+        params = list(self.parameters())
+        if wc.arena is None or not wc.arena.matches(params):
+            wc.arena = GradArena(params) if os.environ.get("CSTS_GRAD_ARENA", "1") == "1" else None
 
     def forward(self, x, y, return_embed=False, return_spatial_attn=False, return_temporal_attn=False):
         video = x[0] if isinstance(x, (list, tuple)) else x
@@ -351,8 +363,11 @@ class CSTS(nn.Module):
         wc = self._wc
         if self.training:
             self._draw_drop_path(video.shape[0], video.device)
-            if torch.is_grad_enabled():
-                wc.begin_training_step()
+        if self.training and torch.is_grad_enabled():
+            wc.begin_training_step()
+            self._ensure_arena()
+        else:
+            wc.begin_inference()
         x = PatchEmbedFn.apply(wc, video, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
                                self.pos_embed_spatial, self.pos_embed_temporal)
         y = PatchEmbedFn.apply(wc, audio, self.patch_embed_audio.proj.weight, self.patch_embed_audio.proj.bias,

@@ -108,36 +108,49 @@ def allreduce_gradients(params, bucket_bytes=256 << 20):
 class OverlappedGradSync:
     """Gradient averaging overlapped with backward, as plain stream-ordered work (graph-capturable).
 
-    Parameters are split into groups in reverse registration order (~ the order backward finishes
-    them).  A post-accumulate-grad hook counts down each group; when a group is complete its
-    gradients are packed and all-reduced (NCCL, AVG) on a side stream while backward keeps running on
-    the main stream.  `finish()` joins the side stream before the clip / optimizer step.  The three
-    151 MB frame-pool kernels become ready after the decoder + fusion backward (~1/3 of the way), so
-    their exchange hides behind the encoder backward.
+    Every parameter gradient lives in the replica's GradArena (host/grad_arena.py), laid out in reverse
+    registration order — the order backward produces them — so a bucket is a contiguous slice of the arena and is
+    all-reduced IN PLACE: no packing copy, no re-pointing of ``p.grad``, and no buffer whose lifetime spans two
+    streams (the arena is persistent).  A post-accumulate-grad hook counts down each bucket; when it is complete
+    its slice is all-reduced (NCCL, AVG) on a side stream while backward keeps running on the main stream.
+    ``finish()`` joins the side stream before the clip / optimizer step.  Buckets are ~32 MB except that a large
+    tensor (the three 151 MB frame-pool kernels, ready after the decoder + fusion backward) closes its own, so only
+    the last small bucket of early-encoder gradients is exposed after backward ends.
     """
 
-    def __init__(self, model, group_bytes=(64 << 20, 512 << 20, 1 << 40)):
+    def __init__(self, model, bucket_bytes=32 << 20):
+        self.model = model
+        self.bucket_bytes = bucket_bytes
         self.params = [p for p in model.parameters() if p.requires_grad][::-1]
-        self.groups, cur, size, gi = [], [], 0, 0
-        for p in self.params:
-            cur.append(p)
-            size += p.numel() * 4
-            if size >= group_bytes[min(gi, len(group_bytes) - 1)]:
-                self.groups.append(cur)
-                cur, size, gi = [], 0, gi + 1
-        if cur:
-            self.groups.append(cur)
-        self.group_of = {id(p): g for g, ps in enumerate(self.groups) for p in ps}
-        self.pending = [0] * len(self.groups)
+        self.arena = None
+        self.groups, self.ranges, self.group_of, self.pending = [], [], {}, []
         self.stream = None
         self.enabled = False
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
+    def _bind(self, arena):
+        self.arena = arena
+        self.groups, cur, size = [], [], 0
+        for p in self.params:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= self.bucket_bytes:
+                self.groups.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.groups.append(cur)
+        self.ranges = [arena.range_of(g) for g in self.groups]
+        self.group_of = {id(p): g for g, ps in enumerate(self.groups) for p in ps}
+
     def start(self):
-        """Call right before loss.backward()."""
+        """Call right before loss.backward() (after the forward pass, which creates the arena)."""
         if get_world_size() == 1:
             return
+        arena = getattr(getattr(self.model, "_wc", None), "arena", None)
+        assert arena is not None, "OverlappedGradSync needs the model's gradient arena (CSTS_GRAD_ARENA=1, training forward first)"
+        if arena is not self.arena:
+            self._bind(arena)
         if self.stream is None:
             self.stream = torch.cuda.Stream()
         self.pending = [len(g) for g in self.groups]
@@ -146,22 +159,14 @@ class OverlappedGradSync:
     def _hook(self, param):
         if not self.enabled:
             return
+        self.arena.adopt(param)          # no-op for gradients written in place; a small copy for the others
         g = self.group_of[id(param)]
         self.pending[g] -= 1
         if self.pending[g] == 0:
-            self._reduce(self.groups[g])
-
-    def _reduce(self, group):
-        main = torch.cuda.current_stream()
-        self.stream.wait_stream(main)
-        with torch.cuda.stream(self.stream):
-            flat = torch.cat([p.grad.reshape(-1) for p in group])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            off = 0
-            for p in group:
-                n = p.numel()
-                p.grad = flat[off: off + n].view_as(p)
-                off += n
+            lo, hi = self.ranges[g]
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.arena.flat[lo:hi], op=dist.ReduceOp.AVG)
 
     def finish(self):
         """Call after loss.backward(): joins the exchange before gradients are consumed."""

@@ -71,7 +71,9 @@ class KLDiv(nn.Module):
 
     def forward(self, pred, target=None):
         if target is None:
-            raise NotImplementedError("uniform-prior KLDiv (target=None) is not used by the CSTS train loop")
+            # uniform prior (losses.py:67-71): sum p log p - log(1/HW), i.e. the same divergence against q = 1/HW
+            B, _, T, H, W = pred.shape
+            target = torch.full((B, T, H, W), 1.0 / (H * W), dtype=torch.float32, device=pred.device)
         src = getattr(pred, "_csts_source", None)
         if src is not None:
             logits, temperature = src

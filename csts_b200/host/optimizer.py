@@ -37,6 +37,7 @@ class FusedClipAdamW(torch.optim.AdamW):
 
     # ---- state -------------------------------------------------------------------------------------------
     def _init_state(self):
+        loaded_step = None
         for group in self.param_groups:
             for p in group["params"]:
                 st = self.state[p]
@@ -45,8 +46,15 @@ class FusedClipAdamW(torch.optim.AdamW):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 elif st["step"] is not self._step:                            # state loaded from a checkpoint
-                    self._step.fill_(float(st["step"]))
+                    if loaded_step is None:
+                        loaded_step = float(st["step"])                       # all parameters step together: read it once
                     st["step"] = self._step
+        if loaded_step is not None:
+            self._step.fill_(loaded_step)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._table_key = None        # the moment buffers were replaced: the pointer table must be rebuilt
 
     def _build_table(self):
         """Device array of csts_mt_tensor (64 bytes each) + the chunk list.  Rebuilt when any pointer moved."""
@@ -65,7 +73,7 @@ class FusedClipAdamW(torch.optim.AdamW):
                 ti = len(rows)
                 rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), w16_ptr,
                              p.numel(), wd_bits | (gi << 32), w16_dt])
-                key.append((p.data_ptr(), p.grad.data_ptr(), w16_ptr))
+                key.append((p.data_ptr(), p.grad.data_ptr(), w16_ptr, st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()))
                 chunks.extend([ti, c] for c in range((p.numel() + chunk - 1) // chunk))
         return rows, chunks, tuple(key)
 

@@ -64,9 +64,19 @@ def make_grad_scaler(cfg, **kw):
     return torch.amp.GradScaler("cuda", enabled=bool(cfg.TRAIN.MIXED_PRECISION), **kw)
 
 
-def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, grad_sync=None, scaler=None):
+def check_nan_losses(loss):
+    """slowfast/utils/misc.py:26-33 — raises on a NaN loss.  Reads the loss on the host (one sync), which is why the
+    hot step only does it on request."""
+    import math
+    from datetime import datetime
+    if math.isnan(float(loss)):
+        raise RuntimeError("ERROR: Got NaN losses {}".format(datetime.now()))
+
+
+def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, grad_sync=None, scaler=None, check_nan=False):
     """Forward, loss, backward, [gradient exchange], clip, optimizer step.  Returns the (device) loss tensor;
-    no host sync.  With a DDP-wrapped model the exchange happens inside backward (DDP reducer); for an
+    no host sync unless check_nan (the reference loop's check_nan_losses, tools/train_avgaze_net.py:95; not
+    available while capturing a CUDA graph).  With a DDP-wrapped model the exchange happens inside backward (DDP reducer); for an
     un-wrapped replica pass grad_sync (e.g. distributed.allreduce_gradients) to average gradients here.
     `scaler` is the reference loop's GradScaler (lines 99-109: scale(loss).backward(), unscale_, clip, step,
     update); with the fused AdamW none of its calls synchronises the host, so the step stays graph-capturable."""
@@ -77,6 +87,8 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, 
             else:
                 group["lr"] = lr
     loss, _, _, _ = compute_loss(cfg, model, inputs, audio_frames, labels_hm)
+    if check_nan:
+        check_nan_losses(loss)
     optimizer.zero_grad(set_to_none=True)
     scaling = scaler is not None and scaler.is_enabled()
     assert scaling or not cfg.TRAIN.MIXED_PRECISION, "TRAIN.MIXED_PRECISION stores fp16 gradients: pass make_grad_scaler(cfg)"
@@ -89,12 +101,18 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, 
         root.backward()
         if grad_sync is not None:
             grad_sync()
+    clip_val = getattr(cfg.SOLVER, "CLIP_GRAD_VAL", None)
     if hasattr(optimizer, "clip_and_step"):          # FusedClipAdamW: lines 101-109 of the reference loop in two launches
+        if clip_val:
+            raise NotImplementedError("SOLVER.CLIP_GRAD_VAL (element-wise clipping, tools/train_avgaze_net.py:103-104) is not "
+                                      "fused: construct the optimizer with fused_clip=False")
         optimizer.clip_and_step(cfg.SOLVER.CLIP_GRAD_L2NORM or 0.0, scaler if scaling else None)
         return loss.detach()
     if scaling:
         scaler.unscale_(optimizer)
-    if cfg.SOLVER.CLIP_GRAD_L2NORM:
+    if clip_val:                                       # takes priority over the norm clip, as in the reference (:103-106)
+        torch.nn.utils.clip_grad_value_(model.parameters(), clip_val)
+    elif cfg.SOLVER.CLIP_GRAD_L2NORM:
         torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM, foreach=True)
     if scaling:
         scaler.step(optimizer)
@@ -190,4 +208,8 @@ class GraphedTrainStep:
         if inputs is not None:
             self._load(inputs, audio_frames, labels_hm)
         self.graph.replay()
+        if not hasattr(self.optimizer, "clip_and_step"):
+            # torch's optimizer moved the parameters; the captured casts refresh the 16-bit copies only at the top of the
+            # NEXT replay, so an eager (evaluation) forward in between must rebuild them
+            self.model._wc.invalidate()
         return self.loss

@@ -16,6 +16,7 @@ Precision modes (one 16-bit type per mode: a tcgen05 kind::f16 MMA cannot mix f1
   10 mantissa bits bring the gradient within ~1e-2 of fp32; the caller scales the loss
   (``scaler.scale(loss).backward()``) exactly as the reference loop does.
 """
+import os
 from collections import namedtuple
 
 import torch
@@ -32,21 +33,51 @@ def precision_of(cfg):
 
 
 class WeightCache:
+    """Per-model context handed to every autograd node of the path: the precision mode, the 16-bit operand copies
+    of the weights, the gradient arena (host/grad_arena.py) and the second stream of the backward pass."""
+
     def __init__(self, precision=BF16):
         self._store = {}
         self.act, self.grad = precision
         self._gen = 0            # training-step generation: copies made in an earlier step are not trusted
         self._fresh = False      # set by the fused optimizer step, which rewrites the copies itself
+        self._dirty = False      # a training step ran since the copies were last rebuilt for a non-training forward
+        self.arena = None        # GradArena, created by the model at its first training forward
+        self._side = None
+        self.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
+
+    def side_stream(self):
+        """Stream of the weight-gradient branch of the backward pass (block.py::_Fork), or None when disabled."""
+        if not self.fork_backward:
+            return None
+        if self._side is None or self._side.device != torch.cuda.current_device():
+            self._side = torch.cuda.Stream()
+        return self._side
 
     def begin_training_step(self):
         """Called at the top of every training forward.  A parameter's version counter is not a reliable
         "changed" signal (torch's *fused* optimizers update parameters without bumping it), so in training the
         copies are rebuilt once per step — unless the fused clip+AdamW step (host/optimizer.py) has just
         rewritten them, which it announces through after_fused_step()."""
+        self._dirty = True
         if self._fresh:
             self._fresh = False
         else:
             self._gen += 1
+
+    def begin_inference(self):
+        """Called at the top of every non-training forward: after a training step the parameters have moved behind
+        the version counter's back, so the copies are rebuilt once before they are used for evaluation."""
+        if self._dirty:
+            self._dirty = False
+            self._fresh = False
+            self._gen += 1
+
+    def invalidate(self):
+        """The parameters changed outside the cache's knowledge (a CUDA-graph replay of a step that does not refresh the
+        copies itself, a checkpoint load): rebuild every copy at its next use."""
+        self._gen += 1
+        self._fresh = False
 
     def _get(self, param, kind, make):
         key = (id(param), kind)
@@ -55,17 +86,19 @@ class WeightCache:
         if hit is not None and hit[0] == ver:
             return hit[1]
         with torch.no_grad():
-            val = make(param.detach())
+            # an existing copy is refreshed IN PLACE: its address is baked into captured CUDA graphs and into the
+            # fused optimizer's pointer table, both of which keep rewriting / reading it
+            val = make(param.detach(), hit[1] if hit is not None and hit[0][0] == ver[0] else None)
         self._store[key] = (ver, val)
         return val
 
     def w(self, param):
         """Linear weight (N, K) f32 -> 16-bit (N, K)."""
-        return self._get(param, "w", lambda p: K.cast16(p.reshape(p.shape[0], -1), self.act))
+        return self._get(param, "w", lambda p, out: K.cast16(p.reshape(p.shape[0], -1), self.act, out=out))
 
     def w_padded(self, param, kp):
         """Conv weight (N, ...) f32 -> 16-bit (N, kp), zero padded columns (patch embed)."""
-        return self._get(param, ("pad", kp), lambda p: K.cast16(p.reshape(p.shape[0], -1), self.act, ld_out=kp))
+        return self._get(param, ("pad", kp), lambda p, out: K.cast16(p.reshape(p.shape[0], -1), self.act, ld_out=kp, out=out))
 
     # ---- fused optimizer step (host/optimizer.py): the AdamW kernel writes the 16-bit copy itself -----------
     def bound_copy(self, param):

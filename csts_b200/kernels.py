@@ -127,14 +127,18 @@ def softmax_bwd(P, dP, n, scale, dtype=None):
     return dS
 
 
-def cast16(src, dtype, ld_out=None, row_scale=None, rows_per_scale=0):
+def cast16(src, dtype, ld_out=None, row_scale=None, rows_per_scale=0, out=None):
     """f32 (rows, cols) -> bf16 / f16 (rows, ld_out), zero padded; optional per-row-group scale
-    (row m is multiplied by row_scale[m // rows_per_scale])."""
+    (row m is multiplied by row_scale[m // rows_per_scale]).  `out`: an existing destination to overwrite."""
     src2 = src.reshape(-1, src.shape[-1]) if src.dim() > 1 else src.reshape(1, -1)
     rows, cols = src2.shape
     ld = cols if ld_out is None else ld_out
-    dst = torch.empty((rows, ld), dtype=dtype, device=src.device)
+    if out is not None and (out.dtype != dtype or out.numel() != rows * ld or not out.is_contiguous()):
+        out = None
+    dst = out.view(rows, ld) if out is not None else torch.empty((rows, ld), dtype=dtype, device=src.device)
     call("csts_cast16", ptr(src2), ptr(dst), dt(dst), rows, cols, ld, ptr(row_scale), rows_per_scale)
+    if out is not None:
+        return out
     return dst if ld_out is not None else dst.reshape(src.shape)
 
 

@@ -297,22 +297,27 @@ def skip_path(x, thw, kind, stride_q):
     return t.squeeze(1)
 
 
-def block(sd, name, x, thw, want_attn=False, spec=None):
+def block(sd, name, x, thw, want_attn=False, spec=None, drop=None):
     """One transformer block (any of the four kinds).  ref: attention.py:238-248, :469-479;
-    av_attention.py:229-250, :450-473.  DropPath is identity (rate 0 / eval) in the oracle.
+    av_attention.py:229-250, :450-473.  DropPath (ref common.py:46-59) is identity unless `drop` = (attention-branch
+    scale (B,), MLP-branch scale (B,)) is given: the two per-sample factors mask / keep_prob that the reference draws
+    with torch.rand at attention.py:242 and :247, supplied by the caller so a run can be reproduced exactly.
     `spec` = (kind, dim, dim_out, heads, stride_q, stride_kv) overrides the ARCH row (unit tests)."""
     kind, dim, dim_out, heads, sq, skv = spec if spec is not None else ARCH[name][1:]
     p = name + "."
+    da = dm = None
+    if drop is not None:
+        da, dm = (t.reshape(-1, 1, 1).to(x.dtype) for t in drop)
     xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], EPS_BLOCK),"xn")
     res = attention(sd, p + "attn.", xn, thw, heads, sq, skv, kind, want_attn)
-    x = skip_path(x, thw, kind, sq) + res[0]
+    x = skip_path(x, thw, kind, sq) + (res[0] if da is None else res[0] * da)
     xn = rnd(F.layer_norm(x, (dim,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], EPS_BLOCK),"xn")
     # decoder MLP hidden is 4*dim_out (ref attention.py:444) — implied by the weight shapes
     hid = rnd_f(_gelu(rnd_b(F.linear(xn, rnd_f(sd[p + "mlp.fc1.weight"],"w"), sd[p + "mlp.fc1.bias"]),"dZ")),"h")     # exact erf
     mlp = rnd_b(F.linear(hid, rnd_f(sd[p + "mlp.fc2.weight"],"w"), sd[p + "mlp.fc2.bias"]),"g2")
     if dim != dim_out:
         x = rnd_b(F.linear(xn, rnd_f(sd[p + "proj.weight"],"wproj"), sd[p + "proj.bias"]),"gproj")    # ref :245-246
-    x = x + mlp
+    x = x + (mlp if dm is None else mlp * dm)
     return (x, res[1], res[2]) if want_attn else (x, res[1])
 
 
@@ -350,15 +355,17 @@ def audio_rescale(p, thw):
 
 
 def csts_forward(sd, video, audio, return_embed=False, return_intermediates=False, spatial_audio_attn=False,
-                 return_spatial_attn=False, return_temporal_attn=False):
+                 return_spatial_attn=False, return_temporal_attn=False, drop_scales=None):
     """CSTS.forward.  ref: custom_multimodal_builder.py:343-498 (CLS_EMBED_ON False, SEP_POS_EMBED True,
     dropout 0; `spatial_audio_attn` = MVIT.SPATIAL_AUDIO_ATTN, default False in every shipped YAML).
 
     video (B,3,8,256,256), audio (B,1,8,256,256) -> logits (B,1,8,64,64) [, v (B,256), a (B,256)]
     With return_spatial_attn / return_temporal_attn (and no return_embed): [logits, spatial_attn?, temporal_attn?]
     (ref :483-491), the attention probabilities of the two fusion blocks.
+    drop_scales: {block name: (attention scale (B,), MLP scale (B,))} — DropPath factors of a training forward.
     """
     inter = {}
+    drop_scales = drop_scales or {}
     x = patch_embed(sd, "patch_embed", video)
     y = patch_embed(sd, "patch_embed_audio", audio)
     B = x.shape[0]
@@ -371,7 +378,7 @@ def csts_forward(sd, video, audio, return_embed=False, return_intermediates=Fals
     skips = [(x, thw)]
     inter["stem_video"], inter["stem_audio"] = x, y
     for i in range(16):                                   # ref :386-411 (interleaving is cosmetic)
-        x, thw = block(sd, f"blocks.{i}", x, thw)
+        x, thw = block(sd, f"blocks.{i}", x, thw, drop=drop_scales.get(f"blocks.{i}"))
         if i in (0, 2, 13):
             skips.append((x, thw))
     for i in range(4):
@@ -462,13 +469,13 @@ def kldiv_egonce(logits, v, a, labels_hm, alpha=0.05):
     return kld + alpha * nce, kld, nce
 
 
-def loss_and_grads(sd, video, audio, labels_hm, alpha=0.05, loss_scale=1.0):
+def loss_and_grads(sd, video, audio, labels_hm, alpha=0.05, loss_scale=1.0, drop_scales=None):
     """Forward + loss + autograd backward over every tensor in `sd` (fp32).  Returns
     (loss, kld, nce, logits, grads{name: tensor}).  loss_scale mirrors GradScaler (backward runs on
     loss_scale * loss, the returned gradients are unscaled); it only matters under EMULATE_BF16 with an
     fp16 BWD_DTYPE."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    logits, v, a = csts_forward(leaves, video, audio, return_embed=True)
+    logits, v, a = csts_forward(leaves, video, audio, return_embed=True, drop_scales=drop_scales)
     loss, kld, nce = kldiv_egonce(logits, v, a, labels_hm, alpha)
     names = list(leaves)
     gs = torch.autograd.grad(loss * loss_scale, [leaves[n] for n in names], allow_unused=True)

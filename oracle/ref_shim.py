@@ -18,11 +18,32 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CSTS_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """The reference tree: $CSTS_REFERENCE_ROOT, else /root/reference (the builder container), else baseline/_ref —
+    the unmodified `slowfast` package as `pip install --no-deps --target baseline/_ref /root/reference` lays it down
+    (git-ignored; it travels to the GPU box with the repo snapshot, where /root/reference does not exist)."""
+    cands = [os.environ.get("CSTS_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "slowfast", "models")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "slowfast", "models"))
+
+
+def config_path(config):
+    """The reference YAML; the pip-installed package carries no configs/, the repo's copies hold identical keys and
+    values (tests/test_host_cpu.py asserts that whenever both are present)."""
+    p = os.path.join(REFERENCE_ROOT, "configs", config)
+    return p if os.path.exists(p) else os.path.join(_REPO, "configs", config)
 
 
 class _Registry(dict):
@@ -45,6 +66,10 @@ class _Registry(dict):
         if name not in self:
             raise KeyError(f"No object named '{name}' found in '{self._name}' registry!")
         return self[name]
+
+    @property
+    def _obj_map(self):          # fvcore keeps its table under this name (INTEGRATION.md's binding line writes to it)
+        return self
 
 
 class _CfgNode(dict):
@@ -170,7 +195,7 @@ def reference_cfg(config="Ego4D/CSTS_Ego4D_Gaze_Forecast.yaml", overrides=()):
     install()
     from slowfast.config.defaults import get_cfg
     cfg = get_cfg()
-    cfg.merge_from_file(os.path.join(REFERENCE_ROOT, "configs", config))
+    cfg.merge_from_file(config_path(config))
     base = ["NUM_GPUS", 0, "MODEL.LOSS_FUNC", "kldiv+egonce", "MVIT.DROPPATH_RATE", 0.0]
     cfg.merge_from_list(base + list(overrides))
     return cfg

@@ -1,0 +1,146 @@
+"""The drop-in binding, EXECUTED: the unmodified reference package (baseline/_ref or /root/reference, imported
+through oracle/ref_shim.py) with the two INTEGRATION.md lines applied builds the csts_b200 model through its own
+``slowfast.models.build_model(cfg)`` (build.py:18-47) from its own CfgNode, loads a ``state_dict`` written by the
+reference model, and runs the literal training-loop lines of ``tools/train_avgaze_net.py:70-109``."""
+import os
+
+import pytest
+import torch
+
+import csts_oracle as O
+import ref_shim
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_shim.reference_available(), reason="no reference tree (baseline/_ref)")]
+dev = torch.device("cuda", 0)
+
+
+@pytest.fixture()
+def bound_reference():
+    ref_shim.install()
+    import slowfast.models as sm
+    from csts_b200.host.csts import CSTS as CSTS_B200
+    original = sm.MODEL_REGISTRY.get("CSTS")
+    sm.MODEL_REGISTRY._obj_map["CSTS"] = CSTS_B200                      # INTEGRATION.md §1, line 2
+    yield sm, original, CSTS_B200
+    sm.MODEL_REGISTRY._obj_map["CSTS"] = original
+
+
+def _literal_steps(cfg, model, optimizer, batches, losses, frame_softmax, sim_matrix):
+    """tools/train_avgaze_net.py:70-109, verbatim apart from the loader / meter lines."""
+    scaler = torch.cuda.amp.GradScaler(enabled=cfg.TRAIN.MIXED_PRECISION)
+    out = []
+    for inputs, audio_frames, labels_hm in batches:
+        with torch.cuda.amp.autocast(enabled=cfg.TRAIN.MIXED_PRECISION):
+            preds = model(inputs, audio_frames, return_embed=True)
+            kldiv_fun = losses.get_loss_func('kldiv')
+            egonce_fun = losses.get_loss_func('egonce')
+            kldiv_fun = kldiv_fun()
+            egonce_fun = egonce_fun()
+            preds, v_embed, a_embed = preds
+            preds = frame_softmax(preds, temperature=2)
+            similarity = sim_matrix(v_embed, a_embed)
+            kldiv_loss = kldiv_fun(preds, labels_hm)
+            egonce_loss = egonce_fun(similarity)
+            loss = kldiv_loss + cfg.MODEL.LOSS_ALPHA * egonce_loss
+        optimizer.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.unscale_(optimizer)
+        if cfg.SOLVER.CLIP_GRAD_VAL:
+            torch.nn.utils.clip_grad_value_(model.parameters(), cfg.SOLVER.CLIP_GRAD_VAL)
+        elif cfg.SOLVER.CLIP_GRAD_L2NORM:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.SOLVER.CLIP_GRAD_L2NORM)
+        scaler.step(optimizer)
+        scaler.update()
+        out.append((loss.item(), kldiv_loss.item(), egonce_loss.item()))
+    return out
+
+
+def test_reference_build_model_builds_the_b200_model_and_its_loop_trains_it(bound_reference):
+    sm, RefCSTS, CSTS_B200 = bound_reference
+    from slowfast.models import losses as ref_losses
+    from slowfast.models import optimizer as ref_optim
+    from slowfast.utils.utils import frame_softmax as ref_frame_softmax, sim_matrix as ref_sim_matrix
+    cfg = ref_shim.reference_cfg(overrides=["NUM_GPUS", 1, "MVIT.DROPPATH_RATE", 0.0, "SOLVER.BASE_LR", 1e-4])
+    torch.manual_seed(0)
+    model = sm.build_model(cfg)                                           # the reference's own build.py:18-47
+    assert type(model) is CSTS_B200 and next(model.parameters()).is_cuda
+    torch.manual_seed(3)
+    ref_model = RefCSTS(cfg)                                              # the reference module (CPU) writes the checkpoint
+    sd = {k: v.clone() for k, v in ref_model.state_dict().items()}
+    assert list(sd) == list(model.state_dict())
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    batches = []
+    for s in range(3):
+        v, a, h = (t.to(dev) for t in O.synthetic_batch(2, seed=40 + s))
+        batches.append(([v], a, h))
+
+    # (1) the reference loop, the reference's torch losses and the reference's optimizer on the bound model
+    optimizer = ref_optim.construct_optimizer(model, cfg)
+    got = _literal_steps(cfg, model, optimizer, batches, ref_losses, ref_frame_softmax, ref_sim_matrix)
+
+    # (2) the same three steps through csts_b200.host.train_step (fused kernels for the loss lines) on a twin
+    from csts_b200.host import losses as b_losses
+    from csts_b200.host.build import build_model
+    from csts_b200.host.config import get_cfg
+    from csts_b200.host.train_step import train_step
+    from csts_b200.host.utils import frame_softmax as b_frame_softmax, sim_matrix as b_sim_matrix
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bcfg = get_cfg()
+    bcfg.merge_from_file(os.path.join(root, "configs", "Ego4D", "CSTS_Ego4D_Gaze_Forecast.yaml"))
+    bcfg.merge_from_list(["NUM_GPUS", 1, "MODEL.LOSS_FUNC", "kldiv+egonce", "MVIT.DROPPATH_RATE", 0.0, "SOLVER.BASE_LR", 1e-4])
+    twin = build_model(bcfg)
+    twin.load_state_dict(sd, strict=True)
+    twin.train()
+    topt = ref_optim.construct_optimizer(twin, cfg)
+    want = [train_step(bcfg, twin, topt, *b).item() for b in batches]
+    # the forward pass is deterministic: the first loss differs only by the loss kernels' summation order; later
+    # steps also see the f32 atomics order of the split-K weight gradients
+    assert abs(got[0][0] - want[0]) <= 2e-6 * abs(want[0]), (got[0], want[0])
+    for g, w in zip(got, want):
+        assert abs(g[0] - w) <= 1e-4 * abs(w), (got, want)
+    assert got[2][0] < got[0][0]                                          # and it trains
+
+    # (3) with the loss lines bound as well (second snippet) the literal loop IS train_step's sequence:
+    #     the first step's loss is bit-identical
+    third = build_model(bcfg)
+    third.load_state_dict(sd, strict=True)
+    third.train()
+    oopt = ref_optim.construct_optimizer(third, cfg)
+    bound = _literal_steps(cfg, third, oopt, batches, b_losses, b_frame_softmax, b_sim_matrix)
+    assert bound[0][0] == want[0], (bound[0], want[0])
+    for g, w in zip(bound, want):
+        assert abs(g[0] - w) <= 1e-4 * abs(w)
+
+
+def test_bound_model_matches_the_reference_model_on_the_same_gpu(bound_reference):
+    """Forward + kldiv+egonce + backward of the reference module (stock PyTorch eager, fp32, on this GPU) against the
+    bound csts_b200 model on the same weights and inputs: BASELINE.json's tolerances."""
+    sm, RefCSTS, CSTS_B200 = bound_reference
+    from slowfast.models import losses as ref_losses
+    from slowfast.utils.utils import frame_softmax, sim_matrix
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = ref_shim.reference_cfg(overrides=["NUM_GPUS", 1, "MVIT.DROPPATH_RATE", 0.0])
+    torch.manual_seed(5)
+    ref_model = RefCSTS(cfg).to(dev).train()
+    model = sm.build_model(cfg)
+    model.load_state_dict(ref_model.state_dict(), strict=True)
+    model.train()
+    v, a, h = (t.to(dev) for t in O.synthetic_batch(2, seed=77))
+
+    def run(m):
+        preds, ve, ae = m([v], a, return_embed=True)
+        p = frame_softmax(preds, temperature=2)
+        loss = ref_losses.get_loss_func("kldiv")()(p, h) + cfg.MODEL.LOSS_ALPHA * ref_losses.get_loss_func("egonce")()(sim_matrix(ve, ae))
+        m.zero_grad()
+        loss.backward()
+        return loss.item(), p.detach(), {n: q.grad.clone() for n, q in m.named_parameters()}
+
+    rl, rp, rg = run(ref_model)
+    bl, bp, bg = run(model)
+    assert abs(bl - rl) <= 1e-3 * abs(rl), (bl, rl)
+    assert (bp - rp).abs().max() <= 1e-2 and (bp - rp).abs().mean() <= 1e-3
+    num = sum((bg[n] - rg[n]).pow(2).sum().item() for n in rg)
+    den = sum(g.pow(2).sum().item() for g in rg.values())
+    assert (num / den) ** 0.5 <= 5e-2, (num / den) ** 0.5

@@ -56,7 +56,9 @@ def _worker(rank, world, port, q):
         (kld + cfg.MODEL.LOSS_ALPHA * nce).backward()
         num = sum((dp[n] - p.grad).pow(2).sum().item() for n, p in model.named_parameters())
         den = sum(p.grad.pow(2).sum().item() for p in model.parameters())
-        q.put((num / den) ** 0.5)
+        worst = max(((dp[n] - p.grad).norm() / p.grad.norm()).item() for n, p in model.named_parameters() if p.grad.norm() > 1e-7)
+        in_arena = all(model._wc.arena.owns(p.grad, p) for p in model.parameters())
+        q.put(((num / den) ** 0.5, worst, in_arena))
     dist.barrier()
     os._exit(0)
 
@@ -69,9 +71,13 @@ def test_two_gpu_gradients_match_global_batch():
     procs = [ctx.Process(target=_worker, args=(r, 2, 29641, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rel = q.get(timeout=300)
+    rel, worst, in_arena = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
-    print("global-batch vs data-parallel gradient, relative L2:", rel)
-    # both sides are bf16 pipelines with different batch tilings: rounding noise only
-    assert rel < 5e-2, rel
+    print("global-batch vs data-parallel gradient, relative L2:", rel, "worst tensor:", worst)
+    # Samples are independent through the network, so both sides evaluate bit-identical per-sample activations; only the
+    # f32 summation order over the batch (split-K atomics, the cross-rank reduction) differs.  A corrupted bucket — e.g.
+    # a gradient buffer recycled while the side-stream all-reduce still reads it — would show up in a single tensor.
+    assert in_arena, "a gradient was not written into the arena"
+    assert rel < 1e-3, rel
+    assert worst < 2e-2, worst

@@ -34,7 +34,7 @@ def test_repo_configs_load_and_build_the_same_plan(name):
         assert (r[1], r[2], r[3], r[4], r[5], r[6]) == (s.kind, s.dim, s.dim_out, s.heads, s.stride_q, s.stride_kv)
 
 
-@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+@pytest.mark.skipif(not os.path.isdir(os.path.join(ref_shim.REFERENCE_ROOT, "configs")), reason="reference tree (with configs/) not mounted")
 @pytest.mark.parametrize("name", CONFIGS)
 def test_reference_yaml_loads_unchanged_and_equals_repo_yaml(name):
     import yaml
@@ -129,10 +129,14 @@ def test_drop_path_masks_are_drawn_once_per_step(cpu_model):
     assert len(blocks) == 15 and all(id(b) in sites for b in blocks)
     for b in (blocks[0], blocks[7], blocks[-1]):
         sc = model._dp_scales[sites[id(b)]]
+        assert sc.shape == (2, 20000)                                 # attention branch, MLP branch (attention.py:242, :247)
         keep = 1.0 - b.spec.drop_path
         vals = torch.unique(sc)
         assert all(min(abs(v - 0.0), abs(v - 1.0 / keep)) < 1e-6 for v in vals.tolist())
         assert abs((sc > 0).float().mean().item() - keep) < 0.012
+        # the two branches of a block are dropped independently: P(both kept) = keep^2, not keep
+        both = ((sc[0] > 0) & (sc[1] > 0)).float().mean().item()
+        assert abs(both - keep * keep) < 0.012, (both, keep)
     assert abs(blocks[-1].spec.drop_path - 0.2) < 1e-6
 
 
@@ -169,13 +173,21 @@ def test_weight_cache_does_not_trust_version_counters():
     wc = WeightCache()
     calls = []
     p = torch.nn.Parameter(torch.zeros(2, 2))
-    make = lambda q: calls.append(1) or q.clone()
-    wc._get(p, "w", make)
+
+    def make(q, out):
+        calls.append(out)
+        if out is None:
+            return q.clone()
+        out.copy_(q)
+        return out
+
+    first = wc._get(p, "w", make)
     wc._get(p, "w", make)
     assert len(calls) == 1                       # same step, same version: cached
     wc.begin_training_step()
-    wc._get(p, "w", make)
+    again = wc._get(p, "w", make)
     assert len(calls) == 2                       # new step: rebuilt even though p._version is unchanged
+    assert calls[1] is first and again is first  # ... IN PLACE: captured graphs / the optimizer's pointer table hold its address
     wc._get(p, ("pad", 8), make)
     wc.after_fused_step()                        # the fused optimizer refreshed the plain copies, dropped the re-laid-out ones
     wc.begin_training_step()
@@ -183,6 +195,18 @@ def test_weight_cache_does_not_trust_version_counters():
     assert len(calls) == 3
     wc._get(p, ("pad", 8), make)
     assert len(calls) == 4
+    # evaluation after training: a non-training forward rebuilds the copies once, whatever the optimizer was
+    wc.begin_training_step()
+    wc._get(p, "w", make)
+    n = len(calls)
+    with torch.no_grad():
+        p.add_(1.0)                              # what torch's fused AdamW does: no version bump visible to the cache key
+    wc.begin_inference()
+    assert torch.equal(wc._get(p, "w", make), p.detach())
+    assert len(calls) == n + 1
+    wc.begin_inference()
+    wc._get(p, "w", make)
+    assert len(calls) == n + 1                   # a second evaluation forward hits the cache
 
 
 def test_cpu_forward_fails_loudly(cpu_model):
@@ -243,3 +267,109 @@ def test_nce_all_gather_gradient_equals_single_process_global_batch():
     torch.testing.assert_close(grad, w.grad, rtol=1e-5, atol=1e-6)     # the reference's ctx.rank = 0 bug would fail this
     assert reduced == 1.5
     assert gathered.flatten().tolist() == [0.0, 0.0, 1.0, 1.0]
+
+
+def test_grad_arena_layout_and_adoption():
+    """host/grad_arena.py: slots in reverse registration order, 16-byte aligned, a block's parameters contiguous;
+    adopt() moves a foreign gradient into its slot; views are fresh objects (autograd steals them without a copy)."""
+    from csts_b200.host.grad_arena import GradArena, grad_slot
+    ps = [torch.nn.Parameter(torch.randn(*s)) for s in [(3, 5), (7,), (2, 2, 2), (9,)]]
+    ar = GradArena(ps)
+    offs = [ar.slot[id(p)][0] for p in ps]
+    assert offs == sorted(offs, reverse=True) and all(o % 4 == 0 for o in offs)
+    assert ar.numel == 12 + 8 + 8 + 16 and ar.matches(ps) and not ar.matches(ps[:3])
+    assert ar.view(ps[0]).shape == (3, 5) and ar.view(ps[0]) is not ar.view(ps[0])
+    lo, hi = ar.range_of(ps[1:3])
+    assert (lo, hi) == (offs[2], offs[1] + 8)
+    assert ar.span(ps[1:3]).numel() == offs[1] + 7 - offs[2]
+    ps[1].grad = torch.arange(7.0)
+    assert not ar.owns(ps[1].grad, ps[1])
+    ar.adopt(ps[1])
+    assert ar.owns(ps[1].grad, ps[1]) and torch.equal(ar.flat[offs[1]: offs[1] + 7], torch.arange(7.0))
+
+    class WC:
+        arena = ar
+    assert grad_slot(WC, ps[1]) is None                      # already holds a gradient: autograd must accumulate
+    assert grad_slot(WC, ps[0]).data_ptr() == ar.flat.data_ptr() + 4 * offs[0]
+    assert grad_slot(WC, torch.nn.Parameter(torch.zeros(1))) is None
+    # a gradient written into the slot and handed to autograd is adopted as p.grad without a copy
+    x = ps[0]
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, w):
+            ctx.w = w
+            return w.sum()
+
+        @staticmethod
+        def backward(ctx, g):
+            out = grad_slot(WC, ctx.w)
+            out.fill_(2.0)
+            return out
+    Fn.apply(x).backward()
+    assert ar.owns(x.grad, x) and float(x.grad.sum()) == 30.0
+
+
+def _k400_like_checkpoint(model_state, tmp_path):
+    """A pre-trained-MViT-like checkpoint: 224-pixel / 16-frame position embeddings, a DDP-style "module." prefix, one
+    tensor of a different shape (the Kinetics classification head) and one unknown name."""
+    g = torch.Generator().manual_seed(11)
+    pre = {"module." + k: torch.randn(v.shape, generator=g) for k, v in list(model_state.items())[:40]}
+    pre["module.pos_embed_spatial"] = torch.randn(1, 56 * 56, 96, generator=g)
+    pre["module.pos_embed_temporal"] = torch.randn(1, 8, 96, generator=g)
+    pre["module.pos_embed_spatial_audio"] = torch.randn(1, 56 * 56, 96, generator=g)   # not in the reference's interpolate list
+    pre["module.blocks.0.attn.qkv.weight"] = torch.randn(288, 96, generator=g)
+    pre["module.blocks.0.attn.proj.bias"] = torch.randn(7, generator=g)          # wrong shape: must be skipped
+    pre["module.head.projection.weight"] = torch.randn(400, 768, generator=g)    # no such tensor in CSTS
+    path = os.path.join(tmp_path, "k400_like.pyth")
+    torch.save({"epoch": 199, "model_state": pre, "optimizer_state": {}, "cfg": "dummy"}, path)
+    return path, pre
+
+
+def test_checkpoint_finetune_load_matches_by_name_and_shape_and_interpolates_pos_embed(cpu_model, tmp_path):
+    """host/checkpoint.py vs slowfast/utils/checkpoint.py:290-354 (run live when the reference is importable)."""
+    from csts_b200.host import checkpoint as cu
+    from csts_b200.host.build import build_model
+    _, cfg = cpu_model
+    torch.manual_seed(1)
+    model = build_model(cfg)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    path, pre = _k400_like_checkpoint(before, str(tmp_path))
+    epoch = cu.load_checkpoint(path, model, data_parallel=False, epoch_reset=True, clear_name_pattern=("module.",))
+    assert epoch == -1
+    after = model.state_dict()
+    assert torch.equal(after["blocks.0.attn.qkv.weight"], pre["module.blocks.0.attn.qkv.weight"])
+    assert torch.equal(after["blocks.0.attn.proj.bias"], before["blocks.0.attn.proj.bias"])          # shape mismatch: untouched
+    assert "blocks.0.attn.proj.bias" in cu.load_checkpoint.last_not_loaded
+    assert "pos_embed_spatial" not in cu.load_checkpoint.last_not_loaded
+    want = torch.nn.functional.interpolate(pre["module.pos_embed_spatial"].unsqueeze(0), (4096, 96), mode="bilinear").squeeze(0)
+    assert torch.equal(after["pos_embed_spatial"], want) and after["pos_embed_temporal"].shape == (1, 4, 96)
+    assert not torch.equal(after["pos_embed_temporal"], before["pos_embed_temporal"])
+    assert torch.equal(after["pos_embed_spatial_audio"], before["pos_embed_spatial_audio"])           # not in the interpolate list
+    if ref_shim.reference_available():
+        ref_shim.install()
+        try:
+            import slowfast.utils.checkpoint as rcu
+        except Exception as e:          # the module pulls optional packages the image may lack
+            pytest.skip(f"reference checkpoint module not importable here: {e}")
+        torch.manual_seed(1)
+        twin = build_model(cfg)
+        rcu.load_checkpoint(path, twin, data_parallel=False, epoch_reset=True, clear_name_pattern=("module.",))
+        ts = twin.state_dict()
+        assert all(torch.equal(after[k], ts[k]) for k in after)
+
+
+def test_checkpoint_round_trip_resumes_epoch_and_optimizer(cpu_model, tmp_path):
+    from csts_b200.host import checkpoint as cu
+    model, cfg = cpu_model
+    opt = torch.optim.AdamW([p for p in model.parameters()][:3], lr=1e-3)
+    for p in opt.param_groups[0]["params"]:
+        p.grad = torch.ones_like(p)
+    opt.step()
+    path = cu.save_checkpoint(os.path.join(str(tmp_path), "checkpoints", "checkpoint_epoch_00003.pyth"), model, opt, 2, cfg,
+                              data_parallel=False)
+    rec = torch.load(path, weights_only=False)
+    assert set(rec) == {"epoch", "model_state", "optimizer_state", "cfg"} and list(rec["model_state"]) == list(model.state_dict())
+    opt2 = torch.optim.AdamW([p for p in model.parameters()][:3], lr=1e-3)
+    assert cu.load_checkpoint(path, model, data_parallel=False, optimizer=opt2) == 2
+    assert float(opt2.state[opt2.param_groups[0]["params"][0]]["step"]) == 1.0

@@ -537,6 +537,20 @@ def test_kldiv_and_egonce(golden_dir):
     # logits are sim/0.05 (|z| up to 20): fp32 exp amplifies rounding, hence 1e-3
     assert rel_err(dv, v.grad) < 1e-3
     assert rel_err(da, a.grad) < 1e-3
+    # KLDiv with target=None: the uniform-prior (negative entropy) branch, slowfast/models/losses.py:67-71
+    from csts_b200.host import losses as L
+    from csts_b200.host.utils import frame_softmax
+    lg = rec["logits"].to(dev).requires_grad_(True)
+    got = L.KLDiv()(frame_softmax(lg, temperature=2))
+    got.backward()
+    p = O.frame_softmax(logits, 2.0)
+    Bn, T, HW = p.shape[0], p.shape[2], p.shape[3] * p.shape[4]
+    pm = p.reshape(Bn, T, -1)
+    want = (((pm * torch.log(pm + 1e-10)).sum(-1) - math.log(1.0 / HW)).sum(-1) / (T * math.log(HW))).mean()
+    logits.grad = None
+    want.backward()
+    assert abs(got.item() - want.item()) < 1e-5 * abs(want.item()) + 1e-7, (got.item(), want.item())
+    assert rel_err(lg.grad, logits.grad) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------ storage types

@@ -297,14 +297,19 @@ def test_droppath_statistics():
     x = torch.randn(2, 1024, 384, device=dev)
     thw = (4, 16, 16)
     names = blk._names
-    one = torch.tensor([1.0, 1.0], device=dev)
-    mixed = torch.tensor([0.0, 1.0 / (1 - blk.spec.drop_path)], device=dev)
+    k = 1.0 / (1 - blk.spec.drop_path)
+    one = torch.ones(2, 2, device=dev)                       # (branch, sample)
+    mixed = torch.tensor([[0.0, k], [0.0, k]], device=dev)
+    attn_only = torch.tensor([[0.0, 1.0], [1.0, 1.0]], device=dev)   # sample 0 loses its attention branch only
     y_plain = BlockFn.apply((blk.spec, model._wc, thw, None, names), x, *blk.tensors())
     y_one = BlockFn.apply((blk.spec, model._wc, thw, one, names), x, *blk.tensors())
     y_mix = BlockFn.apply((blk.spec, model._wc, thw, mixed, names), x, *blk.tensors())
+    y_att = BlockFn.apply((blk.spec, model._wc, thw, attn_only, names), x, *blk.tensors())
     assert torch.equal(y_plain, y_one)
     assert torch.equal(y_mix[0], x[0])                       # dropped sample: both branches vanish
     assert not torch.equal(y_mix[1], y_plain[1])
+    assert torch.equal(y_att[1], y_plain[1])
+    assert not torch.equal(y_att[0], x[0]) and not torch.equal(y_att[0], y_plain[0])   # MLP branch alive, attention gone
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp16"])

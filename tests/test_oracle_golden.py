@@ -120,3 +120,36 @@ def test_optional_paths_against_reference_golden(golden_dir):
     assert (out[1][:, :, ::13, :] - rec["spatial_attn_rows"]).abs().max() < 1e-5
     assert (out[1].sum(-1) - rec["spatial_attn_rowsum"]).abs().max() < 1e-5
     assert len(O.csts_forward(sd, video, audio, return_temporal_attn=True)) == 2
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_oracle_drop_path_against_live_reference_block():
+    """DropPath (common.py:46-59, applied at attention.py:242 and :247 with independent draws): the reference block in
+    train mode with torch.rand replaced by a recorded sequence equals the oracle block given the same two scale vectors."""
+    ref_shim.install()
+    from functools import partial
+    import slowfast.models.common as common
+    from slowfast.models.attention import MultiScaleBlock
+    torch.manual_seed(0)
+    blk = MultiScaleBlock(dim=96, dim_out=192, num_heads=1, qkv_bias=True, drop_path=0.4, kernel_q=(), kernel_kv=(3, 3, 3),
+                          stride_q=(), stride_kv=(1, 2, 2), norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), mode="conv",
+                          has_cls_embed=False)
+    blk.train()
+    x = torch.randn(4, 256, 96)
+    draws = [torch.tensor([0.9, 0.1, 0.7, 0.3]).reshape(4, 1, 1), torch.tensor([0.2, 0.95, 0.61, 0.05]).reshape(4, 1, 1)]
+    seq = list(draws)
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: seq.pop(0)
+    try:
+        y_ref, _ = blk(x, (4, 8, 8))
+    finally:
+        torch.rand = real_rand
+    assert not seq
+    keep = 0.6
+    scales = tuple(torch.floor(keep + d.reshape(-1)) / keep for d in draws)
+    assert len(set(scales[0].tolist())) == 2 and float(scales[0].min()) == 0.0
+    sd = {"b." + k: v.detach() for k, v in blk.state_dict().items()}
+    y, _ = O.block(sd, "b", x, (4, 8, 8), spec=("enc", 96, 192, 1, None, (1, 2, 2)), drop=scales)
+    torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
+    y0, _ = O.block(sd, "b", x, (4, 8, 8), spec=("enc", 96, 192, 1, None, (1, 2, 2)))
+    assert (y0 - y_ref).abs().max() > 1e-2
