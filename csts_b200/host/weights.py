@@ -50,7 +50,7 @@ class WeightCache:
         """Stream of the weight-gradient branch of the backward pass (block.py::_Fork), or None when disabled."""
         if not self.fork_backward:
             return None
-        if self._side is None or self._side.device != torch.cuda.current_device():
+        if self._side is None or self._side.device.index != torch.cuda.current_device():
             self._side = torch.cuda.Stream()
         return self._side
 
