@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("c_dtype", C.c_int32), ("act", C.c_int32), ("accumulate", C.c_int32), ("res_mod", C.c_int32),
         ("split_k", C.c_int32), ("alpha", C.c_float), ("backend", C.c_int32), ("rows_per_scale", C.c_int32),
         ("a_dtype", C.c_int32), ("b_dtype", C.c_int32), ("z_dtype", C.c_int32),
+        ("tile_n", C.c_int32), ("ctas", C.c_int32),
     ]
 
 
@@ -120,6 +121,8 @@ def load():
         fn.restype = C.c_int
     lib.csts_gemm_backend.argtypes = [C.POINTER(GemmArgs)]
     lib.csts_gemm_backend.restype = C.c_int
+    lib.csts_gemm_plan.argtypes = [C.POINTER(GemmArgs), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.csts_gemm_plan.restype = C.c_int
     lib.csts_mt_chunk_elems.argtypes = []
     lib.csts_mt_chunk_elems.restype = C.c_int
     lib.csts_launch_count.argtypes = [C.c_int]

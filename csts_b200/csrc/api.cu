@@ -76,6 +76,11 @@ int csts_gemm_backend(const csts_gemm_args* a) {
   return csts_gemm_tc_supported(*a) ? 2 : 1;
 }
 
+int csts_gemm_plan(const csts_gemm_args* a, int* tile_n, int* ctas, int* splits) {
+  CSTS_REQUIRE(a && tile_n && ctas && splits, "gemm_plan: null argument");
+  return csts_gemm_tc_plan(*a, tile_n, ctas, splits);
+}
+
 int csts_gemm(const csts_gemm_args* a, void* stream) {
   CSTS_REQUIRE(a != nullptr, "gemm: null argument block");
   CSTS_REQUIRE((a->a_dtype == CSTS_BF16 || a->a_dtype == CSTS_F16) && (a->b_dtype == CSTS_BF16 || a->b_dtype == CSTS_F16),

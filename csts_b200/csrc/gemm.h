@@ -8,3 +8,4 @@
 int csts_gemm_mma_launch(const csts_gemm_args& a, cudaStream_t stream);
 int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream);
 bool csts_gemm_tc_supported(const csts_gemm_args& a);
+int csts_gemm_tc_plan(const csts_gemm_args& a, int* bn, int* ctas, int* splits);

@@ -32,10 +32,13 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 12;                         // three per TMEM lane quadrant
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int SMEM_BUDGET = 168 * 1024;
-constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;   // one 32-row x 128-byte tile per epilogue warp
+// Two builds of the kernel (template parameter CTAS = CTAs that fit one SM):
+//   CTAS 1: 12 epilogue warps (three per TMEM lane quadrant), ~215 KB of shared memory, all 512 TMEM columns — the
+//           throughput variant for problems of several waves;
+//   CTAS 2: 4 epilogue warps, <= 113 KB, 256 TMEM columns — two CTAs share an SM, so a problem of up to two "waves" is
+//           resident at once, consecutive kernels overlap under programmatic dependent launch (the next kernel's CTAs
+//           run their prologue next to the draining ones) and a weight-gradient GEMM on the second stream shares SMs
+//           with the data-gradient chain.  Two thirds of the step's GEMMs are at most one wave: this is their variant.
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -147,18 +150,26 @@ struct TcParams {
   float alpha;
 };
 
-template <int BN> struct Cfg {
+template <int BN, int CTAS> struct Cfg {
+  static constexpr int NUM_EPI_WARPS = CTAS == 1 ? 12 : 4;
+  static constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;   // one 32-row x 128-byte tile per epilogue warp
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BOXES = (BN + 63) / 64;                 // MN-major B: 64-wide boxes
   static constexpr int B_BYTES = B_BOXES * 64 * BK * 2;          // >= BN * BK * 2, multiple of 8 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int NACC = (512 / BN) >= 4 ? 4 : 2;            // accumulator stages in TMEM
-  static constexpr int TMEM_COLS = 512;
   static constexpr int ONES_BYTES = 2048;                        // all-ones 16 x 64 operand tile (row-sum MMA)
+  static constexpr int FIXED_BYTES = STAGING_BYTES + ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // CTAS 2: (228 KB - 1 KB reserved per CTA) / 2 = 113 KB each
+  static constexpr int SMEM_BUDGET = (CTAS == 1 ? 168 * 1024 : 113 * 1024 - FIXED_BYTES);
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 512 / CTAS;
+  static constexpr int NACC = (TMEM_COLS / BN) >= 4 ? 4 : ((TMEM_COLS / BN) >= 2 ? 2 : 1);   // accumulator stages in TMEM
   static constexpr int RS_COLS = 32;                             // TMEM columns per accumulator stage for the row sums
-  static constexpr bool RS_FITS = NACC * (BN + RS_COLS) <= 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr bool RS_FITS = NACC * (BN + RS_COLS) <= TMEM_COLS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(STAGES >= 2, "the TMA ring needs two stages");
+  static_assert(CTAS == 1 || SMEM_BYTES <= 113 * 1024, "two CTAs must fit one SM");
 };
 
 // ---- epilogue helpers: a warp moves a 32-row x 128-byte tile between global memory (coalesced: 8 lanes
@@ -450,10 +461,12 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EPI, int CTAS>
+__global__ void __launch_bounds__((Cfg<BN, CTAS>::NUM_THREADS), CTAS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
+  constexpr int NUM_EPI_WARPS = C::NUM_EPI_WARPS;
+  constexpr int STAGING_BYTES = C::STAGING_BYTES;
   extern __shared__ unsigned char smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -587,7 +600,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) {
       // whole-row epilogues: the quadrant's warps take turns on successive tiles (tile seq -> warp seq % NSUB),
       // so up to NSUB tiles per quadrant are drained concurrently and no cross-warp reduction exists
-      constexpr int NSUB = C::NACC < 3 ? C::NACC : 3;
+      constexpr int NSUB = (C::NACC < NUM_EPI_WARPS / 4 ? C::NACC : NUM_EPI_WARPS / 4);
       int seq = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++seq) {
         if (sub >= NSUB || seq % NSUB != sub) continue;
@@ -735,12 +748,15 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch(const csts_gemm_args& a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+// What the launcher decides per problem: tile width, CTAs per SM (kernel build) and split-K factor.
+struct Plan { int bn, ctas, splits; };
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int CTAS>
+int launch(const csts_gemm_args& a, const Plan& plan, cudaStream_t stream) {
+  using C = Cfg<BN, CTAS>;
   static std::atomic<bool> attr_set{false};      // set from the forward thread and from autograd's backward thread
   if (!attr_set.load(std::memory_order_acquire)) {
-    CSTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CSTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set.store(true, std::memory_order_release);
   }
   CUtensorMap ta, tb;
@@ -762,19 +778,18 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   p.a_bf16 = a.a_dtype == CSTS_F16 ? 0 : 1; p.b_bf16 = a.b_dtype == CSTS_F16 ? 0 : 1;
   p.c_half = a.c_dtype == CSTS_F16; p.z_half = a.z_dtype == CSTS_F16;
   const int kblocks = ceil_div(a.K, BK);
-  int splits = a.split_k > 1 ? a.split_k : 1;
-  if (splits > kblocks) splits = kblocks;
-  p.kblocks_per_split = ceil_div(kblocks, splits);
+  p.kblocks_per_split = ceil_div(kblocks, plan.splits);
   p.splits = ceil_div(kblocks, p.kblocks_per_split);
   if (p.splits > 1 && !a.accumulate) {
     CSTS_REQUIRE(p.batch == 1, "gemm_tc: split-K without accumulate supports a single batch");
     CSTS_CUDA(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, (size_t)a.N * sizeof(float), a.M, stream));
   }
-  int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits * p.batch;
-  int grid = items < csts_num_sms() ? items : csts_num_sms();
+  const int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits * p.batch;
+  const int slots = csts_num_sms() * CTAS;
+  const int grid = items < slots ? items : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(C::NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -782,50 +797,114 @@ int launch(const csts_gemm_args& a, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CSTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, EPI>, ta, tb, p));
+  CSTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, EPI, CTAS>, ta, tb, p));
   return csts_check_launch("gemm_tc_kernel");
 }
 
-int pick_bn(int M, int N, int work_mult) {
-  if (const char* f = getenv("CSTS_FORCE_BN")) {       // tuning experiments only
-    int bn = atoi(f);
-    if (bn == 96 || bn == 128 || bn == 192 || bn == 256) return bn;
+int normalized_splits(int K, int splits) {
+  const int kblocks = ceil_div(K, BK);
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+  return ceil_div(kblocks, ceil_div(kblocks, splits));
+}
+
+// Launch-time model used to rank (tile width, CTAs per SM, split-K) candidates: a work item costs a fixed part
+// (pipeline fill, first TMA round trip, accumulator drain), its k-blocks and its epilogue; items run in waves over the
+// CTA slots.  Nanoseconds, calibrated on the per-shape event timings in profiles/ (tuning/gemm_tune.py re-measures it).
+double model_ns(const csts_gemm_args& a, const Plan& pl) {
+  const int sms = csts_num_sms();
+  const int kblocks = ceil_div(a.K, BK);
+  const int kb = ceil_div(kblocks, pl.splits);
+  const long items = (long)ceil_div(a.M, BM) * ceil_div(a.N, pl.bn) * pl.splits * a.batch1 * a.batch2;
+  const long slots = (long)sms * pl.ctas;
+  const long waves = (items + slots - 1) / slots;
+  const bool shared_pipe = pl.ctas == 2 && items > sms;          // two resident CTAs share the SM's tensor pipe and LSU
+  const bool f32_out = a.c_dtype == 0;
+  const double per_col = 1.75;                                   // 128 x 64 x 2 flop per column and k-block at 9.4 TF/s per SM
+  double epi = pl.bn * (f32_out ? 14.0 : 8.0) * (pl.splits > 1 ? 1.5 : 1.0);
+  if (a.act == 1 || a.act == 2) epi *= 1.6;
+  if (pl.ctas == 2) epi *= 2.2;                                  // 4 epilogue warps instead of 12
+  const double fixed = pl.ctas == 2 ? 1400.0 : 2200.0;
+  const double tile = fixed + kb * (pl.bn * per_col * (shared_pipe ? 1.7 : 1.0) + 45.0) + epi;
+  const double memset_ns = (pl.splits > 1 && !a.accumulate) ? 2500.0 : 0.0;
+  return waves * tile + memset_ns;
+}
+
+bool small_variant_exists(int bn, int act) { return bn != 256 && act != 3 && act != 4; }
+
+// Measured plans (benchmarks/tune_gemm.py on a B200) for the problems of the benchmarked training step
+struct TunedPlan { int M, N, K, batch, a_kmajor, b_kmajor, act, c16, rowsum, auto_split, bn, ctas, splits; };
+const TunedPlan kTuned[] = {
+#include "gemm_tune.inc"
+    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+
+Plan plan_for(const csts_gemm_args& a) {
+  static const bool use_table = getenv("CSTS_GEMM_NO_TABLE") == nullptr;
+  if (use_table && a.tile_n == 0 && a.ctas == 0 && (a.split_k < 0 || a.split_k == 0 || a.split_k == 1)) {
+    const int nb = a.batch1 * a.batch2;
+    for (const TunedPlan* t = kTuned; t->M != 0; ++t) {
+      if (t->M == a.M && t->N == a.N && t->K == a.K && t->batch == nb && t->a_kmajor == (a.a_kmajor != 0) && t->b_kmajor == (a.b_kmajor != 0) &&
+          t->act == a.act && t->c16 == (a.c_dtype != 0) && t->rowsum == (a.rowsum != nullptr) && t->auto_split == (a.split_k < 0)) {
+        if (t->ctas == 2 && !small_variant_exists(t->bn, a.act)) break;
+        return Plan{t->bn, t->ctas, normalized_splits(a.K, a.split_k < 0 ? t->splits : 1)};
+      }
+    }
   }
-  // least padded columns first; among equals the widest tile that still gives every SM work, else
-  // the narrowest (most CTAs)
+  static const int force_bn = getenv("CSTS_FORCE_BN") ? atoi(getenv("CSTS_FORCE_BN")) : 0;        // tuning experiments only
+  static const int force_ctas = getenv("CSTS_FORCE_CTAS") ? atoi(getenv("CSTS_FORCE_CTAS")) : 0;
   const int cands[4] = {256, 192, 128, 96};
-  int sms = csts_num_sms();
+  const int kblocks = ceil_div(a.K, BK);
+  int bn_lo = 0, bn_hi = 3;
+  int fixed_bn = a.tile_n ? a.tile_n : force_bn;
+  if (a.act == 3 || a.act == 4) fixed_bn = a.N <= 96 ? 96 : (a.N <= 128 ? 128 : (a.N <= 192 ? 192 : 256));   // one tile holds all keys
+  else if (a.rowsum) fixed_bn = a.N <= 96 ? 96 : 192;            // tile widths that leave TMEM columns for the fused row sums
   int best_pad = 1 << 30;
-  for (int i = 0; i < 4; ++i) best_pad = std::min(best_pad, ceil_div(N, cands[i]) * cands[i]);
-  for (int i = 0; i < 4; ++i) {
-    int bn = cands[i];
-    if (ceil_div(N, bn) * bn != best_pad) continue;
-    if ((long)ceil_div(M, BM) * (best_pad / bn) * work_mult >= sms) return bn;
+  for (int i = 0; i < 4; ++i) best_pad = std::min(best_pad, ceil_div(a.N, cands[i]) * cands[i]);
+  const int split_opts[12] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+  Plan best = {96, 1, 1};
+  double best_ns = 1e30;
+  for (int i = bn_lo; i <= bn_hi; ++i) {
+    const int bn = cands[i];
+    if (fixed_bn ? bn != fixed_bn : ceil_div(a.N, bn) * bn != best_pad) continue;
+    for (int ctas = 1; ctas <= 2; ++ctas) {
+      if (ctas == 2 && !small_variant_exists(bn, a.act)) continue;
+      const int want_ctas = a.ctas ? a.ctas : force_ctas;
+      if (want_ctas && ctas != want_ctas && !(want_ctas == 2 && !small_variant_exists(bn, a.act))) continue;
+      for (int si = 0; si < 12; ++si) {
+        int sp = split_opts[si];
+        if (a.split_k >= 0) { if (si > 0) break; sp = a.split_k > 1 ? a.split_k : 1; }      // caller's choice
+        else if (sp > 1 && ceil_div(kblocks, sp) < 4) break;                                 // auto: >= 4 k-blocks per split
+        Plan pl = {bn, ctas, normalized_splits(a.K, sp)};
+        const double ns = model_ns(a, pl);
+        if (ns < best_ns) { best_ns = ns; best = pl; }
+      }
+    }
   }
-  for (int i = 3; i >= 0; --i)
-    if (ceil_div(N, cands[i]) * cands[i] == best_pad) return cands[i];
-  return 96;
+  return best;
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-int dispatch(const csts_gemm_args& a, cudaStream_t stream) {
-  int bn = pick_bn(a.M, a.N, (a.split_k > 1 ? a.split_k : 1) * a.batch1 * a.batch2);
-  if (a.rowsum) bn = a.N <= 96 ? 96 : 192;            // tile widths that leave TMEM columns for the fused row sums
-  switch (bn) {
-    case 256: return launch<256, A_MN, B_MN, EPI>(a, stream);
-    case 192: return launch<192, A_MN, B_MN, EPI>(a, stream);
-    case 128: return launch<128, A_MN, B_MN, EPI>(a, stream);
-    case 96: return launch<96, A_MN, B_MN, EPI>(a, stream);
+int dispatch(const csts_gemm_args& a, const Plan& pl, cudaStream_t stream) {
+  constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX;
+  if (pl.ctas == 2) {
+    if constexpr (!ROWS) {
+      switch (pl.bn) {
+        case 192: return launch<192, A_MN, B_MN, EPI, 2>(a, pl, stream);
+        case 128: return launch<128, A_MN, B_MN, EPI, 2>(a, pl, stream);
+        case 96: return launch<96, A_MN, B_MN, EPI, 2>(a, pl, stream);
+      }
+    }
+    csts_set_error("gemm_tc: no two-CTA build for tile width %d / epilogue %d", pl.bn, EPI);
+    return 2;
+  }
+  switch (pl.bn) {
+    case 256: return launch<256, A_MN, B_MN, EPI, 1>(a, pl, stream);
+    case 192: return launch<192, A_MN, B_MN, EPI, 1>(a, pl, stream);
+    case 128: return launch<128, A_MN, B_MN, EPI, 1>(a, pl, stream);
+    case 96: return launch<96, A_MN, B_MN, EPI, 1>(a, pl, stream);
   }
   csts_set_error("gemm_tc: no tile width divides N=%d", a.N);
   return 2;
-}
-
-int effective_splits(const csts_gemm_args& a) {
-  int kblocks = ceil_div(a.K, BK);
-  int splits = a.split_k > 1 ? a.split_k : 1;
-  if (splits > kblocks) splits = kblocks;
-  return ceil_div(kblocks, ceil_div(kblocks, splits));
 }
 
 }  // namespace
@@ -845,7 +924,8 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   if (a.residual && (nb > 1 || ((uintptr_t)a.residual & 15) || (a.ldr * 4) % 16)) return false;
   if (a.res_mod > 0 && a.res_mod % 32 != 0) return false;
   if (a.bias && (((uintptr_t)a.bias & 15) || a.N % 4 != 0)) return false;
-  if (a.split_k > 1 && (a.c_dtype != 0 || a.act != 0 || a.row_scale)) return false;
+  if ((a.split_k > 1 || a.split_k < 0) && (a.c_dtype != 0 || a.act != 0 || a.row_scale)) return false;
+  if ((a.split_k > 1 || a.split_k < 0) && !a.accumulate && a.batch1 * a.batch2 != 1) return false;
   if (a.act == 3 || a.act == 4) {                      // fused softmax / softmax-backward rows
     if (!a.a_kmajor || !a.b_kmajor || a.c_dtype == 0 || a.N > 256 || a.bias || a.residual || a.accumulate || a.row_scale ||
         a.split_k > 1 || a.ldc % 8 != 0 || a.ldc < a.N || a.M < 64)
@@ -860,39 +940,30 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   return true;
 }
 
+int csts_gemm_tc_plan(const csts_gemm_args& a, int* bn, int* ctas, int* splits) {
+  Plan pl = plan_for(a);
+  *bn = pl.bn; *ctas = pl.ctas; *splits = pl.splits;
+  return 0;
+}
+
 int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
   CSTS_REQUIRE(csts_gemm_tc_supported(a), "gemm_tc: unsupported problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   if (a.act == 2) CSTS_REQUIRE(a.Z != nullptr, "gemm: act==2 needs Z");
-  const bool atomic = effective_splits(a) > 1;
-  if (a.act == 3 || a.act == 4) {
-    // single column tile: the narrowest tile width that holds all N keys
-    const int bn = a.N <= 96 ? 96 : (a.N <= 128 ? 128 : (a.N <= 192 ? 192 : 256));
-    if (a.act == 3) {
-      switch (bn) {
-        case 96: return launch<96, false, false, EPI_SOFTMAX>(a, stream);
-        case 128: return launch<128, false, false, EPI_SOFTMAX>(a, stream);
-        case 192: return launch<192, false, false, EPI_SOFTMAX>(a, stream);
-        default: return launch<256, false, false, EPI_SOFTMAX>(a, stream);
-      }
-    }
-    switch (bn) {
-      case 96: return launch<96, false, false, EPI_DSOFTMAX>(a, stream);
-      case 128: return launch<128, false, false, EPI_DSOFTMAX>(a, stream);
-      case 192: return launch<192, false, false, EPI_DSOFTMAX>(a, stream);
-      default: return launch<256, false, false, EPI_DSOFTMAX>(a, stream);
-    }
-  }
+  const Plan pl = plan_for(a);
+  const bool atomic = pl.splits > 1;
+  if (a.act == 3) return dispatch<false, false, EPI_SOFTMAX>(a, pl, stream);
+  if (a.act == 4) return dispatch<false, false, EPI_DSOFTMAX>(a, pl, stream);
   if (!a.a_kmajor) {                                    // (MN, MN): weight gradients, dV / dK of attention
-    if (a.c_dtype != 0) return dispatch<true, true, EPI_BF16>(a, stream);
-    return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, stream) : dispatch<true, true, EPI_F32>(a, stream);
+    if (a.c_dtype != 0) return dispatch<true, true, EPI_BF16>(a, pl, stream);
+    return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, pl, stream) : dispatch<true, true, EPI_F32>(a, pl, stream);
   }
   if (!a.b_kmajor) {                                    // (K, MN): P.V and dS.K of attention; dX = dY . W of every Linear
     CSTS_REQUIRE((a.act == 0 || a.act == 2) && !atomic, "gemm_tc: (K-major, MN-major) products have no GELU / split-K epilogue");
-    if (a.act == 2) return dispatch<false, true, EPI_BF16_DGELU>(a, stream);
-    return a.c_dtype != 0 ? dispatch<false, true, EPI_BF16>(a, stream) : dispatch<false, true, EPI_F32>(a, stream);
+    if (a.act == 2) return dispatch<false, true, EPI_BF16_DGELU>(a, pl, stream);
+    return a.c_dtype != 0 ? dispatch<false, true, EPI_BF16>(a, pl, stream) : dispatch<false, true, EPI_F32>(a, pl, stream);
   }
-  if (a.c_dtype == 0) return atomic ? dispatch<false, false, EPI_F32_ATOMIC>(a, stream) : dispatch<false, false, EPI_F32>(a, stream);
-  if (a.act == 1) return dispatch<false, false, EPI_BF16_GELU>(a, stream);
-  if (a.act == 2) return dispatch<false, false, EPI_BF16_DGELU>(a, stream);
-  return dispatch<false, false, EPI_BF16>(a, stream);
+  if (a.c_dtype == 0) return atomic ? dispatch<false, false, EPI_F32_ATOMIC>(a, pl, stream) : dispatch<false, false, EPI_F32>(a, pl, stream);
+  if (a.act == 1) return dispatch<false, false, EPI_BF16_GELU>(a, pl, stream);
+  if (a.act == 2) return dispatch<false, false, EPI_BF16_DGELU>(a, pl, stream);
+  return dispatch<false, false, EPI_BF16>(a, pl, stream);
 }

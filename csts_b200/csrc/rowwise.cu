@@ -66,11 +66,17 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward.  dx = [add +] rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
-// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy  (per-warp registers -> smem -> one atomic per
-// column per block).
+// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy.
+//
+// A row is owned by LPR lanes (8 / 16 / 32 for widths <= 96 / 192 / wider), each holding J vectors of 4 columns, so
+// a warp works on 32/LPR rows at once with every lane busy (the 96-wide pool norms are 60 % of the launches), and U
+// such passes are loaded before the first reduction: U * J * 3 independent 8/16-byte loads in flight per lane.  The
+// grid is persistent (a few blocks per SM): dgamma / dbeta accumulate in registers over all rows of a lane, are folded
+// across the warp's row groups by shuffles and across the block's warps in shared memory, and reach global memory as
+// 2 * width atomics per BLOCK — a few hundred per address per launch instead of one per 32 rows.
 // ------------------------------------------------------------------------------------------------
-template <typename TX, typename TDY, typename TDX, int LN_MAXJ>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+template <typename TX, typename TDY, typename TDX, int LPR, int J, int U>
+__global__ void __launch_bounds__(256, J <= 3 ? 2 : 1) layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ add,
                                                             TDX* __restrict__ dx, float* __restrict__ dgamma,
@@ -80,32 +86,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
   __shared__ float s_dg[768], s_db[768];
   for (int i = threadIdx.x; i < width; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
+  constexpr int G = 32 / LPR;                       // rows per warp pass
   const int lane = threadIdx.x & 31;
+  const int li = lane % LPR, grp = lane / LPR;
   const int warps_per_block = blockDim.x >> 5;
   const float inv_w = 1.f / (float)width;
-  float adg[LN_MAXJ][4], adb[LN_MAXJ][4], g[LN_MAXJ][4];
+  float adg[J][4], adb[J][4], g[J][4];
 #pragma unroll
-  for (int j = 0; j < LN_MAXJ; ++j) {
-    int c = (lane + 32 * j) * 4;
+  for (int j = 0; j < J; ++j) {
+    const int c = (li + LPR * j) * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { adg[j][i] = 0.f; adb[j][i] = 0.f; g[j][i] = 0.f; }
     if (c < width) ld4(gamma + c, g[j]);
   }
-  // U rows per warp iteration: every global read of the U rows (x, dy, add, statistics) is issued before
-  // the first reduction, so a warp keeps 3*U*LN_MAXJ vector loads in flight
-  constexpr int U = LN_MAXJ <= 2 ? 2 : 1;
-  const int wstride = gridDim.x * warps_per_block;
-  for (int row0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < rows; row0 += U * wstride) {
-    float xv[U][LN_MAXJ][4], dv[U][LN_MAXJ][4], av[U][LN_MAXJ][4], mu[U], rs[U];
+  const int total_warps = gridDim.x * warps_per_block;
+  const int passes = (rows + G - 1) / G;
+  for (int p0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p0 < passes; p0 += U * total_warps) {
+    float xv[U][J][4], dv[U][J][4], av[U][J][4], mu[U], rs[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int row = row0 + u * wstride;
-      const bool rv = row < rows;
+      const int row = (p0 + u * total_warps) * G + grp;
+      const bool rv = p0 + u * total_warps < passes && row < rows;
       mu[u] = rv ? mean[row] : 0.f;
       rs[u] = rv ? rstd[row] : 0.f;
 #pragma unroll
-      for (int j = 0; j < LN_MAXJ; ++j) {
-        const int c = (lane + 32 * j) * 4;
+      for (int j = 0; j < J; ++j) {
+        const int c = (li + LPR * j) * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { xv[u][j][i] = 0.f; dv[u][j][i] = 0.f; av[u][j][i] = 0.f; }
         if (rv && c < width) {
@@ -117,38 +123,41 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int row = row0 + u * wstride;
-      if (row >= rows) continue;
-      float xh[LN_MAXJ][4], gd[LN_MAXJ][4];
+      const int row = (p0 + u * total_warps) * G + grp;
+      const bool rv = p0 + u * total_warps < passes && row < rows;      // whole row groups take the shuffles together
+      float xh[J][4], gd[J][4];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < LN_MAXJ; ++j) {
-        const int c = (lane + 32 * j) * 4;
-        if (c < width) {
+      for (int j = 0; j < J; ++j) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            xh[j][i] = (xv[u][j][i] - mu[u]) * rs[u];
-            adg[j][i] += dv[u][j][i] * xh[j][i];
-            adb[j][i] += dv[u][j][i];
-            gd[j][i] = dv[u][j][i] * g[j][i];
-            s1 += gd[j][i];
-            s2 += gd[j][i] * xh[j][i];
-          }
+        for (int i = 0; i < 4; ++i) {
+          xh[j][i] = (xv[u][j][i] - mu[u]) * rs[u];       // lanes beyond the width / rows hold zeros: they add nothing
+          adg[j][i] += dv[u][j][i] * xh[j][i];
+          adb[j][i] += dv[u][j][i];
+          gd[j][i] = dv[u][j][i] * g[j][i];
+          s1 += gd[j][i];
+          s2 += gd[j][i] * xh[j][i];
         }
       }
-      s1 = warp_sum(s1) * inv_w;
-      s2 = warp_sum(s2) * inv_w;
-      TDX* dxr = dx + (int64_t)row * width;
 #pragma unroll
-      for (int j = 0; j < LN_MAXJ; ++j) {
-        const int c = (lane + 32 * j) * 4;
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= inv_w;
+      s2 *= inv_w;
+      if (!rv) continue;
+      TDX* dxr = dx + (int64_t)row * width;
+      const float sc = (dx16 && row_scale) ? row_scale[row / rows_per_scale] : 1.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = (li + LPR * j) * 4;
         if (c < width) {
           float o[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = rs[u] * (gd[j][i] - s1 - xh[j][i] * s2) + av[u][j][i];
           st4(dxr + c, o);
           if (dx16) {                                  // 16-bit (row-scaled) copy: the operand of the next backward GEMM
-            const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] *= sc;
             if (dx16_half) st4(reinterpret_cast<f16*>(dx16) + (int64_t)row * width + c, o);
@@ -158,10 +167,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
       }
     }
   }
+  // fold the warp's row groups (they own the same columns), then the block's warps
 #pragma unroll
-  for (int j = 0; j < LN_MAXJ; ++j) {
-    int c = (lane + 32 * j) * 4;
-    if (c < width) {
+  for (int j = 0; j < J; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) {
+        adg[j][i] += __shfl_xor_sync(0xffffffffu, adg[j][i], o);
+        adb[j][i] += __shfl_xor_sync(0xffffffffu, adb[j][i], o);
+      }
+    }
+    const int c = (li + LPR * j) * 4;
+    if (grp == 0 && c < width) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { atomicAdd(&s_dg[c + i], adg[j][i]); atomicAdd(&s_db[c + i], adb[j][i]); }
     }
@@ -429,19 +447,20 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
   const int dx16_half = dx16_dtype == CSTS_F16;
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  // every block ends with 2 * width global atomics on the same addresses: narrow rows get more rows per block
-  static const int rows_narrow = getenv("CSTS_LN_BWD_ROWS") ? atoi(getenv("CSTS_LN_BWD_ROWS")) : 32;   // tuning hook
-  const int rows_per_block = width <= 128 ? rows_narrow : 32;
-  int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;       // >= 4 rows per warp so the column atomics amortise
-  int grid = (int)(blocks < csts_num_sms() * 8 ? (blocks > 0 ? blocks : 1) : csts_num_sms() * 8);
-#define LN_BWD_J(TX, TDY, TDX, J) \
-  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, J>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width, dx16, dx16_half, row_scale, rows_per_scale)
-#define LN_BWD(TX, TDY, TDX)                             \
-  do {                                                   \
-    if (width <= 128) LN_BWD_J(TX, TDY, TDX, 1);         \
-    else if (width <= 256) LN_BWD_J(TX, TDY, TDX, 2);    \
-    else if (width <= 384) LN_BWD_J(TX, TDY, TDX, 3);    \
-    else LN_BWD_J(TX, TDY, TDX, 6);                      \
+  // persistent grid: enough warps to keep HBM busy, few enough blocks that the 2 * width closing atomics per block are noise
+  const int blocks_per_sm = width <= 384 ? 2 : 1;          // what the register budget of the two variants allows
+  const int lpr = width <= 96 ? 8 : (width <= 192 ? 16 : 32);
+  const int64_t passes = (rows + 32 / lpr - 1) / (32 / lpr);
+  const int64_t blocks = (passes + 8 * 4 - 1) / (8 * 4);                 // >= 4 passes per warp
+  int grid = (int)(blocks < (int64_t)csts_num_sms() * blocks_per_sm ? (blocks > 0 ? blocks : 1) : (int64_t)csts_num_sms() * blocks_per_sm);
+#define LN_BWD_J(TX, TDY, TDX, LPR, J, U) \
+  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, LPR, J, U>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width, dx16, dx16_half, row_scale, rows_per_scale)
+#define LN_BWD(TX, TDY, TDX)                                  \
+  do {                                                        \
+    if (width <= 96) LN_BWD_J(TX, TDY, TDX, 8, 3, 1);         \
+    else if (width <= 192) LN_BWD_J(TX, TDY, TDX, 16, 3, 1);  \
+    else if (width <= 384) LN_BWD_J(TX, TDY, TDX, 32, 3, 1);  \
+    else LN_BWD_J(TX, TDY, TDX, 32, 6, 1);                    \
   } while (0)
   if (x_dtype == 0 && dy_dtype == 1 && dx_dtype == 0) LN_BWD(float, bf16, float);
   else if (x_dtype == 0 && dy_dtype == 2 && dx_dtype == 0) LN_BWD(float, f16, float);

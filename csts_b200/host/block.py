@@ -41,13 +41,6 @@ def block_param_names(spec):
     return n
 
 
-def _split_k(m_out, n_out, k_tokens):
-    """Split factor for weight-gradient GEMMs (few output tiles, very long K = tokens)."""
-    tiles = ((m_out + 127) // 128) * ((n_out + 127) // 128)
-    want = max(1, (2 * 148) // tiles)
-    return max(1, min(want, k_tokens // 512))
-
-
 class _Ref:
     """A (B, heads, L, d) 16-bit tensor addressed by element strides inside `buf`."""
     __slots__ = ("buf", "off", "sB", "sH", "sP", "L", "thw")
@@ -203,9 +196,8 @@ class _Fork:
     step the fork becomes a parallel branch of the CUDA graph.  Every tensor the side stream reads is kept alive
     in `hold` until join() — the caching allocator is not told about the second stream."""
 
-    def __init__(self, stream):
+    def __init__(self, stream=None):
         self.side = stream
-        self.main = torch.cuda.current_stream() if stream is not None else None
         self.hold = []
         self.used = False
 
@@ -213,16 +205,19 @@ class _Fork:
         if self.side is None:
             return fn()
         self.hold.extend(keep)
-        self.side.wait_stream(self.main)
+        self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             r = fn()
         self.used = True
         return r
 
-    def join(self):
+    def join(self, waiter=None):
+        """Make `waiter` (default: the current stream) wait for the branch; drop the kept tensors."""
         if self.used:
-            self.main.wait_stream(self.side)
-        self.hold.clear()
+            (waiter if waiter is not None else torch.cuda.current_stream()).wait_stream(self.side)
+        if waiter is None:
+            self.used = False
+            self.hold.clear()
 
 
 def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
@@ -244,7 +239,7 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
                                                                                (1 if spec.stride_q is not None else 0))
     go = _GradOut(p, wc, dev, 4 * C + 3 * C + C + hid + 2 * Co + n_pool * 29 * d + 64)
     # the second stream needs gradient storage that outlives the block (the arena); see _Fork
-    fork = _Fork(wc.side_stream() if go.arena is not None and hasattr(wc, "side_stream") else None)
+    fork = wc.backward_fork() if go.arena is not None and hasattr(wc, "backward_fork") else _Fork()
 
     def zeros(name, n):
         return go.small(p[name], n)
@@ -254,10 +249,9 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         # sum_rows a_rows comes out of the same kernel (one extra narrow MMA per k-step against an all-ones tile)
         g[bias_name] = zeros(bias_name, m_out)
         out = go.matrix(p[wname])
-        sk = _split_k(m_out, n_out, ktok)
         g[wname] = fork.run(lambda: K.gemm(a_rows, b_rows, M=m_out, N=n_out, K=ktok, a_kmajor=False, b_kmajor=False, lda=m_out,
                                            ldb=n_out, out=None if out is None else out.view(m_out, n_out), out_dtype=torch.float32,
-                                           accumulate=out is not None and sk > 1, split_k=sk, rowsum=g[bias_name]),
+                                           out_is_zero=out is not None, split_k=-1, rowsum=g[bias_name]),
                             a_rows, b_rows)
 
     dy = dy.contiguous().view(Mq, Co)
@@ -354,7 +348,7 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
                     sec = dict(small=du2, small_off=0, big=sv["qkv"], big_off=slot2 * C, dw=g[wname2])
                 K.dwconv_wgrad(du, dense, 0, grid_out, sv["qkv"], qs, slot * C, thw, B, h, d, stride, g[wname], second=sec)
 
-        fork.run(weight_grads, du, du2)
+        fork.run(weight_grads, du, du2, sv["qkv"])
         sec = None
         if len(items) == 2:
             sec = dict(inp=du2, in_off=0, w=p[wname2], out=dqkv, out_off=slot2 * C)
@@ -373,7 +367,8 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
     g["norm1.weight"], g["norm1.bias"] = zeros("norm1.weight", C), zeros("norm1.bias", C)
     dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
                          add=dx_skip.view(B, N, C))
-    fork.join()
+    if not getattr(wc, "defer_join", False):
+        fork.join()         # by default every block hands complete gradients to autograd (DDP's reducer, plain optimizers)
     return dx, g
 
 

@@ -165,6 +165,9 @@ class OverlappedGradSync:
         if self.pending[g] == 0:
             lo, hi = self.ranges[g]
             self.stream.wait_stream(torch.cuda.current_stream())
+            wc = getattr(self.model, "_wc", None)
+            if wc is not None:
+                wc.join_backward(waiter=self.stream)      # weight gradients are produced on the backward pass's second stream
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(self.arena.flat[lo:hi], op=dist.ReduceOp.AVG)
 

@@ -93,14 +93,28 @@ def train_step(cfg, model, optimizer, inputs, audio_frames, labels_hm, lr=None, 
     scaling = scaler is not None and scaler.is_enabled()
     assert scaling or not cfg.TRAIN.MIXED_PRECISION, "TRAIN.MIXED_PRECISION stores fp16 gradients: pass make_grad_scaler(cfg)"
     root = scaler.scale(loss) if scaling else loss
-    if hasattr(grad_sync, "start"):          # OverlappedGradSync: exchange runs during backward
-        grad_sync.start()
-        root.backward()
-        grad_sync.finish()
-    else:
-        root.backward()
-        if grad_sync is not None:
-            grad_sync()
+    # This function owns the backward pass of an un-wrapped replica, so the weight-gradient branch (block.py::_Fork) may
+    # run un-joined across blocks and is joined once below; under DDP every block joins (the reducer reads gradients
+    # from its own hooks).
+    wc = getattr(model, "_wc", None)
+    if wc is not None:
+        wc.defer_join = True
+    try:
+        if hasattr(grad_sync, "start"):          # OverlappedGradSync: exchange runs during backward
+            grad_sync.start()
+            root.backward()
+            if wc is not None:
+                wc.join_backward()
+            grad_sync.finish()
+        else:
+            root.backward()
+            if wc is not None:
+                wc.join_backward()
+            if grad_sync is not None:
+                grad_sync()
+    finally:
+        if wc is not None:
+            wc.defer_join = False
     clip_val = getattr(cfg.SOLVER, "CLIP_GRAD_VAL", None)
     if hasattr(optimizer, "clip_and_step"):          # FusedClipAdamW: lines 101-109 of the reference loop in two launches
         if clip_val:

@@ -43,16 +43,24 @@ class WeightCache:
         self._fresh = False      # set by the fused optimizer step, which rewrites the copies itself
         self._dirty = False      # a training step ran since the copies were last rebuilt for a non-training forward
         self.arena = None        # GradArena, created by the model at its first training forward
-        self._side = None
+        self._fork = None
+        self.defer_join = False
         self.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
 
-    def side_stream(self):
-        """Stream of the weight-gradient branch of the backward pass (block.py::_Fork), or None when disabled."""
+    def backward_fork(self):
+        """The weight-gradient branch of the backward pass (block.py::_Fork): one second stream per model.  With
+        `defer_join` (set by train_step for the duration of a backward it controls) the branch is joined once, by
+        join_backward(), instead of at the end of every block, so it keeps running under the next blocks' dX chain."""
+        from .block import _Fork
         if not self.fork_backward:
-            return None
-        if self._side is None or self._side.device.index != torch.cuda.current_device():
-            self._side = torch.cuda.Stream()
-        return self._side
+            return _Fork()
+        if self._fork is None or self._fork.side.device.index != torch.cuda.current_device():
+            self._fork = _Fork(torch.cuda.Stream())
+        return self._fork
+
+    def join_backward(self, waiter=None):
+        if self._fork is not None:
+            self._fork.join(waiter)
 
     def begin_training_step(self):
         """Called at the top of every training forward.  A parameter's version counter is not a reliable

@@ -21,12 +21,11 @@ def set_gemm_backend(code: int):
     _FORCE_BACKEND = int(code)
 
 
-def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=None,
-         ldc=None, bias=None, act=0, Z=None, residual=None, res_mod=0, accumulate=False, alpha=1.0, split_k=1,
-         batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None,
-         row_scale=None, rows_per_scale=0, rowsum=None):
-    """C = epi(alpha * op(A) @ op(B)).  A/B are bf16 or f16 storage tensors (independently); offsets/strides
-    in elements.  out_dtype defaults to A's type."""
+def build_gemm_args(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=None,
+                    ldc=None, bias=None, act=0, Z=None, residual=None, res_mod=0, accumulate=False, alpha=1.0, split_k=1,
+                    batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None,
+                    row_scale=None, rows_per_scale=0, rowsum=None, tile_n=0, ctas=0, out_is_zero=False, want_out=False):
+    """The csts_gemm_args block of a gemm() call (same keywords)."""
     assert A.dtype in (torch.bfloat16, torch.float16) and B.dtype in (torch.bfloat16, torch.float16)
     if out_dtype is None:
         out_dtype = A.dtype
@@ -67,20 +66,40 @@ def gemm(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out
     a.res_mod = res_mod
     a.split_k = split_k
     a.alpha = alpha
+    a.tile_n, a.ctas = tile_n, ctas
     a.backend = _FORCE_BACKEND if backend is None else backend
     if bias is not None:
         assert bias.dtype == torch.float32
     if residual is not None:
         assert residual.dtype == torch.float32
+    if out_is_zero and not accumulate:
+        # resolve the split factor first: more than one split accumulates into the zeroed output, a single one overwrites it
+        if _lib.load().csts_gemm_backend(C.byref(a)) == 2:
+            bn_, ct_, sp_ = C.c_int(), C.c_int(), C.c_int()
+            _lib.load().csts_gemm_plan(C.byref(a), C.byref(bn_), C.byref(ct_), C.byref(sp_))
+            a.split_k, a.tile_n, a.ctas = sp_.value, bn_.value, ct_.value
+            a.accumulate = int(sp_.value > 1)
+        else:
+            a.split_k = max(1, split_k)
+            a.accumulate = int(a.split_k > 1)
+    return (a, out) if want_out else a
+
+
+def gemm(A, B, **kw):
+    """C = epi(alpha * op(A) @ op(B)).  A/B are bf16 or f16 storage tensors (independently); offsets/strides
+    in elements.  out_dtype defaults to A's type.  split_k < 0: the library picks the factor.  out_is_zero: `out`
+    holds zeros (a slice of the gradient arena), so a split-K product may accumulate into it without its own memset.
+    tile_n / ctas: tuning overrides of the tcgen05 launcher (0 = automatic).  Keywords: see build_gemm_args."""
+    a, out = build_gemm_args(A, B, want_out=True, **kw)
     if GEMM_PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nb = batch[0] * batch[1]
+        nb = a.batch1 * a.batch2
         ev0.record()
         call("csts_gemm", C.byref(a))
         ev1.record()
         tc = _lib.load().csts_gemm_backend(C.byref(a)) == 2
-        GEMM_PROFILE.append((ev0, ev1, 2.0 * M * N * K * nb, nb * (2.0 * (M * K + N * K) + out.element_size() * M * N), tc,
-                             (M, N, K, nb, int(a_kmajor), int(b_kmajor), act, int(residual is not None), a.c_dtype, split_k)))
+        GEMM_PROFILE.append((ev0, ev1, 2.0 * a.M * a.N * a.K * nb, nb * (2.0 * (a.M * a.K + a.N * a.K) + out.element_size() * a.M * a.N), tc,
+                             (a.M, a.N, a.K, nb, a.a_kmajor, a.b_kmajor, a.act, int(a.residual is not None), a.c_dtype, a.split_k)))
         return out
     call("csts_gemm", C.byref(a))
     return out

@@ -67,16 +67,20 @@ typedef struct csts_gemm_args {
                              3 row softmax of alpha*acc (N <= 256, 16-bit C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)) */
   int32_t accumulate;     /* C += result */
   int32_t res_mod;
-  int32_t split_k;        /* > 1: partial sums combined with f32 atomics (C must be f32) */
+  int32_t split_k;        /* > 1: partial sums combined with f32 atomics (C must be f32); < 0: the library picks the factor */
   float alpha;
   int32_t backend;        /* 0 auto, 1 mma.sync, 2 tcgen05 */
   int32_t rows_per_scale;
   int32_t a_dtype;        /* 1 bf16, 2 f16 */
   int32_t b_dtype;        /* 1 bf16, 2 f16 */
   int32_t z_dtype;        /* 1 bf16, 2 f16 (ignored when Z is NULL) */
+  int32_t tile_n;         /* tuning override of the tcgen05 tile width (96 / 128 / 192 / 256); 0: the library picks */
+  int32_t ctas;           /* tuning override of the kernel build: 1 = one CTA per SM (12 epilogue warps, 512 TMEM columns),
+                             2 = two CTAs per SM (4 epilogue warps, 256 TMEM columns each); 0: the library picks */
 } csts_gemm_args;
 int csts_gemm(const csts_gemm_args* a, void* stream);
 int csts_gemm_backend(const csts_gemm_args* a);  /* 2 = tcgen05, 1 = mma.sync for this problem */
+int csts_gemm_plan(const csts_gemm_args* a, int* tile_n, int* ctas, int* splits);   /* what the tcgen05 launcher would choose */
 
 /* ---- LayerNorm: nn.LayerNorm (attention.py:239,243 norm1/norm2 eps 1e-6; :42-43 norm_q/k/v eps 1e-5) --- */
 int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_binding_matches_header():
     from csts_b200 import _lib
-    bound = set(_lib.SIGNATURES) | {"csts_launch_count", "csts_gemm_backend", "csts_mt_chunk_elems"}
+    bound = set(_lib.SIGNATURES) | {"csts_launch_count", "csts_gemm_backend", "csts_gemm_plan", "csts_mt_chunk_elems"}
     assert bound == set(declared_symbols())
     _lib.load()
 
@@ -73,6 +73,6 @@ def test_product_code_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(base, f), errors="replace").read()
-                if re.search(r"^\s*(import|from)\s+(oracle|csts_oracle|ref_shim)", src, flags=re.M):
+                if re.search(r"^\s*(import|from)\s+(oracle|csts_oracle|ref_shim|ref_train)", src, flags=re.M):
                     bad.append(f)
     assert not bad, bad

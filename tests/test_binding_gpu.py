@@ -94,7 +94,7 @@ def test_reference_build_model_builds_the_b200_model_and_its_loop_trains_it(boun
     want = [train_step(bcfg, twin, topt, *b).item() for b in batches]
     # the forward pass is deterministic: the first loss differs only by the loss kernels' summation order; later
     # steps also see the f32 atomics order of the split-K weight gradients
-    assert abs(got[0][0] - want[0]) <= 2e-6 * abs(want[0]), (got[0], want[0])
+    assert abs(got[0][0] - want[0]) <= 5e-5 * abs(want[0]), (got[0], want[0])
     for g, w in zip(got, want):
         assert abs(g[0] - w) <= 5e-4 * abs(w), (got, want)
     assert got[2][1] < got[0][1]                                          # and it trains: the KL term falls on a repeated batch

@@ -735,3 +735,68 @@ def test_paired_pool_launch_equals_two_single_launches(thw, stride):
     k.dwconv_wgrad(duk, dense, 0, thw_o, qkv, qs, Cn, thw, B, h, d, stride, dwk2,
                    second=dict(small=duv, small_off=0, big=qkv, big_off=2 * Cn, dw=dwv2))
     assert rel_err(dwk2, dwk1) < 1e-5 and rel_err(dwv2, dwv1) < 1e-5 and dwv1.abs().sum() > 0     # atomics: order differs
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 kernel builds
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("tile_n", [96, 128, 192])
+def test_gemm_tc_builds_and_tile_widths(ctas, tile_n):
+    """Both builds of the tcgen05 kernel (one CTA per SM with 12 epilogue warps / two CTAs per SM with 4 epilogue warps and
+    256 TMEM columns each) at every tile width they share, on every epilogue: plain, GELU (+GELU'), times-Z, f32 residual,
+    accumulate, split-K atomics with the fused row sums, and the MN-major operand layouts."""
+    k = K()
+    M, N, Kd = 1100, 384, 448                       # ragged M and K tails
+    g = torch.Generator(device="cpu").manual_seed(31 + tile_n + ctas)
+    A = bf(torch.randn(M, Kd, generator=g)).to(dev)
+    B = bf(torch.randn(N, Kd, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    kw = dict(backend=2, tile_n=tile_n, ctas=ctas)
+    pre = A.float() @ B.float().t() + bias
+    Z = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    h = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, act=1, Z=Z, **kw)
+    pr = pre.clone().requires_grad_(True)
+    (gpre,) = torch.autograd.grad(F.gelu(pr).sum(), pr)
+    assert rel_err(Z, gpre) < 4e-3 and rel_err(h, F.gelu(pre)) < 5e-3
+    o = k.gemm(A, B, M=M, N=N, K=Kd, bias=bias, residual=res, out_dtype=torch.float32, **kw)
+    assert rel_err(o, pre + res) < 2e-5
+    acc = res.clone()
+    k.gemm(A, B, M=M, N=N, K=Kd, out=acc, accumulate=True, **kw)
+    assert rel_err(acc, res + A.float() @ B.float().t()) < 2e-5
+    Bt = B.t().contiguous()                                                   # (K, N): MN-major B (dX = dY . W)
+    o = k.gemm(A, Bt, M=M, N=N, K=Kd, b_kmajor=False, act=2, Z=Z, **kw)
+    assert rel_err(o, (A.float() @ B.float().t()) * Z.float()) < 4e-3
+    # weight-gradient form: both operands token-major, contraction over 1100 tokens, split-K + fused bias gradient
+    X = bf(torch.randn(M, 192, generator=g)).to(dev)
+    dY = bf(torch.randn(M, N, generator=g)).to(dev)
+    want = dY.float().t() @ X.float()
+    for split in (1, 3, -1):
+        db = torch.zeros(N, device=dev)
+        dw = torch.zeros(N, 192, device=dev)
+        tn = 192 if tile_n == 128 else tile_n                                # the fused row sums exist for tile widths 96 and 192
+        k.gemm(dY, X, M=N, N=192, K=M, a_kmajor=False, b_kmajor=False, lda=N, ldb=192, out=dw, out_is_zero=True, split_k=split,
+               rowsum=db, backend=2, tile_n=tn, ctas=ctas)
+        assert rel_err(dw, want) < 2e-5, split
+        assert rel_err(db, dY.float().sum(0)) < 2e-5, split
+
+
+def test_gemm_plan_prefers_resident_problems_for_the_two_cta_build():
+    """csts_gemm_plan: a problem whose tiles are all resident at once with two CTAs per SM takes that build; an automatic
+    split factor keeps >= 4 k-blocks per split and never exceeds the k-block count."""
+    import ctypes as C
+    from csts_b200 import _lib
+    lib = _lib.load()
+
+    def plan(M, N, Kd, a_k=1, b_k=1, split=0, c=1, act=0):
+        a = _lib.GemmArgs()
+        a.M, a.N, a.K, a.batch1, a.batch2, a.a_kmajor, a.b_kmajor, a.c_dtype, a.act, a.split_k = M, N, Kd, 1, 1, a_k, b_k, c, act, split
+        a.a_dtype = a.b_dtype = 1
+        bn, ct, sp = C.c_int(), C.c_int(), C.c_int()
+        assert lib.csts_gemm_plan(C.byref(a), C.byref(bn), C.byref(ct), C.byref(sp)) == 0
+        return bn.value, ct.value, sp.value
+    bn, ct, sp = plan(8000, 384, 320)                  # (not a shape of the tuned table: the cost model decides)
+    assert ct == 2 and sp == 1 and 384 % bn == 0
+    assert plan(8192, 1024, 96, act=3)[:2] == (256, 1)  # whole-row softmax epilogues exist in the one-CTA build only
+    bn, ct, sp = plan(1536, 320, 8192, a_k=0, b_k=0, split=-1, c=0)
+    assert sp > 1 and (8192 // 64) // sp >= 4
+    assert plan(1536, 320, 128, a_k=0, b_k=0, split=-1, c=0)[2] == 1

@@ -428,4 +428,6 @@ def test_prefetched_inputs_reach_the_graphed_step(golden_dir):
         loss = step.step_prefetched()
         step.prefetch([batches[nxt][0]], batches[nxt][1], batches[nxt][2])
         got.append(loss.item())
-    assert all(abs(g - w) <= 2e-5 * abs(w) for g, w in zip(got, [want[0], want[1], want[0]])), (got, want)
+    # (the forward pass holds one split-K product with f32 atomics — the frame pools — whose summation order can flip a
+    #  16-bit rounding downstream: two evaluations of one batch agree to ~1e-5, the two batches differ by 1e-3)
+    assert all(abs(g - w) <= 1e-4 * abs(w) for g, w in zip(got, [want[0], want[1], want[0]])), (got, want)
