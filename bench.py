@@ -298,6 +298,7 @@ def run_gpu(args):
         # per-launch CUDA events then bracket kernels that run back to back (no host-side gaps inside the deltas).
         torch.cuda._sleep(int(0.07 * 1.9e9))
         graphed.model._wc.fork_backward = False      # serial launches: each event pair then brackets one kernel running alone
+        graphed.model._wc.parallel_audio = False
         return train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync, scaler=scaler)
 
     def timed(fn, steps, profile=False):
@@ -334,6 +335,7 @@ def run_gpu(args):
         _, _, prof = timed(eager_profile_step, args.steps, profile=(rank == 0))
     if graphed is not None:
         graphed.model._wc.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
+        graphed.model._wc.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
         graphed.prefetch([video_h], audio_h, hm_h)
     for _ in range(2):
         e2e_step()

@@ -368,20 +368,40 @@ class CSTS(nn.Module):
             self._ensure_arena()
         else:
             wc.begin_inference()
-        x = PatchEmbedFn.apply(wc, video, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
-                               self.pos_embed_spatial, self.pos_embed_temporal)
-        y = PatchEmbedFn.apply(wc, audio, self.patch_embed_audio.proj.weight, self.patch_embed_audio.proj.bias,
-                               self.pos_embed_spatial_audio, self.pos_embed_temporal_audio)
-        B = x.shape[0]
+        # The audio encoder (stem + 4 blocks) is independent of the video encoder until the fusion blocks
+        # (custom_multimodal_builder.py:386-411 interleaves them only textually): it runs on a second stream, so its
+        # kernels share the SMs with the video encoder's many sub-wave launches.  autograd replays each node on the stream
+        # of its forward, so the same overlap holds in backward; inside a captured step the two become graph branches.
         thw = tuple(self.patch_dims)
         thw_a = thw
+        side = wc.audio_stream()
+        main = torch.cuda.current_stream() if side is not None else None
+
+        def audio_encoder():
+            y = PatchEmbedFn.apply(wc, audio, self.patch_embed_audio.proj.weight, self.patch_embed_audio.proj.bias,
+                                   self.pos_embed_spatial_audio, self.pos_embed_temporal_audio)
+            t = thw_a
+            for blk in self.blocks_audio:
+                y, t = self._run_block(blk, y, t)
+            return y, t
+
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                y, thw_a = audio_encoder()
+        x = PatchEmbedFn.apply(wc, video, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
+                               self.pos_embed_spatial, self.pos_embed_temporal)
+        B = x.shape[0]
         skips = [(x, thw)]
         for i, blk in enumerate(self.blocks):
             x, thw = self._run_block(blk, x, thw)
             if i in (0, 2, 13):
                 skips.append((x, thw))
-        for blk in self.blocks_audio:
-            y, thw_a = self._run_block(blk, y, thw_a)
+        if side is not None:
+            main.wait_stream(side)
+            y.record_stream(main)          # allocated on the second stream, consumed (and saved for backward) on this one
+        else:
+            y, thw_a = audio_encoder()
         # spatial fusion (custom_multimodal_builder.py:414-432)
         n_vis = x.shape[1]
         y_sp = FramePoolFn.apply(wc, y, self.audio_pool.weight, self.audio_pool.bias)

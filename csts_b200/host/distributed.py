@@ -167,7 +167,10 @@ class OverlappedGradSync:
             self.stream.wait_stream(torch.cuda.current_stream())
             wc = getattr(self.model, "_wc", None)
             if wc is not None:
-                wc.join_backward(waiter=self.stream)      # weight gradients are produced on the backward pass's second stream
+                # a bucket mixes gradients of the video encoder (this stream), of the audio encoder (its own stream) and
+                # weight gradients produced on the backward pass's second stream
+                for s in wc.branch_streams():
+                    self.stream.wait_stream(s)
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(self.arena.flat[lo:hi], op=dist.ReduceOp.AVG)
 

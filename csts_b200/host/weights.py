@@ -44,7 +44,9 @@ class WeightCache:
         self._dirty = False      # a training step ran since the copies were last rebuilt for a non-training forward
         self.arena = None        # GradArena, created by the model at its first training forward
         self._fork = None
+        self._audio = None
         self.defer_join = False
+        self.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
         self.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
 
     def backward_fork(self):
@@ -57,6 +59,21 @@ class WeightCache:
         if self._fork is None or self._fork.side.device.index != torch.cuda.current_device():
             self._fork = _Fork(torch.cuda.Stream())
         return self._fork
+
+    def audio_stream(self):
+        """Second stream of the forward pass (the audio encoder, csts.py), or None when disabled (CSTS_PARALLEL_AUDIO=0)."""
+        if not self.parallel_audio:
+            return None
+        if self._audio is None or self._audio.device.index != torch.cuda.current_device():
+            self._audio = torch.cuda.Stream()
+        return self._audio
+
+    def branch_streams(self):
+        """Streams other than the caller's on which gradients of this model may still be in flight."""
+        out = [s for s in (self._audio,) if s is not None]
+        if self._fork is not None and self._fork.side is not None:
+            out.append(self._fork.side)
+        return out
 
     def join_backward(self, waiter=None):
         if self._fork is not None:

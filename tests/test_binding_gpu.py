@@ -100,13 +100,14 @@ def test_reference_build_model_builds_the_b200_model_and_its_loop_trains_it(boun
     assert got[2][1] < got[0][1]                                          # and it trains: the KL term falls on a repeated batch
 
     # (3) with the loss lines bound as well (second snippet) the literal loop IS train_step's sequence:
-    #     the first step's loss is bit-identical
+    #     the first step's loss agrees to f32 round-off (the forward pass holds one split-K product combined with f32
+    #     atomics — the frame pools — so two evaluations are not bit-reproducible)
     third = build_model(bcfg)
     third.load_state_dict(sd, strict=True)
     third.train()
     oopt = ref_optim.construct_optimizer(third, cfg)
     bound = _literal_steps(cfg, third, oopt, batches, b_losses, b_frame_softmax, b_sim_matrix)
-    assert bound[0][0] == want[0], (bound[0], want[0])
+    assert abs(bound[0][0] - want[0]) <= 5e-6 * abs(want[0]), (bound[0], want[0])
     for g, w in zip(bound, want):
         assert abs(g[0] - w) <= 5e-4 * abs(w)
 
