@@ -126,16 +126,28 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // erf is evaluated with Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7 — below f32 round-off of the
 // surrounding arithmetic and far below the bf16 storage of the result): one reciprocal, one ex2 and six
 // FMAs instead of libm's branchy erff; exp(-x^2/2) is shared between erf(x/sqrt2) and the Gaussian pdf.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float y = fabsf(x) * 0.70710678118654752f;
-  const float e = __expf(-y * y);                                  // exp(-x^2/2)
-  const float t = __fdividef(1.f, fmaf(0.3275911f, y, 1.f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float erf_abs = fmaf(-poly * t, e, 1.f);                   // erf(|x|/sqrt2)
-  cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+  // z = |x| sqrt(log2(e) / 2): exp(-x^2/2) = 2^(-z^2); the A&S argument y = |x| / sqrt2 = z / sqrt(log2 e).  The flush-to-
+  // zero forms of ex2 / rcp are single MUFU instructions (the default ones wrap them in a denormal-scaling sequence).
+  const float z = fabsf(x) * 0.84932180028801904f;
+  const float e = ex2_ftz(-z * z);                                 // exp(-x^2/2)
+  const float t = rcp_ftz(fmaf(0.3275911f * 0.83255461115769776f, z, 1.f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  const float half_erf = fmaf(-poly * t, e, 0.5f);                 // erf(|x|/sqrt2) / 2
+  cdf = 0.5f + copysignf(half_erf, x);
   pdf = 0.3989422804014327f * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {

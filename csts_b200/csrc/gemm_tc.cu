@@ -57,11 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // %2: suspend-time hint (ns): wait in hardware, not in the issue slots
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
@@ -72,6 +72,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Output tiles leave through TMA as well: registers -> swizzled staging tile -> one cp.async.bulk.tensor store (or
+// f32 reduce-add for split-K partial sums) issued by one lane.  Rows / columns beyond M / N are clipped by the tensor
+// map, so the store path carries no predicates and no per-row address arithmetic, and it is asynchronous: the warp
+// goes on to the next accumulator slice while the copy engine drains the tile.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
@@ -201,6 +219,24 @@ __device__ __forceinline__ void stage_row16(uint32_t stage, int lane, const floa
                                                     pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
   }
 }
+// Output tile of a 16-bit result: 32 rows x 64 bytes, dense, in the 64-byte TMA swizzle (16-byte chunk j of row r at
+// chunk j ^ ((r >> 1) & 3)); `tile` must be 512-byte aligned.  A 16-byte store per lane is conflict-free in this layout.
+__device__ __forceinline__ uint32_t out16_addr(uint32_t tile, int row, int chunk) {
+  return tile + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void stage_out16(uint32_t tile, int lane, const float (&v)[32], bool half) {
+  if (half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(out16_addr(tile, lane, j), make_uint4(pack_f162(v[8 * j], v[8 * j + 1]), pack_f162(v[8 * j + 2], v[8 * j + 3]),
+                                                   pack_f162(v[8 * j + 4], v[8 * j + 5]), pack_f162(v[8 * j + 6], v[8 * j + 7])));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(out16_addr(tile, lane, j), make_uint4(pack_bf162(v[8 * j], v[8 * j + 1]), pack_bf162(v[8 * j + 2], v[8 * j + 3]),
+                                                   pack_bf162(v[8 * j + 4], v[8 * j + 5]), pack_bf162(v[8 * j + 6], v[8 * j + 7])));
+  }
+}
 // lane's 16-bit staging row -> 32 floats
 __device__ __forceinline__ void unstage_row16(uint32_t stage, int lane, float (&o)[32], bool half) {
 #pragma unroll
@@ -295,13 +331,16 @@ __device__ __forceinline__ void slice_prefetch(const TcParams& p, int64_t coff, 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, uint32_t stage, int m0, int n0, int cols_in_tile,
-                                               int lane, uint32_t taddr, float rs, bool first_split, const uint4 (&pre)[8]) {
+                                               int lane, uint32_t taddr, float rs, bool first_split, const uint4 (&pre)[8],
+                                               const CUtensorMap* tmc, const CUtensorMap* tmz, int z2, int z1) {
   constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
   constexpr int ESZ = F32 ? 4 : 2;
   const int rows_valid = min(32, p.M - m0);
   const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
   unsigned char* cg = reinterpret_cast<unsigned char*>(p.C) + (coff + (int64_t)m0 * p.ldc + n0) * ESZ;
-  unsigned char* zg = reinterpret_cast<unsigned char*>(p.Z) + ((int64_t)m0 * p.ldz + n0) * 2;
+  // the bulk store of the previous slice must have read the staging tile before it is written again
+  if (lane == 0) bulk_wait_read0();
+  __syncwarp();
   // global reads first: their latency overlaps the TMEM load
   float4 bv[8];
   const bool use_bias = p.bias != nullptr && first_split;
@@ -333,12 +372,7 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
       gp[i] = fmaf(v[i], pdf, cdf);
       v[i] = v[i] * cdf;
     }
-    if (p.Z) {
-      stage_row16(stage, lane, gp, p.z_half);
-      __syncwarp();
-      stage_store<false>(stage, zg, p.ldz * 2, rows_valid, cols_valid * 2, lane);
-      __syncwarp();
-    }
+    if (p.Z) stage_out16(stage + 2048, lane, gp, p.z_half);     // second 2 KB tile; stored together with C below
   }
   if (EPI == EPI_BF16_DGELU) {
     __syncwarp();
@@ -380,17 +414,22 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
     for (int i = 0; i < 32; ++i) v[i] += of[i];
     __syncwarp();
   }
-  if (F32) {
+  if (F32) {                                     // 32 rows x 128 bytes in the 128-byte TMA swizzle (= stage_addr)
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       sts128(stage_addr(stage, lane, j), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
   } else {
-    stage_row16(stage, lane, v, p.c_half);
+    stage_out16(stage, lane, v, p.c_half);
   }
+  fence_async_smem();                            // generic-proxy writes -> visible to the copy engine
   __syncwarp();
-  stage_store<EPI == EPI_F32_ATOMIC>(stage, cg, p.ldc * ESZ, rows_valid, cols_valid * ESZ, lane);
-  __syncwarp();
+  if (lane == 0) {
+    if (EPI == EPI_BF16_GELU && p.Z) tma_store_4d(tmz, stage + 2048, n0, m0, 0, 0);
+    if (EPI == EPI_F32_ATOMIC) tma_reduce_add_4d(tmc, stage, n0, m0, z2, z1);
+    else tma_store_4d(tmc, stage, n0, m0, z2, z1);
+    bulk_commit();
+  }
 }
 
 // Fused attention-softmax epilogues for key counts that fit one tile (N = Lk <= BN <= 256): a warp owns
@@ -463,7 +502,8 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CTAS>
 __global__ void __launch_bounds__((Cfg<BN, CTAS>::NUM_THREADS), CTAS)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z, TcParams p) {
   using C = Cfg<BN, CTAS>;
   constexpr int NUM_EPI_WARPS = C::NUM_EPI_WARPS;
   constexpr int STAGING_BYTES = C::STAGING_BYTES;
@@ -493,6 +533,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX;      // one warp per quadrant drains a tile
     for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, ROWS ? 4 : NUM_EPI_WARPS); }
@@ -512,15 +553,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // overlaps the tail of the previous kernel in the stream; global memory is first touched below.
   pdl_wait();
 
-  // work item -> (tile_m, tile_n, split); consecutive items walk M first so that the B (weight)
-  // tile stays hot in L2 across neighbouring CTAs
+  // work item -> (tile_m, tile_n, split); consecutive items (= CTAs running at the same time) walk N first: the CTAs that
+  // share an A tile read it within microseconds of each other, so it comes from HBM once and from L2 for the other
+  // n-tiles.  B (a weight, or one head's keys) is small and stays in L2 throughout.  (Walking M first re-read a
+  // 100 MB activation once per n-tile: measured 402 MB of DRAM reads for a 100 MB operand.)
   auto decode = [&](int item, int& tm, int& tn, int& z, int& kb0, int& kb1) {
     int split = item % p.splits;
     int t = item / p.splits;
-    tm = t % tiles_m;
-    t /= tiles_m;
     tn = t % tiles_n;
-    z = t / tiles_n;
+    t /= tiles_n;
+    tm = t % tiles_m;
+    z = t / tiles_m;
     kb0 = split * p.kblocks_per_split;
     kb1 = min(kblocks, kb0 + p.kblocks_per_split);
     return split;
@@ -650,7 +693,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 8; ++i) cur[i] = pre[i];
         const int cn = c + CSTEP, n1 = tn * BN + cn;
         if (side && cn < BN && n1 < p.N) slice_prefetch<EPI_S>(p, coff, m0, n1, BN - cn, lane, split == 0, pre);
-        epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0, cur);
+        epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0, cur, &tmap_c, &tmap_z, z % p.batch2,
+                              z / p.batch2);
       }
       if (rowsum_on && tn == 0 && sub == 0 && live) {      // lane = output row: its sum over this item's k-range
         uint32_t r[32];
@@ -663,6 +707,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       if (++as == C::NACC) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) bulk_wait0();                     // every output tile has reached global memory before the CTA retires
+    __syncwarp();
     }
   }
 
@@ -690,22 +736,26 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 [batch1][batch2][rows][cols] tensor, row pitch ld, batch strides s1 / s2 (elements);
-// box = [1, 1, box_rows, 64 cols], 128B swizzle, out-of-bounds elements read as zero
-int encode_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
+// [batch1][batch2][rows][cols] tensor, row pitch ld, batch strides s1 / s2 (elements); out-of-bounds elements read as
+// zero / are not written.  kind 0: 16-bit GEMM operand, box [box_rows x 64 cols], 128-byte swizzle;
+// kind 1: 16-bit output, box [32 x 32] (64-byte rows, 64-byte swizzle); kind 2: f32 output, box [32 x 32] (128-byte rows,
+// 128-byte swizzle).
+int encode_tmap(CUtensorMap* map, int kind, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
                 int64_t s1, int64_t s2) {
   EncodeTiledFn fn = get_encode_fn();
   CSTS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+  const cuuint64_t esz = kind == 2 ? 4 : 2;
   cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch2, (cuuint64_t)batch1};
   // a dimension of extent 1 still needs a legal (16-byte multiple) stride
-  cuuint64_t gstride[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch2 > 1 ? s2 * 2 : ld * 2), (cuuint64_t)(batch1 > 1 ? s1 * 2 : ld * 2)};
-  cuuint32_t box[4] = {64u, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint64_t gstride[3] = {(cuuint64_t)ld * esz, (cuuint64_t)(batch2 > 1 ? s2 * esz : ld * esz), (cuuint64_t)(batch1 > 1 ? s1 * esz : ld * esz)};
+  cuuint32_t box[4] = {kind == 0 ? 64u : 32u, (cuuint32_t)box_rows, 1u, 1u};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CSTS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld ld=%ld batch=%dx%d strides %ld %ld", (int)r,
-               (long)rows, (long)cols, (long)ld, batch1, batch2, (long)s1, (long)s2);
+  const CUtensorMapDataType dt = kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  const CUtensorMapSwizzle sw = kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, dt, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CSTS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) kind=%d rows=%ld cols=%ld ld=%ld batch=%dx%d strides %ld %ld", (int)r,
+               kind, (long)rows, (long)cols, (long)ld, batch1, batch2, (long)s1, (long)s2);
   return 0;
 }
 
@@ -714,7 +764,7 @@ int encode_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
 // values.  The cache is bounded (cleared when full) and guarded by a mutex: autograd's backward thread and the forward
 // thread both launch GEMMs.
 struct TmapKey {
-  const void* base; int64_t rows, cols, ld, s1, s2; int box_rows, batch1, batch2;
+  const void* base; int64_t rows, cols, ld, s1, s2; int box_rows, batch1, batch2, kind;
   bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -727,23 +777,23 @@ struct TmapKeyHash {
 };
 static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed word-wise");
 
-int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
+int make_tmap(CUtensorMap* map, int kind, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int batch1, int batch2,
               int64_t s1, int64_t s2) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey key;
   std::memset(&key, 0, sizeof(key));
   key.base = base; key.rows = rows; key.cols = cols; key.ld = ld; key.s1 = batch1 > 1 ? s1 : 0; key.s2 = batch2 > 1 ? s2 : 0;
-  key.box_rows = box_rows; key.batch1 = batch1; key.batch2 = batch2;
+  key.box_rows = box_rows; key.batch1 = batch1; key.batch2 = batch2; key.kind = kind;
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
     if (it != cache.end()) { *map = it->second; return 0; }
   }
-  int rc = encode_tmap(map, base, rows, cols, ld, box_rows, batch1, batch2, s1, s2);
+  int rc = encode_tmap(map, kind, base, rows, cols, ld, box_rows, batch1, batch2, s1, s2);
   if (rc) return rc;
   std::lock_guard<std::mutex> g(mu);
-  if (cache.size() >= 8192) cache.clear();
+  if (cache.size() >= 16384) cache.clear();
   cache.emplace(key, *map);
   return 0;
 }
@@ -762,12 +812,21 @@ int launch(const csts_gemm_args& a, const Plan& plan, cudaStream_t stream) {
   CUtensorMap ta, tb;
   // K-major operand X[mn][k]: tensor [mn rows, K cols], box [tile rows, 64 k].
   // MN-major operand X[k][mn]: tensor [K rows, mn cols], box [64 k rows, 64 mn].
-  int rc = A_MN ? make_tmap(&ta, a.A, a.K, a.M, a.lda, BK, a.batch1, a.batch2, a.sA1, a.sA2)
-                : make_tmap(&ta, a.A, a.M, a.K, a.lda, BM, a.batch1, a.batch2, a.sA1, a.sA2);
+  int rc = A_MN ? make_tmap(&ta, 0, a.A, a.K, a.M, a.lda, BK, a.batch1, a.batch2, a.sA1, a.sA2)
+                : make_tmap(&ta, 0, a.A, a.M, a.K, a.lda, BM, a.batch1, a.batch2, a.sA1, a.sA2);
   if (rc) return rc;
-  rc = B_MN ? make_tmap(&tb, a.B, a.K, a.N, a.ldb, BK, a.batch1, a.batch2, a.sB1, a.sB2)
-            : make_tmap(&tb, a.B, a.N, a.K, a.ldb, BN, a.batch1, a.batch2, a.sB1, a.sB2);
+  rc = B_MN ? make_tmap(&tb, 0, a.B, a.K, a.N, a.ldb, BK, a.batch1, a.batch2, a.sB1, a.sB2)
+            : make_tmap(&tb, 0, a.B, a.N, a.K, a.ldb, BN, a.batch1, a.batch2, a.sB1, a.sB2);
   if (rc) return rc;
+  // output tiles (32 x 32) leave through TMA stores / f32 reduce-adds; the whole-row softmax epilogues store directly
+  CUtensorMap tc, tz;
+  rc = make_tmap(&tc, a.c_dtype == 0 ? 2 : 1, a.C, a.M, a.N, a.ldc, 32, a.batch1, a.batch2, a.sC1, a.sC2);
+  if (rc) return rc;
+  tz = tc;
+  if (EPI == EPI_BF16_GELU && a.Z) {
+    rc = make_tmap(&tz, 1, a.Z, a.M, a.N, a.ldz, 32, 1, 1, 0, 0);
+    if (rc) return rc;
+  }
   TcParams p;
   p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual; p.rowsum = a.rowsum;
   p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
@@ -797,7 +856,7 @@ int launch(const csts_gemm_args& a, const Plan& plan, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CSTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, EPI, CTAS>, ta, tb, p));
+  CSTS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, EPI, CTAS>, ta, tb, tc, tz, p));
   return csts_check_launch("gemm_tc_kernel");
 }
 
