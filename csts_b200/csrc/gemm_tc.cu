@@ -882,7 +882,9 @@ double model_ns(const csts_gemm_args& a, const Plan& pl) {
   const double per_col = 1.75;                                   // 128 x 64 x 2 flop per column and k-block at 9.4 TF/s per SM
   double epi = pl.bn * (f32_out ? 14.0 : 8.0) * (pl.splits > 1 ? 1.5 : 1.0);
   if (a.act == 1 || a.act == 2) epi *= 1.6;
-  if (pl.ctas == 2) epi *= 2.2;                                  // 4 epilogue warps instead of 12
+  const bool side_input = a.act == 2 || a.residual != nullptr || a.accumulate;
+  if (pl.ctas == 2 && !side_input) epi *= 2.6;                   // 4 epilogue warps instead of 12; epilogues that wait for a
+                                                                 // side tile (Z, residual, old C) are latency-bound either way
   const double fixed = pl.ctas == 2 ? 1400.0 : 2200.0;
   const double tile = fixed + kb * (pl.bn * per_col * (shared_pipe ? 1.7 : 1.0) + 45.0) + epi;
   const double memset_ns = (pl.splits > 1 && !a.accumulate) ? 2500.0 : 0.0;
