@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("split_k", C.c_int32), ("alpha", C.c_float), ("backend", C.c_int32), ("rows_per_scale", C.c_int32),
         ("a_dtype", C.c_int32), ("b_dtype", C.c_int32), ("z_dtype", C.c_int32),
         ("tile_n", C.c_int32), ("ctas", C.c_int32),
+        ("rowvec", C.c_void_p),
     ]
 
 
@@ -72,6 +73,7 @@ SIGNATURES = {
     "csts_gemm": [C.POINTER(GemmArgs), _P],
     "csts_layernorm_fwd": [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _F, _P],
     "csts_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P, _I, _P, _I, _P],
+    "csts_rowdot": [_P, _P, _I, _P, _I, _I, _I, _I, _P],
     "csts_softmax_fwd": [_P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "csts_softmax_bwd": [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P],
     "csts_cast16": [_P, _P, _I, _L, _I, _I, _P, _I, _P],

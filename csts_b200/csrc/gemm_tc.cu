@@ -157,6 +157,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_
 struct TcParams {
   void* C; void* Z; const float* bias; const float* residual; const float* row_scale;
   float* rowsum;                    // += sum_k A[k][m] (weight-gradient products: the bias gradient), or NULL
+  const float* rowvec;              // per-row f32 input of the attention epilogues, [batch][M]
   int64_t ldc, ldz, ldr;
   int64_t sC1, sC2;                 // batch strides of C (elements)
   int M, N, K;
@@ -298,7 +299,13 @@ __device__ __forceinline__ void stage_store(uint32_t stage, unsigned char* gbase
   }
 }
 
-enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32_ATOMIC = 4, EPI_SOFTMAX = 5, EPI_DSOFTMAX = 6 };
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32_ATOMIC = 4, EPI_SOFTMAX = 5, EPI_DSOFTMAX = 6,
+       // attention with more keys than one tile holds (Lk > 256), in two passes over q.k^T so that neither the f32 scores
+       // nor dP ever reach HBM (the contraction is only d = 96 deep, evaluating it twice is cheap):
+       EPI_LSE = 7,        // pass 1: C[z][m] = logsumexp_n(alpha * acc)  — one CTA walks all n-tiles of its rows, online max / sum
+       EPI_EXPSUB = 8,     // pass 2: C = P = exp(alpha * acc - rowvec[m])                (16-bit)
+       EPI_DSOFTMAX_D = 9  // backward: C = dS = alpha * Z o (acc - rowvec[m]),  Z = P, rowvec = rowsum(dO o O)   (16-bit)
+};
 
 // One 32-column slice of the accumulator rows owned by this warp -> epilogue math -> global memory.
 // m0 = first row of the warp's 32-row band, n0 = first column, `stage` = the warp's staging tile.
@@ -307,7 +314,7 @@ enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_DGELU = 2, EPI_F32 = 3, EPI_F32
 template <int EPI>
 __device__ __forceinline__ bool slice_side_input(const TcParams& p, bool first_split) {
   constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
-  if (EPI == EPI_BF16_DGELU) return true;
+  if (EPI == EPI_BF16_DGELU || EPI == EPI_DSOFTMAX_D) return true;
   if (F32 && p.residual != nullptr && first_split) return true;
   return (EPI == EPI_F32 || EPI == EPI_BF16) && p.accumulate;
 }
@@ -320,6 +327,9 @@ __device__ __forceinline__ void slice_prefetch(const TcParams& p, int64_t coff, 
   const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
   if (EPI == EPI_BF16_DGELU) {
     stage_fetch(pre, reinterpret_cast<const unsigned char*>(p.Z) + ((int64_t)m0 * p.ldz + n0) * 2, p.ldz * 2, rows_valid, cols_valid * 2, lane);
+  } else if (EPI == EPI_DSOFTMAX_D) {          // P has C's layout, batch strides included
+    stage_fetch(pre, reinterpret_cast<const unsigned char*>(p.Z) + (coff + (int64_t)m0 * p.ldz + n0) * 2, p.ldz * 2, rows_valid, cols_valid * 2,
+                lane);
   } else if (F32 && p.residual != nullptr && first_split) {
     int rrow = p.res_mod > 0 ? m0 % p.res_mod : m0;
     stage_fetch(pre, reinterpret_cast<const unsigned char*>(p.residual + (int64_t)rrow * p.ldr + n0), p.ldr * 4, rows_valid, cols_valid * 4, lane);
@@ -331,7 +341,7 @@ __device__ __forceinline__ void slice_prefetch(const TcParams& p, int64_t coff, 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, uint32_t stage, int m0, int n0, int cols_in_tile,
-                                               int lane, uint32_t taddr, float rs, bool first_split, const uint4 (&pre)[8],
+                                               int lane, uint32_t taddr, float rs, float rv, bool first_split, const uint4 (&pre)[8],
                                                const CUtensorMap* tmc, const CUtensorMap* tmz, int z2, int z1) {
   constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
   constexpr int ESZ = F32 ? 4 : 2;
@@ -350,13 +360,26 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
   }
   const bool has_res = F32 && p.residual != nullptr && first_split;
   const bool has_acc = (EPI == EPI_F32 || EPI == EPI_BF16) && p.accumulate;
-  if (EPI == EPI_BF16_DGELU || has_res || has_acc) stage_put(stage, pre, lane);      // tile prefetched by the caller
+  if (EPI == EPI_BF16_DGELU || EPI == EPI_DSOFTMAX_D || has_res || has_acc) stage_put(stage, pre, lane);      // tile prefetched by the caller
   uint32_t r[32];
   tmem_ld32(taddr, r);
   tmem_ld_wait();
   float v[32];
+  if (EPI == EPI_EXPSUB) {                       // P = exp(alpha * s - lse): rv holds lse * log2(e)
+    const float a2 = p.alpha * 1.4426950408889634f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    for (int i = 0; i < 32; ++i) v[i] = ex2_ftz(fmaf(__uint_as_float(r[i]), a2, -rv));
+  } else if (EPI == EPI_DSOFTMAX_D) {            // dS = alpha * P o (dP - D)
+    __syncwarp();
+    float pf[32];
+    unstage_row16(stage, lane, pf, p.z_half);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = p.alpha * pf[i] * (__uint_as_float(r[i]) - rv);
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  }
   if (use_bias) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w; }
@@ -500,6 +523,29 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
   }
 }
 
+// One n-tile of the logsumexp pass: lane = row, running (max, sum) of t = alpha * log2(e) * acc in the base-2 domain.
+__device__ __forceinline__ void lse_tile(const TcParams& p, uint32_t trow, int n_base, int bn, float& m, float& l) {
+  const float a2 = p.alpha * 1.4426950408889634f;
+#pragma unroll 1
+  for (int c = 0; c < bn && n_base + c < p.N; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(trow + c, r);
+    tmem_ld_wait();
+    float t[32], mloc = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      t[i] = (n_base + c + i < p.N) ? __uint_as_float(r[i]) * a2 : -INFINITY;
+      mloc = fmaxf(mloc, t[i]);
+    }
+    const float mnew = fmaxf(m, mloc);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += ex2_ftz(t[i] - mnew);
+    l = l * ex2_ftz(m - mnew) + sum;
+    m = mnew;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI, int CTAS>
 __global__ void __launch_bounds__((Cfg<BN, CTAS>::NUM_THREADS), CTAS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -527,7 +573,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int num_items = tiles_m * tiles_n * p.splits * p.batch;
+  // EPI_LSE: a work item is a row band and the CTA walks its n-tiles itself (the row statistics live in registers)
+  constexpr bool NINNER = EPI == EPI_LSE;
+  const int n_rep = NINNER ? tiles_n : 1;
+  const int num_items = tiles_m * (NINNER ? 1 : tiles_n) * p.splits * p.batch;
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -535,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX;      // one warp per quadrant drains a tile
+    constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX || EPI == EPI_LSE;      // one warp per quadrant drains a tile
     for (int s = 0; s < C::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, ROWS ? 4 : NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -560,8 +609,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto decode = [&](int item, int& tm, int& tn, int& z, int& kb0, int& kb1) {
     int split = item % p.splits;
     int t = item / p.splits;
-    tn = t % tiles_n;
-    t /= tiles_n;
+    tn = 0;
+    if (!NINNER) {
+      tn = t % tiles_n;
+      t /= tiles_n;
+    }
     tm = t % tiles_m;
     z = t / tiles_m;
     kb0 = split * p.kblocks_per_split;
@@ -577,6 +629,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int tm, tn, z, kb0, kb1;
         decode(item, tm, tn, z, kb0, kb1);
         const int z1 = z / p.batch2, z2 = z % p.batch2;
+        for (int rep = 0; rep < n_rep; ++rep) {
+        if (NINNER) tn = rep;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           mbar_expect_tx(full0 + 8 * stage, C::A_BYTES + (B_MN ? C::B_BOXES * 8192 : BN * BK * 2));
@@ -596,6 +650,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -609,6 +664,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int tm, tn, z, kb0, kb1;
         decode(item, tm, tn, z, kb0, kb1);
+        for (int rep = 0; rep < n_rep; ++rep) {
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -633,6 +689,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         umma_commit(tfull0 + 8 * as);                // accumulator complete
         if (++as == C::NACC) { as = 0; aphase ^= 1; }
+        }
       }
     }
   } else {
@@ -640,7 +697,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int sub = (warp - 2) >> 2;                 // which of the quadrant's three warps
     const uint32_t stage_buf = smem_u32(sStage) + (warp - 2) * (32 * 128);
-    if (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) {
+    if (EPI == EPI_LSE) {
+      // logsumexp pass: the first warp of every quadrant follows its 32 rows across the n-tiles of the band
+      int as = 0; uint32_t aphase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int tm, tn, z, kb0, kb1;
+        decode(item, tm, tn, z, kb0, kb1);
+        const int m0 = tm * BM + quad * 32;
+        float m = -INFINITY, l = 0.f;
+        for (int rep = 0; rep < n_rep; ++rep) {
+          if (sub == 0) {
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            if (m0 < p.M) lse_tile(p, tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN, rep * BN, BN, m, l);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+          }
+          if (++as == C::NACC) { as = 0; aphase ^= 1; }
+        }
+        if (sub == 0 && m0 + lane < p.M)
+          reinterpret_cast<float*>(p.C)[(int64_t)z * p.M + m0 + lane] = (m + __log2f(l)) * 0.6931471805599453f;
+      }
+    } else if (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) {
       // whole-row epilogues: the quadrant's warps take turns on successive tiles (tile seq -> warp seq % NSUB),
       // so up to NSUB tiles per quadrant are drained concurrently and no cross-warp reduction exists
       constexpr int NSUB = (C::NACC < NUM_EPI_WARPS / 4 ? C::NACC : NUM_EPI_WARPS / 4);
@@ -668,9 +747,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int split = decode(item, tm, tn, z, kb0, kb1);
       const int64_t coff = (int64_t)(z / p.batch2) * p.sC1 + (int64_t)(z % p.batch2) * p.sC2;
       const int m0 = tm * BM + quad * 32;
-      float rs = 1.f;
+      float rs = 1.f, rv = 0.f;
       if (p.row_scale) rs = p.row_scale[min(m0 + lane, p.M - 1) / p.rows_per_scale];
-      constexpr int EPI_S = (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX) ? EPI_BF16 : EPI;
+      if (EPI == EPI_EXPSUB || EPI == EPI_DSOFTMAX_D) {
+        rv = p.rowvec[(int64_t)z * p.M + min(m0 + lane, p.M - 1)];
+        if (EPI == EPI_EXPSUB) rv *= 1.4426950408889634f;
+      }
+      constexpr int EPI_S = (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX || EPI == EPI_LSE) ? EPI_BF16 : EPI;
       constexpr int CSTEP = (NUM_EPI_WARPS / 4) * 32;
       const bool live = m0 < p.M && kb1 > kb0;       // rows beyond M / an empty k-range contribute nothing
       const bool side = live && slice_side_input<EPI_S>(p, split == 0);
@@ -693,7 +776,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 8; ++i) cur[i] = pre[i];
         const int cn = c + CSTEP, n1 = tn * BN + cn;
         if (side && cn < BN && n1 < p.N) slice_prefetch<EPI_S>(p, coff, m0, n1, BN - cn, lane, split == 0, pre);
-        epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, split == 0, cur, &tmap_c, &tmap_z, z % p.batch2,
+        epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, rv, split == 0, cur, &tmap_c, &tmap_z, z % p.batch2,
                               z / p.batch2);
       }
       if (rowsum_on && tn == 0 && sub == 0 && live) {      // lane = output row: its sum over this item's k-range
@@ -820,15 +903,19 @@ int launch(const csts_gemm_args& a, const Plan& plan, cudaStream_t stream) {
   if (rc) return rc;
   // output tiles (32 x 32) leave through TMA stores / f32 reduce-adds; the whole-row softmax epilogues store directly
   CUtensorMap tc, tz;
-  rc = make_tmap(&tc, a.c_dtype == 0 ? 2 : 1, a.C, a.M, a.N, a.ldc, 32, a.batch1, a.batch2, a.sC1, a.sC2);
-  if (rc) return rc;
+  if (EPI == EPI_LSE) {
+    tc = ta;                                     // the logsumexp pass writes one float per row with plain stores
+  } else {
+    rc = make_tmap(&tc, a.c_dtype == 0 ? 2 : 1, a.C, a.M, a.N, a.ldc, 32, a.batch1, a.batch2, a.sC1, a.sC2);
+    if (rc) return rc;
+  }
   tz = tc;
   if (EPI == EPI_BF16_GELU && a.Z) {
     rc = make_tmap(&tz, 1, a.Z, a.M, a.N, a.ldz, 32, 1, 1, 0, 0);
     if (rc) return rc;
   }
   TcParams p;
-  p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual; p.rowsum = a.rowsum;
+  p.C = a.C; p.Z = a.Z; p.bias = a.bias; p.residual = a.residual; p.rowsum = a.rowsum; p.rowvec = a.rowvec;
   p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
   p.ldc = a.ldc; p.ldz = a.ldz; p.ldr = a.ldr;
   p.sC1 = a.sC1; p.sC2 = a.sC2; p.batch = a.batch1 * a.batch2; p.batch2 = a.batch2;
@@ -843,7 +930,7 @@ int launch(const csts_gemm_args& a, const Plan& plan, cudaStream_t stream) {
     CSTS_REQUIRE(p.batch == 1, "gemm_tc: split-K without accumulate supports a single batch");
     CSTS_CUDA(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, (size_t)a.N * sizeof(float), a.M, stream));
   }
-  const int items = ceil_div(a.M, BM) * ceil_div(a.N, BN) * p.splits * p.batch;
+  const int items = ceil_div(a.M, BM) * (EPI == EPI_LSE ? 1 : ceil_div(a.N, BN)) * p.splits * p.batch;
   const int slots = csts_num_sms() * CTAS;
   const int grid = items < slots ? items : slots;
   cudaLaunchConfig_t cfg = {};
@@ -891,7 +978,7 @@ double model_ns(const csts_gemm_args& a, const Plan& pl) {
   return waves * tile + memset_ns;
 }
 
-bool small_variant_exists(int bn, int act) { return bn != 256 && act != 3 && act != 4; }
+bool small_variant_exists(int bn, int act) { return bn != 256 && act != 3 && act != 4 && act != 5; }
 
 // Measured plans (benchmarks/tune_gemm.py on a B200) for the problems of the benchmarked training step
 struct TunedPlan { int M, N, K, batch, a_kmajor, b_kmajor, act, c16, rowsum, auto_split, bn, ctas, splits; };
@@ -918,6 +1005,7 @@ Plan plan_for(const csts_gemm_args& a) {
   int bn_lo = 0, bn_hi = 3;
   int fixed_bn = a.tile_n ? a.tile_n : force_bn;
   if (a.act == 3 || a.act == 4) fixed_bn = a.N <= 96 ? 96 : (a.N <= 128 ? 128 : (a.N <= 192 ? 192 : 256));   // one tile holds all keys
+  else if (a.act == 5) fixed_bn = 256;           // logsumexp pass: two 256-column accumulators alternate
   else if (a.rowsum) fixed_bn = a.N <= 96 ? 96 : 192;            // tile widths that leave TMEM columns for the fused row sums
   int best_pad = 1 << 30;
   for (int i = 0; i < 4; ++i) best_pad = std::min(best_pad, ceil_div(a.N, cands[i]) * cands[i]);
@@ -946,7 +1034,7 @@ Plan plan_for(const csts_gemm_args& a) {
 
 template <bool A_MN, bool B_MN, int EPI>
 int dispatch(const csts_gemm_args& a, const Plan& pl, cudaStream_t stream) {
-  constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX;
+  constexpr bool ROWS = EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX || EPI == EPI_LSE;
   if (pl.ctas == 2) {
     if constexpr (!ROWS) {
       switch (pl.bn) {
@@ -981,7 +1069,7 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   // coalesced epilogue: 16-byte aligned rows, whole 16-byte chunks
   if (((uintptr_t)a.C & 15) || (a.ldc * cbytes) % 16 || ((int64_t)a.N * cbytes) % 16) return false;
   if (nb > 1 && (((a.sC1 | a.sC2) * cbytes) % 16 != 0)) return false;
-  if (a.Z && a.act != 4 && (nb > 1 || ((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
+  if (a.Z && a.act != 4 && a.act != 7 && (nb > 1 || ((uintptr_t)a.Z & 15) || (a.ldz * 2) % 16)) return false;
   if (a.residual && (nb > 1 || ((uintptr_t)a.residual & 15) || (a.ldr * 4) % 16)) return false;
   if (a.res_mod > 0 && a.res_mod % 32 != 0) return false;
   if (a.bias && (((uintptr_t)a.bias & 15) || a.N % 4 != 0)) return false;
@@ -992,6 +1080,14 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
         a.split_k > 1 || a.ldc % 8 != 0 || a.ldc < a.N || a.M < 64)
       return false;
     if (a.act == 4 && (!a.Z || a.ldz != a.ldc || ((uintptr_t)a.Z & 15))) return false;
+    return true;
+  }
+  if (a.act >= 5 && a.act <= 7) {                      // two-pass attention epilogues (more keys than one tile holds)
+    if (!a.a_kmajor || !a.b_kmajor || a.bias || a.residual || a.accumulate || a.row_scale || a.split_k > 1 || a.split_k < 0 || a.M < 64)
+      return false;
+    if (a.act == 5) return a.c_dtype == 0 && !a.Z;                                   // C = logsumexp rows, f32 [batch][M]
+    if (!a.rowvec || a.c_dtype == 0 || a.ldc % 8 != 0) return false;
+    if (a.act == 7 && (!a.Z || a.ldz != a.ldc || ((uintptr_t)a.Z & 15))) return false;
     return true;
   }
   if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with 16-bit outputs only
@@ -1014,6 +1110,9 @@ int csts_gemm_tc_launch(const csts_gemm_args& a, cudaStream_t stream) {
   const bool atomic = pl.splits > 1;
   if (a.act == 3) return dispatch<false, false, EPI_SOFTMAX>(a, pl, stream);
   if (a.act == 4) return dispatch<false, false, EPI_DSOFTMAX>(a, pl, stream);
+  if (a.act == 5) return dispatch<false, false, EPI_LSE>(a, pl, stream);
+  if (a.act == 6) return dispatch<false, false, EPI_EXPSUB>(a, pl, stream);
+  if (a.act == 7) return dispatch<false, false, EPI_DSOFTMAX_D>(a, pl, stream);
   if (!a.a_kmajor) {                                    // (MN, MN): weight gradients, dV / dK of attention
     if (a.c_dtype != 0) return dispatch<true, true, EPI_BF16>(a, pl, stream);
     return atomic ? dispatch<true, true, EPI_F32_ATOMIC>(a, pl, stream) : dispatch<true, true, EPI_F32>(a, pl, stream);

@@ -253,6 +253,35 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const TP* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// D[b][head][q] = sum_d dO[b][q][head][d] * O[b][q][head][d]: the row term of the softmax backward, rowsum(dP o P) = dO . O,
+// so that dP itself never has to exist.  One warp per (b, q) token; 8 consecutive lanes own a 64-column stripe.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rowdot_kernel(const T* __restrict__ dO, const T* __restrict__ O, float* __restrict__ D, int B, int Lq,
+                                                     int heads, int d) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int Cn = heads * d;
+  for (int64_t tok = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); tok < (int64_t)B * Lq; tok += (int64_t)gridDim.x * wpb) {
+    const T* a = dO + tok * Cn;
+    const T* b = O + tok * Cn;
+    const int bi = (int)(tok / Lq), q = (int)(tok - (int64_t)bi * Lq);
+    for (int h = 0; h < heads; ++h) {
+      float acc = 0.f;
+      for (int c = lane * 4; c < d; c += 128) {
+        float x[4], y[4];
+        ld4(a + h * d + c, x);
+        ld4(b + h * d + c, y);
+        acc += x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) D[((int64_t)bi * heads + h) * Lq + q] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // casts / permutes / elementwise
 // ------------------------------------------------------------------------------------------------
 // f32 [rows, cols] -> 16-bit [rows, ld_out] (zero padded columns), T in {bf16, f16}
@@ -467,11 +496,25 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
   else if (x_dtype == 2 && dy_dtype == 2 && dx_dtype == 2) LN_BWD(f16, f16, f16);
   else if (x_dtype == 2 && dy_dtype == 1 && dx_dtype == 1) LN_BWD(f16, bf16, bf16);
   else if (x_dtype == 1 && dy_dtype == 1 && dx_dtype == 1) LN_BWD(bf16, bf16, bf16);
+  else if (x_dtype == 1 && dy_dtype == 0 && dx_dtype == 1) LN_BWD(bf16, float, bf16);      // split-K (f32) dK / dV of the pooled keys
+  else if (x_dtype == 2 && dy_dtype == 0 && dx_dtype == 2) LN_BWD(f16, float, f16);
   else if (x_dtype == 0 && dy_dtype == 0 && dx_dtype == 0) LN_BWD(float, float, float);
   else CSTS_REQUIRE(false, "layernorm_bwd: unsupported dtype combination x=%d dy=%d dx=%d", x_dtype, dy_dtype, dx_dtype);
 #undef LN_BWD
 #undef LN_BWD_J
   return csts_check_launch("layernorm_bwd");
+}
+
+int csts_rowdot(const void* dO, const void* O, int dtype, float* D, int B, int Lq, int heads, int d, void* stream) {
+  CSTS_REQUIRE(dtype == CSTS_BF16 || dtype == CSTS_F16, "rowdot: 16-bit inputs only");
+  CSTS_REQUIRE(d % 4 == 0, "rowdot: head dim %d must be a multiple of 4", d);
+  if ((int64_t)B * Lq == 0) return 0;
+  const int grid = grid_for((int64_t)B * Lq, 8);
+  if (dtype == CSTS_F16)
+    launch_pdl(rowdot_kernel<f16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const f16*)dO, (const f16*)O, D, B, Lq, heads, d);
+  else
+    launch_pdl(rowdot_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dO, (const bf16*)O, D, B, Lq, heads, d);
+  return csts_check_launch("rowdot");
 }
 
 int csts_softmax_fwd(const float* S, void* P, int p_dtype, int64_t rows, int n, int lds, int ldp, int nq, int mask_hw, int mask_t,

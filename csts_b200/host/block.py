@@ -100,10 +100,18 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
     scale = d ** -0.5
     # Lk <= 256 (20 of the 26 blocks): softmax runs in the epilogue of the q.k^T kernel, S never reaches HBM
     fused_softmax = Lk <= 256 and Lq >= 64 and spec.kind != "spatial"
+    # Lk > 256 (6 blocks, 1024 keys): two passes over q.k^T — row logsumexp first, then P = exp(scale * s - lse) from the
+    # epilogue of a second evaluation (the contraction is only d deep); the f32 scores never reach HBM either
+    two_pass = not fused_softmax and spec.kind != "spatial" and Lq >= 64 and Lk % 8 == 0 and not want_attn
+    qk = dict(M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, alpha=scale, batch=(B, h), sA=(q.sB, q.sH), sB=(k.sB, k.sH), a_off=q.off, b_off=k.off)
     if fused_softmax:
         P = torch.empty((B, h, Lq, ldS), dtype=wc.act, device=x.device)
-        K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=P, ldc=ldS, alpha=scale, act=3, batch=(B, h),
-               sA=(q.sB, q.sH), sB=(k.sB, k.sH), sC=(h * Lq * ldS, Lq * ldS), a_off=q.off, b_off=k.off)
+        K.gemm(q.buf, k.buf, out=P, ldc=ldS, act=3, sC=(h * Lq * ldS, Lq * ldS), **qk)
+    elif two_pass:
+        lse = torch.empty((B, h, Lq), dtype=torch.float32, device=x.device)
+        K.gemm(q.buf, k.buf, out=lse, ldc=Lk, act=5, sC=(h * Lq, Lq), **qk)
+        P = torch.empty((B, h, Lq, ldS), dtype=wc.act, device=x.device)
+        K.gemm(q.buf, k.buf, out=P, ldc=ldS, act=6, rowvec=lse, sC=(h * Lq * ldS, Lq * ldS), **qk)
     else:
         S = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=x.device)
         K.gemm(q.buf, k.buf, M=Lq, N=Lk, K=d, lda=q.sP, ldb=k.sP, out=S, ldc=ldS, alpha=scale, batch=(B, h),
@@ -147,7 +155,7 @@ def block_forward(spec, p, wc, x, thw, dp_scale=None, save=True, want_attn=False
         return y, thw_q, None, attn
     sv.update(x=x, thw=tuple(thw), mean1=mean1, rstd1=rstd1, xn1=xn1, qkv=qkv, q=q, k=k, v=v, P=P, o=o, arg=arg,
               x1=x1, mean2=mean2, rstd2=rstd2, xn2=xn2, Z=Z, hdn=hdn, dp=dp_scale, Lq=Lq, Lk=Lk, ldS=ldS, thw_q=thw_q,
-              fused_softmax=fused_softmax)
+              fused_softmax=fused_softmax, two_pass=two_pass)
     return y, thw_q, sv, attn
 
 
@@ -290,19 +298,34 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
     qs = (N * 3 * C, d, 3 * C)
     pooled_q, pooled_kv = spec.stride_q is not None, spec.stride_kv is not None
 
-    def grad_target(pooled, L, slot):
+    # dV = P^T.dO and dK = dS^T.Q contract over the Lq queries.  With few pooled keys and many queries (the decoder: 64 keys,
+    # up to 32768 queries) the product has fewer output tiles than SMs: it is then split over the queries into an f32
+    # buffer (vectorised reduce-adds), which the LayerNorm backward of the pool reads directly.
+    split_kv = pooled_kv and B * h * ((Lk + 127) // 128) * 2 <= 148 and Lq >= 2048
+
+    def grad_target(pooled, L, slot, split=False):
+        if pooled and split:
+            t = torch.zeros((B, h, L, d), dtype=torch.float32, device=dev)
+            return t, dict(out=t, ldc=d, sC=(h * L * d, L * d), c_off=0, out_is_zero=True, split_k=-1)
         if pooled:
             t = torch.empty((B, h, L, d), dtype=wc.grad, device=dev)
             return t, dict(out=t, ldc=d, sC=(h * L * d, L * d), c_off=0)
         return None, dict(out=dqkv, ldc=3 * C, sC=(qs[0], qs[1]), c_off=slot * C)
 
     sP = (h * Lq * ldS, Lq * ldS)
-    dv_t, tgt = grad_target(pooled_kv, Lk, 2)
+    dv_t, tgt = grad_target(pooled_kv, Lk, 2, split_kv)
     K.gemm(P, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=C, batch=(B, h), sA=sP, sB=(Lq * C, d), **tgt)
     if sv["fused_softmax"]:
         # dS = scale * P o (dP - rowsum(dP o P)) in the epilogue of the dO.v^T kernel: dP never reaches HBM
         dS = torch.empty(P.shape, dtype=wc.grad, device=dev)
         K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dS, ldc=ldS, alpha=d ** -0.5, act=4, Z=P, batch=(B, h),
+               sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP, b_off=v.off)
+    elif sv.get("two_pass") and d_audio_rows is None:
+        # rowsum(dP o P) = dO . O: with that row term in hand dS = scale * P o (dP - D) is element-wise in the epilogue of
+        # the dO.v^T kernel, for any number of keys — dP never reaches HBM
+        D = K.rowdot(do, sv["o"], B, Lq, h, d)
+        dS = torch.empty(P.shape, dtype=wc.grad, device=dev)
+        K.gemm(do, v.buf, M=Lq, N=Lk, K=d, lda=C, ldb=v.sP, out=dS, ldc=ldS, alpha=d ** -0.5, act=7, Z=P, rowvec=D, batch=(B, h),
                sA=(Lq * C, d), sB=(v.sB, v.sH), sC=sP, b_off=v.off)
     else:
         dP = torch.empty((B, h, Lq, ldS), dtype=torch.float32, device=dev)
@@ -316,7 +339,7 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         del dP
     dq_t, tgt = grad_target(pooled_q, Lq, 0)
     K.gemm(dS, k.buf, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=k.sP, batch=(B, h), sA=sP, sB=(k.sB, k.sH), b_off=k.off, **tgt)
-    dk_t, tgt = grad_target(pooled_kv, Lk, 1)
+    dk_t, tgt = grad_target(pooled_kv, Lk, 1, split_kv)
     K.gemm(dS, q.buf, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=q.sP, batch=(B, h), sA=sP, sB=(q.sB, q.sH),
            b_off=q.off, **tgt)
     del dS

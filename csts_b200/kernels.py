@@ -24,7 +24,8 @@ def set_gemm_backend(code: int):
 def build_gemm_args(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ldb=None, out=None, out_dtype=None,
                     ldc=None, bias=None, act=0, Z=None, residual=None, res_mod=0, accumulate=False, alpha=1.0, split_k=1,
                     batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), a_off=0, b_off=0, c_off=0, backend=None,
-                    row_scale=None, rows_per_scale=0, rowsum=None, tile_n=0, ctas=0, out_is_zero=False, want_out=False):
+                    row_scale=None, rows_per_scale=0, rowsum=None, tile_n=0, ctas=0, out_is_zero=False, want_out=False,
+                    rowvec=None):
     """The csts_gemm_args block of a gemm() call (same keywords)."""
     assert A.dtype in (torch.bfloat16, torch.float16) and B.dtype in (torch.bfloat16, torch.float16)
     if out_dtype is None:
@@ -48,6 +49,7 @@ def build_gemm_args(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ld
     a.residual = residual.data_ptr() if residual is not None else None
     a.row_scale = row_scale.data_ptr() if row_scale is not None else None
     a.rowsum = rowsum.data_ptr() if rowsum is not None else None      # f32 [M], += row sums of op(A) (bias gradient of a wgrad)
+    a.rowvec = rowvec.data_ptr() if rowvec is not None else None      # f32 [batch][M] (two-pass attention epilogues)
     a.rows_per_scale = rows_per_scale
     a.lda, a.ldb, a.ldc = lda, ldb, ldc
     a.ldz = ldc
@@ -74,6 +76,7 @@ def build_gemm_args(A, B, *, M, N, K, a_kmajor=True, b_kmajor=True, lda=None, ld
         assert residual.dtype == torch.float32
     if out_is_zero and not accumulate:
         # resolve the split factor first: more than one split accumulates into the zeroed output, a single one overwrites it
+        a.accumulate = 1
         if _lib.load().csts_gemm_backend(C.byref(a)) == 2:
             bn_, ct_, sp_ = C.c_int(), C.c_int(), C.c_int()
             _lib.load().csts_gemm_plan(C.byref(a), C.byref(bn_), C.byref(ct_), C.byref(sp_))
@@ -144,6 +147,14 @@ def softmax_bwd(P, dP, n, scale, dtype=None):
     dS = torch.empty(P.shape, dtype=P.dtype if dtype is None else dtype, device=P.device)
     call("csts_softmax_bwd", ptr(P), dt(P), ptr(dP), ptr(dS), dt(dS), rows, n, ldp, dP.shape[-1], scale)
     return dS
+
+
+def rowdot(dO, O, B, Lq, heads, d):
+    """D[b, head, q] = sum_d dO[b, q, head, d] * O[b, q, head, d]  (f32) for 16-bit (B*Lq, heads*d) tensors."""
+    assert dO.dtype == O.dtype and dO.is_contiguous() and O.is_contiguous()
+    D = torch.empty((B, heads, Lq), dtype=torch.float32, device=O.device)
+    call("csts_rowdot", ptr(dO), ptr(O), dt(O), ptr(D), B, Lq, heads, d)
+    return D
 
 
 def cast16(src, dtype, ld_out=None, row_scale=None, rows_per_scale=0, out=None):

@@ -64,7 +64,10 @@ typedef struct csts_gemm_args {
   int32_t b_kmajor;       /* 1: B[n*ldb + k]   0: B[k*ldb + n] */
   int32_t c_dtype;        /* 0 f32, 1 bf16, 2 f16 */
   int32_t act;            /* 0 none, 1 erf GELU (nn.GELU(), common.py:21; Z <- GELU'), 2 times Z (GELU backward),
-                             3 row softmax of alpha*acc (N <= 256, 16-bit C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)) */
+                             3 row softmax of alpha*acc (N <= 256, 16-bit C = P), 4 softmax backward: C = alpha*Z o (acc - rowsum(acc o Z)),
+                             two-pass attention for N > 256 (neither the f32 scores nor dP reach memory):
+                             5 C[z][m] = logsumexp_n(alpha*acc) (f32, one value per row), 6 C = exp(alpha*acc - rowvec[z][m]) (16-bit P),
+                             7 C = alpha * Z o (acc - rowvec[z][m]) (16-bit dS; Z = P with C's layout, rowvec = rowsum(dO o O)) */
   int32_t accumulate;     /* C += result */
   int32_t res_mod;
   int32_t split_k;        /* > 1: partial sums combined with f32 atomics (C must be f32); < 0: the library picks the factor */
@@ -77,10 +80,15 @@ typedef struct csts_gemm_args {
   int32_t tile_n;         /* tuning override of the tcgen05 tile width (96 / 128 / 192 / 256); 0: the library picks */
   int32_t ctas;           /* tuning override of the kernel build: 1 = one CTA per SM (12 epilogue warps, 512 TMEM columns),
                              2 = two CTAs per SM (4 epilogue warps, 256 TMEM columns each); 0: the library picks */
+  const float* rowvec;    /* act 6 / 7: f32 [batch][M] per-row input (row logsumexp; rowsum(dO o O)) */
 } csts_gemm_args;
 int csts_gemm(const csts_gemm_args* a, void* stream);
 int csts_gemm_backend(const csts_gemm_args* a);  /* 2 = tcgen05, 1 = mma.sync for this problem */
 int csts_gemm_plan(const csts_gemm_args* a, int* tile_n, int* ctas, int* splits);   /* what the tcgen05 launcher would choose */
+
+/* D[b][head][q] = sum_d dO[b][q][head][d] * O[b][q][head][d] for two 16-bit (B, Lq, heads*d) tensors: the row term of the
+ * softmax backward (rowsum(dP o P) = dO . O), computed without dP (attention.py:154-158 backward) */
+int csts_rowdot(const void* dO, const void* O, int dtype, float* D, int B, int Lq, int heads, int d, void* stream);
 
 /* ---- LayerNorm: nn.LayerNorm (attention.py:239,243 norm1/norm2 eps 1e-6; :42-43 norm_q/k/v eps 1e-5) --- */
 int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, float* mean,

@@ -800,3 +800,45 @@ def test_gemm_plan_prefers_resident_problems_for_the_two_cta_build():
     bn, ct, sp = plan(1536, 320, 8192, a_k=0, b_k=0, split=-1, c=0)
     assert sp > 1 and (8192 // 64) // sp >= 4
     assert plan(1536, 320, 128, a_k=0, b_k=0, split=-1, c=0)[2] == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("Lq,Lk,heads", [(256, 1024, 2), (1000, 520, 1)])
+def test_two_pass_attention_epilogues(Lq, Lk, heads, dtype):
+    """Attention with more keys than one accumulator tile holds (attention.py:154-158 at the 1024-key blocks): pass 1 = row
+    logsumexp of scale * q.k^T (one CTA walks the n-tiles), pass 2 = P = exp(scale * s - lse) from a second evaluation;
+    backward dS = scale * P o (dP - D) with D = rowsum(dO o O) — against torch softmax and its autograd."""
+    k = K()
+    B, d = 2, 96
+    g = torch.Generator(device="cpu").manual_seed(Lq + Lk)
+    q = (torch.randn(B, heads, Lq, d, generator=g) * 1.5).to(dtype).to(dev)
+    kk = (torch.randn(B, heads, Lk, d, generator=g) * 1.5).to(dtype).to(dev)
+    v = torch.randn(B, heads, Lk, d, generator=g).to(dtype).to(dev)
+    scale = d ** -0.5
+    S = (q.float() @ kk.float().transpose(-1, -2)) * scale
+    ldS = (Lk + 7) // 8 * 8
+    qk = dict(M=Lq, N=Lk, K=d, lda=d, ldb=d, alpha=scale, batch=(B, heads), sA=(heads * Lq * d, Lq * d), sB=(heads * Lk * d, Lk * d), backend=2)
+    lse = torch.empty(B, heads, Lq, device=dev)
+    k.gemm(q, kk, out=lse, ldc=Lk, act=5, sC=(heads * Lq, Lq), **qk)
+    assert (lse - torch.logsumexp(S, dim=-1)).abs().max() < 2e-4
+    P = torch.zeros(B, heads, Lq, ldS, dtype=dtype, device=dev)
+    k.gemm(q, kk, out=P, ldc=ldS, act=6, rowvec=lse, sC=(heads * Lq * ldS, Lq * ldS), **qk)
+    ref_p = torch.softmax(S, dim=-1)
+    tol = 4e-3 if dtype == torch.bfloat16 else 1e-3
+    assert rel_err(P[..., :Lk], ref_p) < tol
+    assert (P[..., :Lk].float().sum(-1) - 1).abs().max() < 2e-2
+    # backward: O = P.V, dO given
+    o = (P[..., :Lk].float() @ v.float())                                     # (B, heads, Lq, d)
+    o16 = o.permute(0, 2, 1, 3).reshape(B * Lq, heads * d).to(dtype).contiguous()
+    do16 = torch.randn(B * Lq, heads * d, generator=g).to(dtype).to(dev)
+    D = k.rowdot(do16, o16, B, Lq, heads, d)
+    do = do16.float().view(B, Lq, heads, d).permute(0, 2, 1, 3)
+    assert rel_err(D, (do * o16.float().view(B, Lq, heads, d).permute(0, 2, 1, 3)).sum(-1)) < 1e-5
+    dS = torch.zeros(B, heads, Lq, ldS, dtype=dtype, device=dev)
+    Cn = heads * d
+    k.gemm(do16, v, M=Lq, N=Lk, K=d, lda=Cn, ldb=d, out=dS, ldc=ldS, alpha=scale, act=7, Z=P, rowvec=D, batch=(B, heads),
+           sA=(Lq * Cn, d), sB=(heads * Lk * d, Lk * d), sC=(heads * Lq * ldS, Lq * ldS), backend=2)
+    Pf = P[..., :Lk].float()
+    dP = do @ v.float().transpose(-1, -2)
+    want = scale * Pf * (dP - (dP * Pf).sum(-1, keepdim=True))
+    assert rel_err(dS[..., :Lk], want) < (2e-2 if dtype == torch.bfloat16 else 5e-3)
