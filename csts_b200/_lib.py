@@ -73,6 +73,7 @@ SIGNATURES = {
     "csts_gemm": [C.POINTER(GemmArgs), _P],
     "csts_layernorm_fwd": [_P, _I, _P, _I, _P, _P, _P, _P, _L, _I, _F, _P],
     "csts_layernorm_bwd": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _P, _I, _P, _I, _P],
+    "csts_layernorm_bwd_pair": [_P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _P],
     "csts_rowdot": [_P, _P, _I, _P, _I, _I, _I, _I, _P],
     "csts_softmax_fwd": [_P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "csts_softmax_bwd": [_P, _I, _P, _P, _I, _L, _I, _I, _I, _F, _P],
@@ -162,6 +163,7 @@ def dt(t):
 
 
 _device_checked = False
+PROFILE = None        # when a list: every call() appends (name, start_event, end_event) — tools/step_profile.py
 
 
 def call(name, *args):
@@ -173,4 +175,11 @@ def call(name, *args):
             raise RuntimeError("csts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         check(lib.csts_check_device(), "csts_check_device")
         _device_checked = True
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib, name)(*args, stream_ptr()), name)
+        e1.record()
+        PROFILE.append((name + str(tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool))), e0, e1))
+        return
     check(getattr(lib, name)(*args, stream_ptr()), name)

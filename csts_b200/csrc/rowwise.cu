@@ -75,14 +75,23 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI* __restrict
 // across the warp's row groups by shuffles and across the block's warps in shared memory, and reach global memory as
 // 2 * width atomics per BLOCK — a few hundred per address per launch instead of one per 32 rows.
 // ------------------------------------------------------------------------------------------------
+// second problem of a paired launch (blockIdx.y == 1): same geometry and types, other tensors — the norm_k / norm_v
+// backward of a block run as one launch
+struct LnSecond { const void* dy; const void* x; const float* mean; const float* rstd; const float* gamma; void* dx; float* dgamma; float* dbeta; };
+
 template <typename TX, typename TDY, typename TDX, int LPR, int J, int U>
 __global__ void __launch_bounds__(256, J <= 3 ? 2 : 1) layernorm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ add,
                                                             TDX* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int rows, int width, void* __restrict__ dx16,
-                                                            int dx16_half, const float* __restrict__ row_scale, int rows_per_scale) {
+                                                            int dx16_half, const float* __restrict__ row_scale, int rows_per_scale,
+                                                            LnSecond sec) {
   pdl_wait();
+  if (blockIdx.y == 1) {
+    dy = reinterpret_cast<const TDY*>(sec.dy); x = reinterpret_cast<const TX*>(sec.x); mean = sec.mean; rstd = sec.rstd; gamma = sec.gamma;
+    dx = reinterpret_cast<TDX*>(sec.dx); dgamma = sec.dgamma; dbeta = sec.dbeta;
+  }
   __shared__ float s_dg[768], s_db[768];
   for (int i = threadIdx.x; i < width; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
@@ -467,23 +476,28 @@ int csts_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const f
   return csts_check_launch("layernorm_fwd");
 }
 
-int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
-                       const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
-                       int width, void* dx16, int dx16_dtype, const float* row_scale, int rows_per_scale, void* stream) {
+static int layernorm_bwd_launch(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                                const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
+                                int width, void* dx16, int dx16_dtype, const float* row_scale, int rows_per_scale, const LnSecond* second,
+                                void* stream) {
   CSTS_REQUIRE(width % 4 == 0 && width <= LN_MAX_WIDTH, "layernorm_bwd: width %d unsupported", width);
   if (dx16) CSTS_REQUIRE(dx16_dtype == CSTS_BF16 || dx16_dtype == CSTS_F16, "layernorm_bwd: dx16 must be bf16 or f16");
   if (dx16 && row_scale) CSTS_REQUIRE(rows_per_scale > 0, "layernorm_bwd: rows_per_scale must be positive");
   const int dx16_half = dx16_dtype == CSTS_F16;
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  LnSecond sec = {};
+  if (second) sec = *second;
+  const int ny = second ? 2 : 1;
   // persistent grid: enough warps to keep HBM busy, few enough blocks that the 2 * width closing atomics per block are noise
   const int blocks_per_sm = width <= 384 ? 2 : 1;          // what the register budget of the two variants allows
   const int lpr = width <= 96 ? 8 : (width <= 192 ? 16 : 32);
   const int64_t passes = (rows + 32 / lpr - 1) / (32 / lpr);
   const int64_t blocks = (passes + 8 * 4 - 1) / (8 * 4);                 // >= 4 passes per warp
   int grid = (int)(blocks < (int64_t)csts_num_sms() * blocks_per_sm ? (blocks > 0 ? blocks : 1) : (int64_t)csts_num_sms() * blocks_per_sm);
+  if (ny == 2 && grid > csts_num_sms() * blocks_per_sm / 2) grid = csts_num_sms() * blocks_per_sm / 2;
 #define LN_BWD_J(TX, TDY, TDX, LPR, J, U) \
-  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, LPR, J, U>, dim3(grid), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width, dx16, dx16_half, row_scale, rows_per_scale)
+  launch_pdl(layernorm_bwd_kernel<TX, TDY, TDX, LPR, J, U>, dim3(grid, ny), dim3(256), 0, st, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, add, (TDX*)dx, dgamma, dbeta, (int)rows, width, dx16, dx16_half, row_scale, rows_per_scale, sec)
 #define LN_BWD(TX, TDY, TDX)                                  \
   do {                                                        \
     if (width <= 96) LN_BWD_J(TX, TDY, TDX, 8, 3, 1);         \
@@ -503,6 +517,22 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
 #undef LN_BWD
 #undef LN_BWD_J
   return csts_check_launch("layernorm_bwd");
+}
+
+int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                       const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
+                       int width, void* dx16, int dx16_dtype, const float* row_scale, int rows_per_scale, void* stream) {
+  return layernorm_bwd_launch(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, add, dx, dx_dtype, dgamma, dbeta, rows, width, dx16, dx16_dtype,
+                              row_scale, rows_per_scale, nullptr, stream);
+}
+
+int csts_layernorm_bwd_pair(const void* dy0, const void* dy1, int dy_dtype, const void* x0, const void* x1, int x_dtype, const float* mean0,
+                            const float* mean1, const float* rstd0, const float* rstd1, const float* gamma0, const float* gamma1, void* dx0,
+                            void* dx1, int dx_dtype, float* dgamma0, float* dgamma1, float* dbeta0, float* dbeta1, int64_t rows, int width,
+                            void* stream) {
+  LnSecond sec = {dy1, x1, mean1, rstd1, gamma1, dx1, dgamma1, dbeta1};
+  return layernorm_bwd_launch(dy0, dy_dtype, x0, x_dtype, mean0, rstd0, gamma0, nullptr, dx0, dx_dtype, dgamma0, dbeta0, rows, width, nullptr, 0,
+                              nullptr, 0, &sec, stream);
 }
 
 int csts_rowdot(const void* dO, const void* O, int dtype, float* D, int B, int Lq, int heads, int d, void* stream) {

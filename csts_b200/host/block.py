@@ -228,9 +228,12 @@ class _Fork:
             self.hold.clear()
 
 
-def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
+def block_backward(spec, p, wc, sv, dy, d_audio_rows=None, hand=None):
     """dy: f32 (B, Lq, dim_out).  Returns (dx f32 (B,N,C), {param name: grad}).  d_audio_rows: gradient w.r.t.
-    audio_rows(P) (MVIT.SPATIAL_AUDIO_ATTN), folded into dP before the softmax backward."""
+    audio_rows(P) (MVIT.SPATIAL_AUDIO_ATTN), folded into dP before the softmax backward.
+    hand = {"dp": MLP-branch DropPath scale of the block that produced x, or None}: the closing LayerNorm backward then also
+    writes the 16-bit, DropPath-scaled copy of dx that the producer's backward starts from (its `g2`), handed over
+    through wc.handoff — one cast launch per block less."""
     x = sv["x"]
     B, N, C = x.shape
     h, d = spec.heads, spec.head_dim
@@ -263,7 +266,9 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
                             a_rows, b_rows)
 
     dy = dy.contiguous().view(Mq, Co)
-    g2 = K.cast16(dy, wc.grad, row_scale=dp_m, rows_per_scale=rps)            # gradient entering the (drop-path scaled) MLP branch
+    g2 = wc.take_handoff(dy) if hasattr(wc, "take_handoff") else None         # written by the consumer block's LayerNorm backward
+    if g2 is None:
+        g2 = K.cast16(dy, wc.grad, row_scale=dp_m, rows_per_scale=rps)        # gradient entering the (drop-path scaled) MLP branch
     # ---- fc2, GELU, fc1 ----------------------------------------------------------------------------
     wgrad(g2, sv["hdn"], "mlp.fc2.weight", Co, hid, Mq, "mlp.fc2.bias")
     dZ = K.gemm(g2, wc.w(p["mlp.fc2.weight"]), M=Mq, N=hid, K=Co, b_kmajor=False, act=2, Z=sv["Z"])
@@ -382,14 +387,27 @@ def block_backward(spec, p, wc, sv, dy, d_audio_rows=None):
         qname = "attn.upsample_q.weight" if dec else "attn.pool_q.weight"
         pool_backward([(pool_ln_backward(dq_t, "q_pool", "attn.norm_q"), 0, qname)], spec.stride_q, dec, thw_q)
     if pooled_kv:
-        pool_backward([(pool_ln_backward(dk_t, "k_pool", "attn.norm_k"), 1, "attn.pool_k.weight"),
-                       (pool_ln_backward(dv_t, "v_pool", "attn.norm_v"), 2, "attn.pool_v.weight")], spec.stride_kv, False, k.thw)
+        # norm_k and norm_v backward share their geometry: one launch
+        for nn_ in ("attn.norm_k", "attn.norm_v"):
+            g[nn_ + ".weight"], g[nn_ + ".bias"] = zeros(nn_ + ".weight", d), zeros(nn_ + ".bias", d)
+        (kp, km, kr), (vp, vm, vr) = sv["k_pool"], sv["v_pool"]
+        duk, duv = K.layernorm_bwd_pair((dk_t, dv_t), (kp, vp), (km, vm), (kr, vr), (p["attn.norm_k.weight"], p["attn.norm_v.weight"]),
+                                        (g["attn.norm_k.weight"], g["attn.norm_v.weight"]), (g["attn.norm_k.bias"], g["attn.norm_v.bias"]),
+                                        dx_dtype=wc.grad)
+        pool_backward([(duk, 1, "attn.pool_k.weight"), (duv, 2, "attn.pool_v.weight")], spec.stride_kv, False, k.thw)
     # ---- qkv projection and norm1 ---------------------------------------------------------------------------
     wgrad(dqkv, sv["xn1"].view(M, C), "attn.qkv.weight", 3 * C, C, M, "attn.qkv.bias")
     dxn1 = K.gemm(dqkv, wc.w(p["attn.qkv.weight"]), M=M, N=C, K=3 * C, b_kmajor=False)
     g["norm1.weight"], g["norm1.bias"] = zeros("norm1.weight", C), zeros("norm1.bias", C)
-    dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
-                         add=dx_skip.view(B, N, C))
+    if hand is not None and hasattr(wc, "give_handoff"):
+        hdp = hand.get("dp")
+        dx, dx16 = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
+                                   add=dx_skip.view(B, N, C), copy16=wc.grad, row_scale=None if hdp is None else hdp[1],
+                                   rows_per_scale=N if hdp is not None else 0)
+        wc.give_handoff(dx, dx16.view(M, C))
+    else:
+        dx = K.layernorm_bwd(dxn1, x, sv["mean1"], sv["rstd1"], p["norm1.weight"], g["norm1.weight"], g["norm1.bias"],
+                             add=dx_skip.view(B, N, C))
     if not getattr(wc, "defer_join", False):
         fork.join()         # by default every block hands complete gradients to autograd (DDP's reducer, plain optimizers)
     return dx, g
@@ -403,6 +421,7 @@ class BlockFn(torch.autograd.Function):
     def forward(ctx, meta, x, *params):
         spec, wc, thw, dp_scale, names = meta[:5]
         extra = meta[5] if len(meta) > 5 else None       # {"want": "attn" | "audio_rows"}: optional attention outputs
+        ctx.hand = meta[6] if len(meta) > 6 else None    # gradient hand-over to the producer block (block_backward)
         p = dict(zip(names, params))
         need = any(ctx.needs_input_grad)      # forward runs under no_grad: ask the node, not the mode
         y, thw_q, sv, attn = block_forward(spec, p, wc, x.contiguous(), thw, dp_scale, save=need, want_attn=extra is not None)
@@ -423,6 +442,6 @@ class BlockFn(torch.autograd.Function):
         p = dict(zip(names, ctx.params))
         if dy is None:
             dy = torch.zeros(ctx.sv["x"].shape[0], ctx.sv["Lq"], spec.dim_out, dtype=torch.float32, device=ctx.sv["x"].device)
-        dx, g = block_backward(spec, p, wc, ctx.sv, dy, d_audio_rows)
+        dx, g = block_backward(spec, p, wc, ctx.sv, dy, d_audio_rows, hand=ctx.hand)
         ctx.sv = None
         return (None, dx) + tuple(g[n].view_as(p[n]) for n in names)

@@ -304,6 +304,7 @@ class CSTS(nn.Module):
         self.apply(self._init_weights)
         self._wc = WeightCache(precision_of(cfg))
         self._dp_site, self._dp_keep, self._dp_scales = None, None, None
+        self._last_out = None
 
     @staticmethod
     def _init_weights(m):
@@ -328,8 +329,18 @@ class CSTS(nn.Module):
         dp_scale = None
         if self.training and spec.drop_path > 0.0:
             dp_scale = self._dp_scales[self._dp_site[id(blk)]]
-        meta = (spec, self._wc, tuple(thw), dp_scale, blk._names) + ((extra,) if extra is not None else ())
+        # x produced by another block (directly, or through a decoder skip add): that block's backward starts from a
+        # 16-bit copy of this block's dx, written by this block's closing LayerNorm backward (block.py "hand")
+        hand = None
+        last = self._last_out
+        if last is not None and last[0] is x and torch.is_grad_enabled() and self.training:
+            hand = {"dp": last[1]}
+        meta = (spec, self._wc, tuple(thw), dp_scale, blk._names, extra, hand)
         y = BlockFn.apply(meta, x, *blk.tensors())
+        if isinstance(y, tuple):
+            self._last_out = None
+        else:
+            self._last_out = (y, dp_scale)
         return y, spec.q_grid(thw)
 
     def _draw_drop_path(self, batch, device):
@@ -377,6 +388,8 @@ class CSTS(nn.Module):
         side = wc.audio_stream()
         main = torch.cuda.current_stream() if side is not None else None
 
+        self._last_out = None
+
         def audio_encoder():
             y = PatchEmbedFn.apply(wc, audio, self.patch_embed_audio.proj.weight, self.patch_embed_audio.proj.bias,
                                    self.pos_embed_spatial_audio, self.pos_embed_temporal_audio)
@@ -397,6 +410,7 @@ class CSTS(nn.Module):
             x, thw = self._run_block(blk, x, thw)
             if i in (0, 2, 13):
                 skips.append((x, thw))
+                self._last_out = None          # this output has a second consumer (a decoder skip): its gradient is a sum
         if side is not None:
             main.wait_stream(side)
             y.record_stream(main)          # allocated on the second stream, consumed (and saved for backward) on this one
@@ -432,7 +446,11 @@ class CSTS(nn.Module):
         for i in range(4):
             f, thw = self._run_block(getattr(self, f"decode_block{i + 1}"), f, thw)
             if i < 3:
+                prev = self._last_out
                 f = AddFn.apply(f, skips[3 - i][0])
+                if prev is not None:
+                    self._last_out = (f, prev[1])          # the add passes the gradient through unchanged
+        self._last_out = None
         stem, thw0 = skips[0]
         logits = HeadFn.apply(f, stem, self.classifier.weight, self.classifier.bias, thw0)
         if not return_embed and (return_spatial_attn or return_temporal_attn):           # :485-491, visualisation outputs

@@ -45,6 +45,7 @@ class WeightCache:
         self.arena = None        # GradArena, created by the model at its first training forward
         self._fork = None
         self._audio = None
+        self._handoff = {}
         self.defer_join = False
         self.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
         self.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
@@ -79,7 +80,20 @@ class WeightCache:
         if self._fork is not None:
             self._fork.join(waiter)
 
+    # ---- gradient hand-over between consecutive blocks (block.py::block_backward) ---------------------------------
+    def give_handoff(self, dx, dx16):
+        """dx: the f32 gradient a block returns for its input; dx16: its 16-bit DropPath-scaled copy.  Keeping dx in the entry
+        keeps its address unique until the producer block picks the pair up."""
+        self._handoff[dx.data_ptr()] = (dx, dx16)
+
+    def take_handoff(self, dy):
+        hit = self._handoff.pop(dy.data_ptr(), None)
+        if hit is None or hit[0].shape.numel() != dy.numel() or hit[1].shape != dy.shape:
+            return None
+        return hit[1]
+
     def begin_training_step(self):
+        self._handoff.clear()
         """Called at the top of every training forward.  A parameter's version counter is not a reliable
         "changed" signal (torch's *fused* optimizers update parameters without bumping it), so in training the
         copies are rebuilt once per step — unless the fused clip+AdamW step (host/optimizer.py) has just

@@ -131,6 +131,18 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, add=None, dx_dtype=to
     return dx if copy16 is None else (dx, dx16)
 
 
+def layernorm_bwd_pair(dy, x, mean, rstd, gamma, dgamma, dbeta, dx_dtype):
+    """Two LayerNorm backward problems of identical shape and types in one launch; every argument is a pair."""
+    width = x[0].shape[-1]
+    rows = x[0].numel() // width
+    assert x[1].shape == x[0].shape and dy[0].dtype == dy[1].dtype and x[0].dtype == x[1].dtype
+    dx = (torch.empty(x[0].shape, dtype=dx_dtype, device=x[0].device), torch.empty(x[1].shape, dtype=dx_dtype, device=x[1].device))
+    call("csts_layernorm_bwd_pair", ptr(dy[0]), ptr(dy[1]), dt(dy[0]), ptr(x[0]), ptr(x[1]), dt(x[0]), ptr(mean[0]), ptr(mean[1]),
+         ptr(rstd[0]), ptr(rstd[1]), ptr(gamma[0]), ptr(gamma[1]), ptr(dx[0]), ptr(dx[1]), dt(dx[0]), ptr(dgamma[0]), ptr(dgamma[1]),
+         ptr(dbeta[0]), ptr(dbeta[1]), rows, width)
+    return dx
+
+
 def softmax_fwd(S, n, ldp, nq, mask_hw=0, mask_t=0, dtype=torch.bfloat16):
     """S f32 (..., lds) -> P (bf16 / f16) (..., ldp) with zeroed pad columns."""
     lds = S.shape[-1]

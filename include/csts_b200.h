@@ -100,6 +100,12 @@ int csts_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype,
                        const float* gamma, const float* add, void* dx, int dx_dtype, float* dgamma, float* dbeta, int64_t rows,
                        int width, void* dx16, int dx16_dtype, const float* row_scale, int rows_per_scale, void* stream);
 
+/* two LayerNorm backward problems of identical geometry and types in one launch (norm_k / norm_v of a block, attention.py:135-138) */
+int csts_layernorm_bwd_pair(const void* dy0, const void* dy1, int dy_dtype, const void* x0, const void* x1, int x_dtype, const float* mean0,
+                            const float* mean1, const float* rstd0, const float* rstd1, const float* gamma0, const float* gamma1, void* dx0,
+                            void* dx1, int dx_dtype, float* dgamma0, float* dgamma1, float* dbeta0, float* dbeta1, int64_t rows, int width,
+                            void* stream);
+
 /* ---- attention softmax: attn.softmax(dim=-1) (attention.py:155), with the in-frame mask of
  * SpatialAttention (av_attention.py:336-348) when mask_hw > 0.  P is bf16 / f16 (p_dtype), pad columns
  * [n, ldp) zero; dS is bf16 / f16 (ds_dtype). */

@@ -386,7 +386,7 @@ def test_optional_paths_against_reference_golden(golden_dir, mode):
         got = model.get_parameter(n).grad / scale
         # (the audio-attention map is min-max rescaled over 64 near-uniform probabilities at random init — a division by
         #  ~1e-3 — so 16-bit rounding of P is amplified into these 1e-6-sized gradients: measured 0.06-0.18)
-        assert rel_err(got, g.to(dev)) <= 0.3 * tol, (n, rel_err(got, g.to(dev)))
+        assert rel_err(got, g.to(dev)) <= (0.3 if mode == "bf16" else 0.15), (n, rel_err(got, g.to(dev)))
     # without the flag the network computes something else (the fixture is not vacuous)
     cfg2 = make_cfg(mixed=mode == "fp16")
     plain = build_model(cfg2)
