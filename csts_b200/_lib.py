@@ -101,6 +101,7 @@ SIGNATURES = {
     "csts_sim_matrix_fwd": [_P, _P, _P, _P, _P, _I, _I, _F, _P],
     "csts_sim_matrix_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "csts_egonce": [_P, _P, _P, _P, _I, _F, _P],
+    "csts_adaptive_f1": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "csts_grad_sqnorm": [_P, _P, _I, _P, _P],
     "csts_clip_adamw_step": [_P, _P, _I, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _F, _F, _P],
 }

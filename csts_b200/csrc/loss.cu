@@ -163,9 +163,118 @@ __global__ void __launch_bounds__(256) egonce_kernel(const float* __restrict__ s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// adaptive_f1 (slowfast/utils/metrics.py:9-74) with the min-max rescale of the loops fused in
+// (tools/train_avgaze_net.py:125-127, test_avgaze_net.py:66-68): the reference materialises two
+// (thresholds, B, T, H, W) f32 tensors per call; here one block per frame counts, for every threshold at once,
+//   tp = #(pred > th  and  label > 0.001), fg_pred = #(pred > th), fg_label = #(label > 0.001)
+// and a single-block second kernel turns the counts of the tracked frames (labels[:, :, 2] == fixation_idx) into
+// recall / precision / f1 per threshold and picks the best threshold.  Nothing is read back by the kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int F1_MAX_THR = 32;
+
+__global__ void __launch_bounds__(256) f1_count_kernel(const float* __restrict__ preds, const float* __restrict__ labels_hm,
+                                                       const float* __restrict__ thr, int n_thr, int HW, int rescale,
+                                                       float* __restrict__ counts /* [frames][2*n_thr+1] */) {
+  pdl_wait();
+  __shared__ float red[33];
+  __shared__ int s_cnt[2 * F1_MAX_THR + 1];
+  for (int i = threadIdx.x; i < 2 * n_thr + 1; i += blockDim.x) s_cnt[i] = 0;
+  const int64_t base = (int64_t)blockIdx.x * HW;
+  float mn = INFINITY, mx = -INFINITY;
+  if (rescale) {
+    for (int c = threadIdx.x; c < HW; c += blockDim.x) {
+      float v = preds[base + c];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    mn = -block_max(-mn, red);
+  }
+  __syncthreads();
+  const float den = mx - mn + 1e-6f;
+  int tp[F1_MAX_THR], fp[F1_MAX_THR], fl = 0;
+#pragma unroll
+  for (int i = 0; i < F1_MAX_THR; ++i) { tp[i] = 0; fp[i] = 0; }
+  for (int c = threadIdx.x; c < HW; c += blockDim.x) {
+    float v = preds[base + c];
+    if (rescale) v = (v - mn) / den;
+    const int lab = labels_hm[base + c] > 0.001f;
+    fl += lab;
+#pragma unroll
+    for (int i = 0; i < F1_MAX_THR; ++i) {
+      if (i < n_thr) {
+        const int on = v > thr[i];
+        fp[i] += on;
+        tp[i] += on & lab;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < F1_MAX_THR; ++i) {
+    if (i < n_thr) {
+      int a = tp[i], b = fp[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[2 * i], a); atomicAdd(&s_cnt[2 * i + 1], b); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fl += __shfl_xor_sync(0xffffffffu, fl, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt[2 * n_thr], fl);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * n_thr + 1; i += blockDim.x) counts[(int64_t)blockIdx.x * (2 * n_thr + 1) + i] = (float)s_cnt[i];
+}
+
+// out[0..4] = f1, recall, precision, threshold, index of the best threshold (first maximum, as torch.argmax)
+__global__ void __launch_bounds__(256) f1_select_kernel(const float* __restrict__ counts, const float* __restrict__ labels,
+                                                        const float* __restrict__ thr, int n_thr, int frames, int fixation_idx,
+                                                        float* __restrict__ out) {
+  pdl_wait();
+  __shared__ float red[33];
+  __shared__ float s_f1[F1_MAX_THR], s_rc[F1_MAX_THR], s_pr[F1_MAX_THR];
+  const int stride = 2 * n_thr + 1;
+  float ntr = 0.f;
+  for (int f = threadIdx.x; f < frames; f += blockDim.x) ntr += (labels[3 * f + 2] == (float)fixation_idx) ? 1.f : 0.f;
+  ntr = block_sum(ntr, red);
+  for (int i = 0; i < n_thr; ++i) {
+    float rc = 0.f, pr = 0.f;
+    for (int f = threadIdx.x; f < frames; f += blockDim.x) {
+      if (labels[3 * f + 2] == (float)fixation_idx) {
+        const float tp = counts[(int64_t)f * stride + 2 * i], fgp = counts[(int64_t)f * stride + 2 * i + 1], fgl = counts[(int64_t)f * stride + 2 * n_thr];
+        rc += tp / (fgl + 1e-6f);
+        pr += tp / (fgp + 1e-6f);
+      }
+    }
+    rc = block_sum(rc, red) / ntr;
+    pr = block_sum(pr, red) / ntr;
+    if (threadIdx.x == 0) { s_rc[i] = rc; s_pr[i] = pr; s_f1[i] = (2.f * rc * pr) / (rc + pr + 1e-6f); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = 0;
+    for (int i = 1; i < n_thr; ++i)
+      if (s_f1[i] > s_f1[best]) best = i;
+    out[0] = s_f1[best]; out[1] = s_rc[best]; out[2] = s_pr[best]; out[3] = thr[best]; out[4] = (float)best;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// counts: scratch f32 [frames * (2 * n_thr + 1)]; out: f32 [5] (f1, recall, precision, threshold, threshold index)
+int csts_adaptive_f1(const float* preds, const float* labels_hm, const float* labels, const float* thresholds, int n_thr, int frames, int HW,
+                     int fixation_idx, int rescale, float* counts, float* out, void* stream) {
+  CSTS_REQUIRE(n_thr >= 1 && n_thr <= F1_MAX_THR, "adaptive_f1: 1..%d thresholds", F1_MAX_THR);
+  CSTS_REQUIRE(frames > 0 && HW > 0, "adaptive_f1: empty input");
+  launch_pdl(f1_count_kernel, dim3(frames), dim3(256), 0, (cudaStream_t)stream, preds, labels_hm, thresholds, n_thr, HW, rescale, counts);
+  int rc = csts_check_launch("adaptive_f1 (count)");
+  if (rc) return rc;
+  launch_pdl(f1_select_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (const float*)counts, labels, thresholds, n_thr, frames, fixation_idx, out);
+  return csts_check_launch("adaptive_f1 (select)");
+}
+
 
 // logits/target/prob/dlogits: [frames, HW] f32; frame_kl: [frames] scratch; loss: [1]
 // loss = (1 / (T * log(HW) * B)) * sum_frames kl ; frames = B*T.  dlogits already carries that factor.

@@ -424,9 +424,14 @@ class BlockFn(torch.autograd.Function):
         ctx.hand = meta[6] if len(meta) > 6 else None    # gradient hand-over to the producer block (block_backward)
         p = dict(zip(names, params))
         need = any(ctx.needs_input_grad)      # forward runs under no_grad: ask the node, not the mode
-        y, thw_q, sv, attn = block_forward(spec, p, wc, x.contiguous(), thw, dp_scale, save=need, want_attn=extra is not None)
+        # MODEL.ACT_CHECKPOINT (custom_multimodal_builder.py:154-155,178-179,214-215: fairscale checkpoint_wrapper around the
+        # video and audio encoder blocks): keep only the block input, re-run the forward inside backward
+        ckpt = need and getattr(wc, "act_checkpoint", False) and spec.kind == "enc" and extra is None
+        x = x.contiguous()
+        y, thw_q, sv, attn = block_forward(spec, p, wc, x, thw, dp_scale, save=need and not ckpt, want_attn=extra is not None)
         ctx.meta = meta
         ctx.sv = sv
+        ctx.recompute = (x, tuple(thw), dp_scale) if ckpt else None
         ctx.params = params
         ctx.thw_q = thw_q
         if extra is not None and extra.get("want") == "audio_rows":
@@ -442,6 +447,10 @@ class BlockFn(torch.autograd.Function):
         p = dict(zip(names, ctx.params))
         if dy is None:
             dy = torch.zeros(ctx.sv["x"].shape[0], ctx.sv["Lq"], spec.dim_out, dtype=torch.float32, device=ctx.sv["x"].device)
+        if ctx.recompute is not None:
+            x, thw_in, dp = ctx.recompute
+            _, _, ctx.sv, _ = block_forward(spec, p, wc, x, thw_in, dp, save=True)
+            ctx.recompute = None
         dx, g = block_backward(spec, p, wc, ctx.sv, dy, d_audio_rows, hand=ctx.hand)
         ctx.sv = None
         return (None, dx) + tuple(g[n].view_as(p[n]) for n in names)

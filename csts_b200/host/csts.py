@@ -260,7 +260,7 @@ class CSTS(nn.Module):
         mv = cfg.MVIT
         assert not mv.CLS_EMBED_ON and mv.SEP_POS_EMBED and not mv.PATCH_2D and not mv.NORM_STEM, \
             "csts_b200 implements the configuration of configs/{Ego4D,Aria}/CSTS_*.yaml"
-        assert mv.DROPOUT_RATE == 0.0 and not cfg.MODEL.ACT_CHECKPOINT
+        assert mv.DROPOUT_RATE == 0.0
         assert mv.NORM == "layernorm"
         assert list(mv.PATCH_KERNEL) == [3, 7, 7] and list(mv.PATCH_STRIDE) == [2, 4, 4] and list(mv.PATCH_PADDING) == [1, 3, 3], \
             "the patch-embed kernel is specialised for k(3,7,7) s(2,4,4) p(1,3,3)"
@@ -303,6 +303,7 @@ class CSTS(nn.Module):
         trunc_normal_(self.pos_embed_temporal_audio, std=0.02)
         self.apply(self._init_weights)
         self._wc = WeightCache(precision_of(cfg))
+        self._wc.act_checkpoint = bool(cfg.MODEL.ACT_CHECKPOINT)       # encoder blocks recompute their forward in backward
         self._dp_site, self._dp_keep, self._dp_scales = None, None, None
         self._last_out = None
 

@@ -46,6 +46,7 @@ class WeightCache:
         self._fork = None
         self._audio = None
         self._handoff = {}
+        self.act_checkpoint = False     # MODEL.ACT_CHECKPOINT: encoder blocks keep their input only and recompute in backward
         self.defer_join = False
         self.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
         self.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"

@@ -243,6 +243,13 @@ int csts_clip_adamw_step(const csts_mt_tensor* tensors, const int32_t* chunks, i
                          float* found_inf, const float* step, const float* lr0, const float* lr1, double beta1, double beta2, float eps,
                          float max_norm, void* stream);
 
+/* ---- metric: adaptive-threshold F1 (slowfast/utils/metrics.py:9-74), with the per-frame min-max rescale of the loops
+ * (tools/train_avgaze_net.py:125-127) fused in when rescale != 0.  preds / labels_hm: f32 [frames][HW]; labels: f32
+ * [frames][3] (x, y, gaze type); thresholds: f32 [n_thr <= 32], ascending.  counts: scratch f32 [frames * (2*n_thr + 1)];
+ * out: f32 [5] = f1, recall, precision, best threshold, its index.  No host synchronisation. */
+int csts_adaptive_f1(const float* preds, const float* labels_hm, const float* labels, const float* thresholds, int n_thr, int frames, int HW,
+                     int fixation_idx, int rescale, float* counts, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -484,6 +484,45 @@ def loss_and_grads(sd, video, audio, labels_hm, alpha=0.05, loss_scale=1.0, drop
 
 
 # --------------------------------------------------------------------------------------------
+# Metric.  ref: slowfast/utils/metrics.py:9-74 and the rescale of tools/train_avgaze_net.py:125-127
+# --------------------------------------------------------------------------------------------
+
+def minmax_rescale(preds):
+    """ref: tools/train_avgaze_net.py:125-127 — per-frame (p - min) / (max - min + 1e-6)."""
+    flat = preds.detach().view(preds.size()[:-2] + (preds.size(-1) * preds.size(-2),))
+    mn, mx = flat.min(dim=-1, keepdim=True)[0], flat.max(dim=-1, keepdim=True)[0]
+    return ((flat - mn) / (mx - mn + 1e-6)).view(preds.size())
+
+
+def adaptive_f1(preds, labels_hm, labels, dataset):
+    """ref: slowfast/utils/metrics.py:30-74 (the PyTorch branch), computed per threshold instead of through the two
+    (thresholds, B, T, H, W) temporaries.  Returns (f1, recall, precision, threshold)."""
+    import numpy as np
+    if "forecast" in dataset and "aria" not in dataset:
+        thresholds = np.linspace(0.01, 0.07, 31)
+    elif "forecast" in dataset and "aria" in dataset:
+        thresholds = np.linspace(0.0, 0.02, 21)
+    else:
+        thresholds = np.linspace(0, 0.02, 11)
+    fixation_idx = 1 if dataset == "egteagaze" else 0
+    binary_labels = (labels_hm > 0.001).float()
+    tracked = torch.where(labels.reshape(-1, labels.shape[-1])[:, 2] == fixation_idx)[0]
+    f1s, rcs, prs = [], [], []
+    for th in thresholds:
+        bp = (preds.squeeze(1) > th).float()
+        tp = (bp * binary_labels).sum(dim=(2, 3)).reshape(-1).index_select(0, tracked)
+        fgl = binary_labels.sum(dim=(2, 3)).reshape(-1).index_select(0, tracked)
+        fgp = bp.sum(dim=(2, 3)).reshape(-1).index_select(0, tracked)
+        rc, pr = (tp / (fgl + 1e-6)).mean(), (tp / (fgp + 1e-6)).mean()
+        rcs.append(rc)
+        prs.append(pr)
+        f1s.append((2 * rc * pr) / (rc + pr + 1e-6))
+    f1 = torch.stack(f1s)
+    i = int(torch.argmax(f1))
+    return float(f1[i]), float(rcs[i]), float(prs[i]), thresholds[i]
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic weights and inputs (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------------
 

@@ -433,3 +433,40 @@ def test_prefetched_inputs_reach_the_graphed_step(golden_dir):
     # (the forward pass holds one split-K product with f32 atomics — the frame pools — whose summation order can flip a
     #  16-bit rounding downstream: two evaluations of one batch agree to ~1e-5, the two batches differ by 1e-3)
     assert all(abs(g - w) <= 1e-4 * abs(w) for g, w in zip(got, [want[0], want[1], want[0]])), (got, want)
+
+
+def test_activation_checkpointing_recomputes_encoder_blocks(golden_dir):
+    """MODEL.ACT_CHECKPOINT (custom_multimodal_builder.py:154-155,178-179,214-215 wrap the 16 + 4 encoder blocks in fairscale's
+    checkpoint_wrapper): same loss and gradients as the stored-activation path, with less memory alive between forward
+    and backward."""
+    import csts_oracle as O
+    from csts_b200.host.build import build_model
+    from csts_b200.host.train_step import compute_loss
+    shapes = json.load(open(os.path.join(golden_dir, "param_shapes.json")))
+    sd = O.synthetic_state(shapes, seed=5, gain=1.0)
+    video, audio, hm = (t.to(dev) for t in O.synthetic_batch(2, seed=6))
+
+    def run(ckpt):
+        cfg = make_cfg()
+        cfg.MODEL.ACT_CHECKPOINT = ckpt
+        m = build_model(cfg)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        loss, _, _, _ = compute_loss(cfg, m, [video], audio, hm)
+        held = torch.cuda.memory_allocated() - base          # activations alive after the forward pass
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.item(), {n: p.grad.clone() for n, p in m.named_parameters()}, held
+
+    l0, g0, held0 = run(False)
+    l1, g1, held1 = run(True)
+    assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+    worst = max(rel_err(g1[n], g0[n]) for n in g0 if g0[n].norm() > 1e-5)      # (a few biases have analytically zero gradients: noise)
+    assert worst < 2e-2, worst          # same arithmetic; 16-bit rounding flips downstream of the frame pools' f32 atomics only
+    num = sum((g1[n] - g0[n]).pow(2).sum().item() for n in g0)
+    den = sum(g.pow(2).sum().item() for g in g0.values())
+    assert (num / den) ** 0.5 < 2e-3
+    assert held1 < 0.6 * held0, (held0, held1)

@@ -153,3 +153,25 @@ def test_oracle_drop_path_against_live_reference_block():
     torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=1e-5)
     y0, _ = O.block(sd, "b", x, (4, 8, 8), spec=("enc", 96, 192, 1, None, (1, 2, 2)))
     assert (y0 - y_ref).abs().max() > 1e-2
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("dataset", ["ego4d_av_gaze_forecast", "aria_av_gaze_forecast", "ego4d_av_gaze"])
+def test_oracle_adaptive_f1_against_live_reference(dataset):
+    """oracle adaptive_f1 / minmax_rescale vs slowfast/utils/metrics.py:9-74 and tools/train_avgaze_net.py:125-127."""
+    ref_shim.install()
+    from slowfast.utils import metrics as rmetrics
+    g = torch.Generator().manual_seed(2)
+    _, _, hm = O.synthetic_batch(3, seed=5)
+    logits = torch.randn(3, 1, 8, 64, 64, generator=g) + 6.0 * hm.unsqueeze(1) / hm.amax(dim=(-1, -2), keepdim=True).unsqueeze(1)
+    preds = O.minmax_rescale(O.frame_softmax(logits, 2.0))
+    if "forecast" in dataset:
+        preds = preds * 0.08                                # put the maps inside the dataset's threshold grid
+    labels = torch.rand(3, 8, 3, generator=g)
+    labels[:, :, 2] = (torch.rand(3, 8, generator=g) > 0.3).float() * 0      # tracked frames: type 0 ...
+    labels[0, 1, 2] = 1.0                                                    # ... and two untracked ones
+    labels[2, 5, 2] = 2.0
+    want = rmetrics.adaptive_f1(preds, hm, labels, dataset)
+    got = O.adaptive_f1(preds, hm, labels, dataset)
+    assert all(abs(a - b) <= 1e-6 for a, b in zip(got, want)), (got, want)
+    assert 0.0 < want[0] < 1.0
