@@ -322,6 +322,40 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), launches, prof
 
+    def gemm_graph_ms(reps=3):
+        """Dominant-kernel time of one step, live: every tcgen05 GEMM launch of the step (its real argument block and
+        operands, recorded from one eager step) replayed once each, in step order, as one CUDA graph on one stream — the
+        kernels run back to back exactly as inside the step's graph, with no event pair between them — timed with CUDA
+        events around the replay.  Returns (ms per replay, FLOPs per replay, launches)."""
+        import ctypes as C
+        graphed.model._wc.fork_backward = False
+        graphed.model._wc.parallel_audio = False
+        K.GEMM_RECORD = []
+        train_step(cfg, graphed.model, opt, [video_d], audio_d, hm_d, grad_sync=graphed.grad_sync, scaler=scaler)
+        recs, K.GEMM_RECORD = [r for r in K.GEMM_RECORD if r[3]], None
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for r in recs:
+                _lib.call("csts_gemm", C.byref(r[0]))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for r in recs:
+                _lib.call("csts_gemm", C.byref(r[0]))
+        ms = []
+        for _ in range(reps + 1):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            g.replay()
+            e.record()
+            torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        return statistics.median(ms[1:]), sum(r[2] for r in recs), len(recs)
+
     for _ in range(args.warmup):
         resident_step()
     sampler = ClockSampler(local)
@@ -333,6 +367,7 @@ def run_gpu(args):
         launches = launches_per_step * args.steps
         # per-kernel CUDA-event timing needs un-captured launches: same kernels, eager, right after the timed region
         _, _, prof = timed(eager_profile_step, args.steps, profile=(rank == 0))
+    gg = gemm_graph_ms() if (graphed is not None and rank == 0) else None
     if graphed is not None:
         graphed.model._wc.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
         graphed.model._wc.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
@@ -356,12 +391,22 @@ def run_gpu(args):
     tc_ms, tc_flops = sum(t for t, _ in tc), sum(f for _, f in tc)
     all_ms = sum(r[0].elapsed_time(r[1]) for r in prof)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    evented = {"achieved": achieved, "frac": achieved / tf_peak, "kernel_ms_per_step": tc_ms / args.steps, "launches_per_step": len(tc) // max(1, args.steps),
+               "timing": "a CUDA-event pair around every launch of an eager replay of the step (adds ~2 us per launch and removes the "
+                         "programmatic-dependent-launch overlap of consecutive kernels)"}
+    if gg is not None:
+        g_ms, g_flops, g_n = gg
+        achieved, tc_ms_step, n_tc = g_flops / (g_ms * 1e-3) / 1e12, g_ms, g_n
+    else:
+        tc_ms_step, n_tc = tc_ms / args.steps, len(tc) // max(1, args.steps)
     out = {
         "metric": METRIC, "value": clips / (total_ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "precision": args.precision + (" storage, fp32 accumulate / master weights" if args.precision == "bf16" else
-                                                                        " storage + GradScaler (TRAIN.MIXED_PRECISION), fp32 accumulate / master weights"), "global_batch": B * world, "parallelism": f"dp{world}", "droppath": cfg.MVIT.DROPPATH_RATE,
+                                                                        " storage + GradScaler (the reference's TRAIN.MIXED_PRECISION contract), fp32 accumulate / master "
+                                                                        "weights; tensor-core rate identical to bf16; meets the 2e-2 gradient tolerance "
+                                                                        "(bf16 storage: 3e-2, stock bf16 autocast of the reference: 9e-2 — profiles/r02_parity_vs_autocast.json)"), "global_batch": B * world, "parallelism": f"dp{world}", "droppath": cfg.MVIT.DROPPATH_RATE,
                    "l2": "192 MiB buffer rewritten before every timed step (activations per step also exceed L2)",
                    "optimizer": ("clip_grad_norm_ 1.0 + AdamW + 16-bit weight refresh fused in two launches (csts_clip_adamw_step)"
                                  if args.fused_optimizer else "clip_grad_norm_ 1.0 + AdamW (torch fused)"), "cuda_graph": graphed is not None},
@@ -375,12 +420,30 @@ def run_gpu(args):
         "roofline": {"kernel": "gemm_tc_kernel (tcgen05 Linear GEMMs, all shapes of the step)", "bound": "tensor",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
                      "traffic_source": traffic_src,
-                     "peak_source": f"{peak_src} sustained bf16", "launches": len(tc), "kernel_ms_per_step": tc_ms / args.steps,
-                     "share_of_step": tc_ms / total_ms, "all_gemm_ms_per_step": all_ms / args.steps,
-                     "timing": "CUDA events around every launch" + (" (eager replay of the same step; the timed region itself is one CUDA-graph launch per step)" if graphed is not None else "")},
+                     "peak_source": f"{peak_src} sustained bf16", "launches": n_tc, "kernel_ms_per_step": tc_ms_step,
+                     "share_of_step": tc_ms_step / (total_ms / args.steps), "all_gemm_ms_per_step": all_ms / args.steps,
+                     "timing": ("all tcgen05 GEMM launches of one step (real argument blocks and operands) replayed once each, in step order, "
+                                "as one CUDA graph; CUDA events around the replay, L2 flushed before it; achieved = sum of 2MNK / that time")
+                     if gg is not None else "CUDA events around every launch",
+                     "per_launch_events": evented},
     }
     if dpc is not None:
         out["dp_check"] = dpc
+    if args.second_mode and world == 1 and graphed is not None:
+        other = "bf16" if args.precision == "fp16" else "fp16"
+        cfg2 = make_cfg(world, other)
+        torch.manual_seed(cfg2.RNG_SEED)
+        m2 = build_model(cfg2, ddp=False)
+        m2.train()
+        o2 = construct_optimizer(m2, cfg2, capturable=True, fused_clip=args.fused_optimizer)
+        sc2 = make_grad_scaler(cfg2)
+        g2 = GraphedTrainStep(cfg2, m2, o2, video_d, audio_d, hm_d, scaler=sc2)
+        for _ in range(3):
+            g2(None, None, None)
+        ms2, _, _ = timed(lambda: g2(None, None, None), args.steps)
+        out[other + "_mode"] = {"value": clips / (ms2 * 1e-3), "unit": "clips/s", "ms_per_step": ms2 / args.steps,
+                                "what": f"the same step in the {other} storage mode (same kernels; operand formats are runtime fields)"}
+        del g2, m2, o2
     if args.gpu_reference and world == 1:
         torch.cuda.empty_cache()
         out["gpu_reference"] = gpu_reference(dev)
@@ -405,8 +468,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="csts_b200", choices=["csts_b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
-                    help="16-bit storage mode: bf16 (headline, BASELINE.json) or fp16 = TRAIN.MIXED_PRECISION with GradScaler")
+    ap.add_argument("--precision", default="fp16", choices=["bf16", "fp16"],
+                    help="16-bit storage mode.  fp16 (default, headline) = the reference's TRAIN.MIXED_PRECISION contract (fp16 + GradScaler): "
+                         "the mode that meets BASELINE.json's 2e-2 gradient tolerance.  bf16: same kernels, same speed, 3e-2 from fp32 "
+                         "(stock PyTorch bf16 autocast of the reference: 9e-2); reported as a second line (`bf16_mode`) at N=1")
+    ap.add_argument("--no-second-mode", dest="second_mode", action="store_false", help="skip the other precision mode's measurement")
     ap.add_argument("--torch-optimizer", dest="fused_optimizer", action="store_false",
                     help="clip_grad_norm_ + torch's fused AdamW instead of the library's fused clip+AdamW step")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

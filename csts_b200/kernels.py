@@ -14,6 +14,7 @@ _FORCE_BACKEND = 0   # 0 auto, 1 mma.sync, 2 tcgen05 (tests flip this to cross-c
 
 
 GEMM_PROFILE = None   # when a list: every gemm() appends (start_event, end_event, flops, bytes, used_tcgen05)
+GEMM_RECORD = None    # when a list: every gemm() appends (argument block, tensors kept alive, flops, used_tcgen05) — bench.py replays them
 
 
 def set_gemm_backend(code: int):
@@ -94,6 +95,9 @@ def gemm(A, B, **kw):
     holds zeros (a slice of the gradient arena), so a split-K product may accumulate into it without its own memset.
     tile_n / ctas: tuning overrides of the tcgen05 launcher (0 = automatic).  Keywords: see build_gemm_args."""
     a, out = build_gemm_args(A, B, want_out=True, **kw)
+    if GEMM_RECORD is not None:
+        GEMM_RECORD.append((a, (A, B, out) + tuple(v for v in kw.values() if torch.is_tensor(v)), 2.0 * a.M * a.N * a.K * a.batch1 * a.batch2,
+                            _lib.load().csts_gemm_backend(C.byref(a)) == 2))
     if GEMM_PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nb = a.batch1 * a.batch2
