@@ -367,7 +367,7 @@ def run_gpu(args):
         launches = launches_per_step * args.steps
         # per-kernel CUDA-event timing needs un-captured launches: same kernels, eager, right after the timed region
         _, _, prof = timed(eager_profile_step, args.steps, profile=(rank == 0))
-    gg = gemm_graph_ms() if (graphed is not None and rank == 0) else None
+    gg = gemm_graph_ms() if graphed is not None else None          # every rank: the recorded step issues the step's collectives
     if graphed is not None:
         graphed.model._wc.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
         graphed.model._wc.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
