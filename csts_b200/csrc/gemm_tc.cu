@@ -1093,7 +1093,10 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   if (a.c_dtype == 0 && a.act != 0) return false;      // activations pair with 16-bit outputs only
   if (a.act != 0 && (a.accumulate || a.residual)) return false;
   if (a.c_dtype != 0 && a.residual) return false;
-  if (a.M < 64) return false;                          // skinny problems: the generic kernel with split-K
+  // skinny problems go to the generic kernel — unless they stream a large operand (the (1,8,8) frame pools: 32 rows against
+  // a 75 MB weight): those are bandwidth problems, and TMA + a deep ring move bytes faster than cp.async, whatever the tile's
+  // fill (rows beyond M are zero-filled by the tensor map and clipped by the TMA store)
+  if (a.M < 64 && (int64_t)a.N * a.K < (1 << 24)) return false;
   return true;
 }
 

@@ -145,7 +145,7 @@ class FramePoolFn(torch.autograd.Function):
         T = N // 64
         a = K.permute_021(tok.contiguous(), B * T, 64, Cn, wc.act)          # (B*T, hw, c) f32 -> (B*T, c, hw) 16-bit
         Kd = 64 * Cn
-        out = K.gemm(a.view(B * T, Kd), wc.w(weight), M=B * T, N=weight.shape[0], K=Kd, bias=bias, out_dtype=torch.float32, split_k=24)
+        out = K.gemm(a.view(B * T, Kd), wc.w(weight), M=B * T, N=weight.shape[0], K=Kd, bias=bias, out_dtype=torch.float32, split_k=-1)
         ctx.save_for_backward(a)
         ctx.wc, ctx.weight, ctx.dims = wc, weight, (B, N, Cn)
         return out.view(B, T, weight.shape[0])

@@ -447,7 +447,7 @@ def test_activation_checkpointing_recomputes_encoder_blocks(golden_dir):
     video, audio, hm = (t.to(dev) for t in O.synthetic_batch(2, seed=6))
 
     def run(ckpt):
-        cfg = make_cfg()
+        cfg = make_cfg(mixed=True)
         cfg.MODEL.ACT_CHECKPOINT = ckpt
         m = build_model(cfg)
         m.load_state_dict(sd, strict=True)
@@ -457,20 +457,21 @@ def test_activation_checkpointing_recomputes_encoder_blocks(golden_dir):
         base = torch.cuda.memory_allocated()
         loss, _, _, _ = compute_loss(cfg, m, [video], audio, hm)
         held = torch.cuda.memory_allocated() - base          # activations alive after the forward pass
-        loss.backward()
+        (loss * LOSS_SCALE).backward()
         torch.cuda.synchronize()
-        return loss.item(), {n: p.grad.clone() for n, p in m.named_parameters()}, held
+        return loss.item(), {n: p.grad.clone() / LOSS_SCALE for n, p in m.named_parameters()}, held
 
     l0, g0, held0 = run(False)
     l1, g1, held1 = run(True)
     assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
     worst = max(rel_err(g1[n], g0[n]) for n in g0 if g0[n].norm() > 1e-5)      # (a few biases have analytically zero gradients: noise)
-    # same arithmetic in both runs; what differs is what differs between ANY two runs: the f32 atomics order of the frame
-    # pools' split-K forward flips 16-bit roundings downstream, which shows in the smallest tensors
-    assert worst < 0.15, worst
+    # same arithmetic in both runs; what differs is what differs between ANY two runs of one computation: the f32 summation
+    # order of the split-K products flips 16-bit roundings downstream (tools/grad_noise.py: ~3e-3 of the whole gradient in fp16
+    # storage, ~1e-2 in bf16), which shows most in the smallest tensors
+    assert worst < 0.3, worst
     num = sum((g1[n] - g0[n]).pow(2).sum().item() for n in g0)
     den = sum(g.pow(2).sum().item() for g in g0.values())
-    assert (num / den) ** 0.5 < 2e-3
+    assert (num / den) ** 0.5 < 1e-2, (num / den) ** 0.5
     assert held1 < 0.6 * held0, (held0, held1)
 
 
