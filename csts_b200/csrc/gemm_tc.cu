@@ -88,6 +88,7 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -342,15 +343,24 @@ __device__ __forceinline__ void slice_prefetch(const TcParams& p, int64_t coff, 
 template <int EPI>
 __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, uint32_t stage, int m0, int n0, int cols_in_tile,
                                                int lane, uint32_t taddr, float rs, float rv, bool first_split, const uint4 (&pre)[8],
-                                               const CUtensorMap* tmc, const CUtensorMap* tmz, int z2, int z1) {
+                                               const CUtensorMap* tmc, const CUtensorMap* tmz, int z2, int z1, int& parity) {
   constexpr bool F32 = EPI == EPI_F32 || EPI == EPI_F32_ATOMIC;
   constexpr int ESZ = F32 ? 4 : 2;
   const int rows_valid = min(32, p.M - m0);
   const int cols_valid = min(min(32, cols_in_tile), p.N - n0);
   unsigned char* cg = reinterpret_cast<unsigned char*>(p.C) + (coff + (int64_t)m0 * p.ldc + n0) * ESZ;
-  // the bulk store of the previous slice must have read the staging tile before it is written again
-  if (lane == 0) bulk_wait_read0();
+  // A 16-bit output tile is 2 KB, half of the warp's staging: plain 16-bit epilogues (no second output, no side tile)
+  // alternate between the halves, so only the store issued TWO slices ago has to have read its tile; the others wait for
+  // the previous slice's store before the staging is written again.
+  constexpr bool ALT = EPI == EPI_BF16 || EPI == EPI_EXPSUB;
+  const bool alt = ALT && !(EPI == EPI_BF16 && p.accumulate);
+  if (lane == 0) {
+    if (alt) bulk_wait_read1();
+    else bulk_wait_read0();
+  }
   __syncwarp();
+  const uint32_t out_tile = stage + ((alt && (parity & 1)) ? 2048u : 0u);
+  parity ^= 1;
   // global reads first: their latency overlaps the TMEM load
   float4 bv[8];
   const bool use_bias = p.bias != nullptr && first_split;
@@ -443,14 +453,14 @@ __device__ __forceinline__ void epilogue_slice(const TcParams& p, int64_t coff, 
       sts128(stage_addr(stage, lane, j), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
   } else {
-    stage_out16(stage, lane, v, p.c_half);
+    stage_out16(out_tile, lane, v, p.c_half);
   }
   fence_async_smem();                            // generic-proxy writes -> visible to the copy engine
   __syncwarp();
   if (lane == 0) {
     if (EPI == EPI_BF16_GELU && p.Z) tma_store_4d(tmz, stage + 2048, n0, m0, 0, 0);
     if (EPI == EPI_F32_ATOMIC) tma_reduce_add_4d(tmc, stage, n0, m0, z2, z1);
-    else tma_store_4d(tmc, stage, n0, m0, z2, z1);
+    else tma_store_4d(tmc, F32 ? stage : out_tile, n0, m0, z2, z1);
     bulk_commit();
   }
 }
@@ -742,6 +752,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     } else {
     int as = 0; uint32_t aphase = 0;
+    int out_parity = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tm, tn, z, kb0, kb1;
       const int split = decode(item, tm, tn, z, kb0, kb1);
@@ -777,7 +788,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int cn = c + CSTEP, n1 = tn * BN + cn;
         if (side && cn < BN && n1 < p.N) slice_prefetch<EPI_S>(p, coff, m0, n1, BN - cn, lane, split == 0, pre);
         epilogue_slice<EPI_S>(p, coff, stage_buf, m0, n0, BN - c, lane, trow + c, rs, rv, split == 0, cur, &tmap_c, &tmap_z, z % p.batch2,
-                              z / p.batch2);
+                              z / p.batch2, out_parity);
       }
       if (rowsum_on && tn == 0 && sub == 0 && live) {      // lane = output row: its sum over this item's k-range
         uint32_t r[32];
