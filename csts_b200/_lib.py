@@ -167,6 +167,20 @@ _device_checked = False
 PROFILE = None        # when a list: every call() appends (name, start_event, end_event) — tools/step_profile.py
 
 
+def _describe(args):
+    """Shape signature of a call for tools/step_profile.py: the plain integer arguments, or the geometry fields of an argument block."""
+    out = [a for a in args if isinstance(a, int) and not isinstance(a, bool)]
+    for a in args:
+        s = getattr(a, "_obj", None)
+        if isinstance(s, PoolArgs):
+            out += [s.B, s.heads, s.d, s.Ti, s.Hi, s.Wi, s.To, s.Ho, s.Wo, s.transposed, int(bool(s.gamma)), int(bool(s.in2))]
+        elif isinstance(s, WgradArgs):
+            out += [s.B, s.heads, s.d, s.Ts, s.Hs, s.Ws, s.Tb, s.Hb, s.Wb, int(bool(s.small2))]
+        elif isinstance(s, GemmArgs):
+            out += [s.M, s.N, s.K, s.batch1 * s.batch2, s.a_kmajor, s.b_kmajor, s.act, s.c_dtype, int(bool(s.residual)), s.split_k]
+    return str(tuple(out))
+
+
 def call(name, *args):
     """Invoke `name(*args, stream)` on the current CUDA stream and raise on a non-zero code."""
     global _device_checked
@@ -181,6 +195,6 @@ def call(name, *args):
         e0.record()
         check(getattr(lib, name)(*args, stream_ptr()), name)
         e1.record()
-        PROFILE.append((name + str(tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool))), e0, e1))
+        PROFILE.append((name + _describe(args), e0, e1))
         return
     check(getattr(lib, name)(*args, stream_ptr()), name)
