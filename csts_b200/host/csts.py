@@ -386,6 +386,7 @@ class CSTS(nn.Module):
         # of its forward, so the same overlap holds in backward; inside a captured step the two become graph branches.
         thw = tuple(self.patch_dims)
         thw_a = thw
+        wc.note_main_stream()
         side = wc.audio_stream()
         main = torch.cuda.current_stream() if side is not None else None
 

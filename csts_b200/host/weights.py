@@ -45,6 +45,7 @@ class WeightCache:
         self.arena = None        # GradArena, created by the model at its first training forward
         self._fork = None
         self._audio = None
+        self._main = None
         self._handoff = {}
         self.act_checkpoint = False     # MODEL.ACT_CHECKPOINT: encoder blocks keep their input only and recompute in backward
         self.defer_join = False
@@ -70,9 +71,15 @@ class WeightCache:
             self._audio = torch.cuda.Stream()
         return self._audio
 
+    def note_main_stream(self):
+        """Called at the top of the forward pass: the stream the video encoder, fusion and decoder (and their backward) run on."""
+        self._main = torch.cuda.current_stream()
+
     def branch_streams(self):
-        """Streams other than the caller's on which gradients of this model may still be in flight."""
-        out = [s for s in (self._audio,) if s is not None]
+        """Every stream on which gradients of this model may still be in flight: the forward's own stream, the audio
+        encoder's and the weight-gradient branch's.  A gradient bucket mixes tensors produced on all three, and the hook
+        that completes it runs on only one of them."""
+        out = [s for s in (self._main, self._audio) if s is not None]
         if self._fork is not None and self._fork.side is not None:
             out.append(self._fork.side)
         return out
