@@ -120,6 +120,8 @@ class OverlappedGradSync:
 
     def __init__(self, model, bucket_bytes=32 << 20):
         self.model = model
+        if hasattr(model, "_wc"):
+            model._wc.sync_aware = True           # this exchange waits for the model's audio and weight-gradient streams
         self.bucket_bytes = bucket_bytes
         self.params = [p for p in model.parameters() if p.requires_grad][::-1]
         self.arena = None

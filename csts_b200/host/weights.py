@@ -46,6 +46,7 @@ class WeightCache:
         self._fork = None
         self._audio = None
         self._main = None
+        self.sync_aware = False         # set by OverlappedGradSync: the gradient exchange waits for every stream of the model
         self._handoff = {}
         self.act_checkpoint = False     # MODEL.ACT_CHECKPOINT: encoder blocks keep their input only and recompute in backward
         self.defer_join = False
@@ -66,6 +67,12 @@ class WeightCache:
     def audio_stream(self):
         """Second stream of the forward pass (the audio encoder, csts.py), or None when disabled (CSTS_PARALLEL_AUDIO=0)."""
         if not self.parallel_audio:
+            return None
+        # Under data parallelism a gradient reducer must know about the second stream (OverlappedGradSync does and says so);
+        # DistributedDataParallel's reducer orders its buckets after the hook's stream only, so under DDP everything stays
+        # on one stream.
+        if not self.sync_aware and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
             return None
         if self._audio is None or self._audio.device.index != torch.cuda.current_device():
             self._audio = torch.cuda.Stream()
