@@ -736,6 +736,135 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The factors that occur on the path are (1,2,2) (decoder blocks 1-3) and (2,1,1) (decoder block 4).  For a factor of two
+// the half-pixel (align_corners=False) weights are constants: along an axis of n inputs
+//   y[2i]   = 0.25 x[i-1] + 0.75 x[i]   (y[0]    = x[0]),      y[2i+1] = 0.75 x[i] + 0.25 x[i+1]   (y[2n-1] = x[n-1]).
+// Forward: a thread owns one INPUT cell (4 channels), loads its <= 3x3 (or 3) neighbourhood once and writes the 2x2 (or 2)
+// outputs it centres.  Adjoint: a thread owns one input cell and gathers its 4 taps per doubled axis,
+//   dx[i] = 0.25 dy[2i-1] + w0 dy[2i] + w1 dy[2i+1] + 0.25 dy[2i+2],  w0 = (i == 0 ? 1 : 0.75),  w1 = (i == n-1 ? 1 : 0.75).
+// No divisions, no coefficient evaluation: the generic kernels above spend most of their time there.
+// ------------------------------------------------------------------------------------------------
+template <bool UP_T>       // false: (1,2,2)   true: (2,1,1)
+__global__ void __launch_bounds__(256) upsample2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int H, int W,
+                                                            int C) {
+  pdl_wait();
+  const int C4 = C / 4;
+  const uint32_t total = (uint32_t)B * T * H * W * C4;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C4) * 4;
+    const int wi = (int)divmod(q, W), hi = (int)divmod(q, H), ti = (int)divmod(q, T);
+    const int64_t b = q;
+    if (UP_T) {
+      const int64_t plane = (int64_t)H * W * C;
+      const float* px = x + ((b * T + ti) * H + hi) * (int64_t)W * C + (int64_t)wi * C + c;
+      float m[4], lo[4], hi4[4];
+      ld4(px, m);
+      ld4(ti > 0 ? px - plane : px, lo);
+      ld4(ti < T - 1 ? px + plane : px, hi4);
+      float o0[4], o1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o0[k] = ti > 0 ? 0.25f * lo[k] + 0.75f * m[k] : m[k];
+        o1[k] = ti < T - 1 ? 0.75f * m[k] + 0.25f * hi4[k] : m[k];
+      }
+      float* py = y + ((b * 2 * T + 2 * ti) * H + hi) * (int64_t)W * C + (int64_t)wi * C + c;
+      st4(py, o0);
+      st4(py + plane, o1);
+    } else {
+      const int64_t row = (int64_t)W * C;
+      const float* pc = x + ((b * T + ti) * H + hi) * row + (int64_t)wi * C + c;
+      const int dh0 = hi > 0 ? -1 : 0, dh1 = hi < H - 1 ? 1 : 0, dw0 = wi > 0 ? -1 : 0, dw1 = wi < W - 1 ? 1 : 0;
+      float v[3][3][4];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) ld4(pc + (a == 0 ? dh0 : (a == 2 ? dh1 : 0)) * row + (bb == 0 ? dw0 : (bb == 2 ? dw1 : 0)) * C, v[a][bb]);
+      // separable: rows first (two output rows), then columns (two output columns)
+      const float ha0 = hi > 0 ? 0.25f : 0.f, ha1 = hi > 0 ? 0.75f : 1.f;          // output row 2hi   = ha0 * up + ha1 * mid
+      const float hb1 = hi < H - 1 ? 0.75f : 1.f, hb2 = hi < H - 1 ? 0.25f : 0.f;  // output row 2hi+1 = hb1 * mid + hb2 * down
+      const float wa0 = wi > 0 ? 0.25f : 0.f, wa1 = wi > 0 ? 0.75f : 1.f;
+      const float wb1 = wi < W - 1 ? 0.75f : 1.f, wb2 = wi < W - 1 ? 0.25f : 0.f;
+      float* py = y + ((b * T + ti) * 2 * H + 2 * hi) * (2 * row) + (int64_t)(2 * wi) * C + c;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float rowv[3][4];
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            rowv[bb][k] = r == 0 ? ha0 * v[0][bb][k] + ha1 * v[1][bb][k] : hb1 * v[1][bb][k] + hb2 * v[2][bb][k];
+        float o0[4], o1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          o0[k] = wa0 * rowv[0][k] + wa1 * rowv[1][k];
+          o1[k] = wb1 * rowv[1][k] + wb2 * rowv[2][k];
+        }
+        st4(py + r * (2 * row), o0);
+        st4(py + r * (2 * row) + C, o1);
+      }
+    }
+  }
+}
+
+template <bool UP_T>
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int T, int H, int W,
+                                                            int C, int accumulate) {
+  pdl_wait();
+  const int C4 = C / 4;
+  const uint32_t total = (uint32_t)B * T * H * W * C4;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = i;
+    const int c = (int)divmod(q, C4) * 4;
+    const int64_t pos = q;
+    const int wi = (int)divmod(q, W), hi = (int)divmod(q, H), ti = (int)divmod(q, T);
+    const int64_t b = q;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (UP_T) {
+      const int64_t plane = (int64_t)H * W * C;
+      const float* p0 = dy + ((b * 2 * T + 2 * ti) * H + hi) * (int64_t)W * C + (int64_t)wi * C + c;   // output plane 2ti
+      const float w[4] = {ti > 0 ? 0.25f : 0.f, ti > 0 ? 0.75f : 1.f, ti < T - 1 ? 0.75f : 1.f, ti < T - 1 ? 0.25f : 0.f};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (w[a] == 0.f) continue;
+        float v[4];
+        ld4(p0 + (a - 1) * plane, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = fmaf(w[a], v[k], acc[k]);
+      }
+    } else {
+      const int64_t row = 2 * (int64_t)W * C;                       // one output row
+      const float* p0 = dy + ((b * T + ti) * 2 * H + 2 * hi) * row + (int64_t)(2 * wi) * C + c;           // output (2hi, 2wi)
+      const float wh[4] = {hi > 0 ? 0.25f : 0.f, hi > 0 ? 0.75f : 1.f, hi < H - 1 ? 0.75f : 1.f, hi < H - 1 ? 0.25f : 0.f};
+      const float ww[4] = {wi > 0 ? 0.25f : 0.f, wi > 0 ? 0.75f : 1.f, wi < W - 1 ? 0.75f : 1.f, wi < W - 1 ? 0.25f : 0.f};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (wh[a] == 0.f) continue;
+        float racc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          if (ww[bb] == 0.f) continue;
+          float v[4];
+          ld4(p0 + (a - 1) * row + (bb - 1) * C, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) racc[k] = fmaf(ww[bb], v[k], racc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = fmaf(wh[a], racc[k], acc[k]);
+      }
+    }
+    float* d = dx + pos * C + c;
+    if (accumulate) {
+      float o[4];
+      ld4(d, o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += o[k];
+    }
+    st4(d, acc);
+  }
+}
+
 int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
   int64_t cap = (int64_t)csts_num_sms() * 8;
@@ -882,6 +1011,15 @@ int csts_upsample_fwd(const float* x, float* y, int B, int T, int H, int W, int 
   int64_t total = (int64_t)B * T * ft * H * fh * W * fw * (C / 4);
   if (total == 0) return 0;
   CSTS_REQUIRE(total < (1LL << 32), "upsample_fwd: tensor too large for 32-bit indexing");
+  const int64_t cells = (int64_t)B * T * H * W * (C / 4);
+  if (ft == 1 && fh == 2 && fw == 2 && H >= 2 && W >= 2) {
+    launch_pdl(upsample2_fwd_kernel<false>, dim3(grid_for(cells, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, B, T, H, W, C);
+    return csts_check_launch("upsample_fwd");
+  }
+  if (ft == 2 && fh == 1 && fw == 1 && T >= 2) {
+    launch_pdl(upsample2_fwd_kernel<true>, dim3(grid_for(cells, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, B, T, H, W, C);
+    return csts_check_launch("upsample_fwd");
+  }
   launch_pdl(upsample_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, B, T, H, W, C, ft, fh, fw);
   return csts_check_launch("upsample_fwd");
 }
@@ -890,6 +1028,14 @@ int csts_upsample_bwd(const float* dy, float* dx, int B, int T, int H, int W, in
   int64_t total = (int64_t)B * T * H * W * (C / 4);
   if (total == 0) return 0;
   CSTS_REQUIRE(total < (1LL << 32), "upsample_bwd: tensor too large for 32-bit indexing");
+  if (ft == 1 && fh == 2 && fw == 2 && H >= 2 && W >= 2) {
+    launch_pdl(upsample2_bwd_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, dx, B, T, H, W, C, accumulate);
+    return csts_check_launch("upsample_bwd");
+  }
+  if (ft == 2 && fh == 1 && fw == 1 && T >= 2) {
+    launch_pdl(upsample2_bwd_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, dx, B, T, H, W, C, accumulate);
+    return csts_check_launch("upsample_bwd");
+  }
   launch_pdl(upsample_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, dy, dx, B, T, H, W, C, ft, fh, fw, accumulate);
   return csts_check_launch("upsample_bwd");
 }

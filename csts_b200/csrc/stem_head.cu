@@ -1,5 +1,7 @@
 // Stem, fusion glue and head kernels of CSTS: patch-embed im2col, separable position embedding,
 // fusion re-weighting, token mean, and the 1x1x1 classifier fused with the trilinear stem skip.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -270,6 +272,129 @@ __global__ void __launch_bounds__(256) classifier_bwd_stem_kernel(const float* _
   }
 }
 
+// ---- C <= 96 (the model's 96): a token is owned by 8 lanes with 3 four-channel vectors each, a warp works on 4 tokens at once
+// with 16-byte accesses (the kernels above walk one token per warp with scalar loads)
+__global__ void __launch_bounds__(256) classifier96_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ stem,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               float* __restrict__ logits, int B, int Ti, int S, int C) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31, li = lane & 7, grp = lane >> 3, wpb = blockDim.x >> 5;
+  const int To = 2 * Ti;
+  const uint32_t total = (uint32_t)B * To * S;
+  float wv[3][4];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = (li + 8 * j) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wv[j][k] = 0.f;
+    if (c < C) ld4(w + c, wv[j]);
+  }
+  const float b0 = bias[0];
+  for (uint32_t t0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 4; t0 < total; t0 += gridDim.x * wpb * 4) {
+    const uint32_t tok = t0 + grp;
+    const bool ok = tok < total;
+    uint32_t q = ok ? tok : 0;
+    const int s = (int)divmod(q, S), to = (int)divmod(q, To);
+    const int64_t b = q;
+    int i0, i1; float lam;
+    t_coef(to, Ti, i0, i1, lam);
+    const float* f = feat + (int64_t)(ok ? tok : 0) * C;
+    const float* a0 = stem + ((b * Ti + i0) * S + s) * C;
+    const float* a1 = stem + ((b * Ti + i1) * S + s) * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = (li + 8 * j) * 4;
+      if (c < C) {
+        float fv[4], x0[4], x1[4];
+        ld4(f + c, fv);
+        ld4(a0 + c, x0);
+        ld4(a1 + c, x1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += wv[j][k] * (fv[k] + (1.f - lam) * x0[k] + lam * x1[k]);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (ok && li == 0) logits[tok] = acc + b0;
+  }
+}
+
+__global__ void __launch_bounds__(256) classifier96_bwd_feat_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat,
+                                                                    const float* __restrict__ stem, const float* __restrict__ w,
+                                                                    float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ dbias,
+                                                                    int B, int Ti, int S, int C) {
+  pdl_wait();
+  __shared__ float s_dw[96];
+  __shared__ float s_db;
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) s_dw[i] = 0.f;
+  if (threadIdx.x == 0) s_db = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, li = lane & 7, grp = lane >> 3, wpb = blockDim.x >> 5;
+  const int To = 2 * Ti;
+  const uint32_t total = (uint32_t)B * To * S;
+  float wv[3][4], adw[3][4];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = (li + 8 * j) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { wv[j][k] = 0.f; adw[j][k] = 0.f; }
+    if (c < C) ld4(w + c, wv[j]);
+  }
+  float adb = 0.f;
+  for (uint32_t t0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 4; t0 < total; t0 += gridDim.x * wpb * 4) {
+    const uint32_t tok = t0 + grp;
+    if (tok >= total) continue;
+    uint32_t q = tok;
+    const int s = (int)divmod(q, S), to = (int)divmod(q, To);
+    const int64_t b = q;
+    int i0, i1; float lam;
+    t_coef(to, Ti, i0, i1, lam);
+    const float g = dlogits[tok];
+    const float* f = feat + (int64_t)tok * C;
+    const float* a0 = stem + ((b * Ti + i0) * S + s) * C;
+    const float* a1 = stem + ((b * Ti + i1) * S + s) * C;
+    float* df = dfeat + (int64_t)tok * C;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = (li + 8 * j) * 4;
+      if (c < C) {
+        float fv[4], x0[4], x1[4], o[4];
+        ld4(f + c, fv);
+        ld4(a0 + c, x0);
+        ld4(a1 + c, x1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          o[k] = g * wv[j][k];
+          adw[j][k] += g * (fv[k] + (1.f - lam) * x0[k] + lam * x1[k]);
+        }
+        st4(df + c, o);
+      }
+    }
+    if (li == 0) adb += g;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      adw[j][k] += __shfl_xor_sync(0xffffffffu, adw[j][k], 8);
+      adw[j][k] += __shfl_xor_sync(0xffffffffu, adw[j][k], 16);
+    }
+    const int c = (li + 8 * j) * 4;
+    if (grp == 0 && c < C) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&s_dw[c + k], adw[j][k]);
+    }
+  }
+  adb += __shfl_xor_sync(0xffffffffu, adb, 8);
+  adb += __shfl_xor_sync(0xffffffffu, adb, 16);
+  if (lane == 0) atomicAdd(&s_db, adb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+  if (threadIdx.x == 0) atomicAdd(dbias, s_db);
+}
+
 }  // namespace
 
 extern "C" {
@@ -318,6 +443,11 @@ int csts_token_mean_bwd(const float* dout, float* dx, int B, int N, int C, int a
 }
 int csts_classifier_fwd(const float* feat, const float* stem, const float* w, const float* bias, float* logits, int B, int Ti, int S, int C,
                         void* stream) {
+  if (C <= 96 && C % 4 == 0 && (int64_t)B * 2 * Ti * S < (1LL << 31)) {
+    launch_pdl(classifier96_fwd_kernel, dim3(grid_for((int64_t)B * 2 * Ti * S, 32)), dim3(256), 0, (cudaStream_t)stream, feat, stem, w, bias, logits,
+               B, Ti, S, C);
+    return csts_check_launch("classifier_fwd");
+  }
   launch_pdl(classifier_fwd_kernel, dim3(grid_for((int64_t)B * 2 * Ti * S, 8)), dim3(256), 0, (cudaStream_t)stream, feat, stem, w, bias, logits, B, Ti, S, C);
   return csts_check_launch("classifier_fwd");
 }
@@ -328,7 +458,13 @@ int csts_classifier_bwd(const float* dlogits, const float* feat, const float* st
   int64_t toks = (int64_t)B * 2 * Ti * S;
   int64_t blocks = (toks + 255) / 256;
   int grid = (int)(blocks < csts_num_sms() * 2 ? blocks : csts_num_sms() * 2);
-  launch_pdl(classifier_bwd_feat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dlogits, feat, stem, w, dfeat, dw, dbias, B, Ti, S, C);
+  if (C <= 96 && C % 4 == 0 && toks < (1LL << 31)) {
+    const int g96 = (int)std::min<int64_t>((toks + 127) / 128, (int64_t)csts_num_sms() * 4);       // >= 4 passes per warp
+    launch_pdl(classifier96_bwd_feat_kernel, dim3(g96 > 0 ? g96 : 1), dim3(256), 0, (cudaStream_t)stream, dlogits, feat, stem, w, dfeat, dw, dbias,
+               B, Ti, S, C);
+  } else {
+    launch_pdl(classifier_bwd_feat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dlogits, feat, stem, w, dfeat, dw, dbias, B, Ti, S, C);
+  }
   int rc = csts_check_launch("classifier_bwd_feat");
   if (rc) return rc;
   CSTS_REQUIRE((int64_t)B * Ti * S * C < (1LL << 32), "classifier_bwd: tensor too large for 32-bit indexing");
