@@ -58,19 +58,44 @@ def main():
         mask = dict(mask_hw=64, mask_t=4) if name == "spatial_fusion" else {}
         state = {}
 
+        # the path host/block.py takes at this site: fused whole-row softmax epilogue (<= 256 keys), two-pass logsumexp +
+        # exp epilogue (> 256 keys), or f32 scores + masked softmax kernel (spatial fusion)
+        fused = Lk <= 256 and Lq >= 64 and name != "spatial_fusion"
+        two_pass = not fused and name != "spatial_fusion"
+        scale = d ** -0.5
+        P = torch.empty(B, h, Lq, ldS, dtype=torch.bfloat16, device=dev)
+        dS = torch.empty_like(P)
+        lse = torch.empty(B, h, Lq, dtype=torch.float32, device=dev)
+        qk = dict(M=Lq, N=Lk, K=d, lda=q_ld, ldb=d, alpha=scale, batch=(B, h), sA=q_s, sB=kv_s)
+
         def fwd():
-            K.gemm(qbuf, k, M=Lq, N=Lk, K=d, lda=q_ld, ldb=d, out=S, ldc=ldS, alpha=d ** -0.5, batch=(B, h), sA=q_s, sB=kv_s, sC=sP)
-            state["P"] = K.softmax_fwd(S, Lk, ldS, nq=Lq, **mask)
-            K.gemm(state["P"], v, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=d, out=o, ldc=Cn, batch=(B, h), sA=sP, sB=kv_s, sC=(Lq * Cn, d))
+            if fused:
+                K.gemm(qbuf, k, out=P, ldc=ldS, act=3, sC=sP, **qk)
+            elif two_pass:
+                K.gemm(qbuf, k, out=lse, ldc=Lk, act=5, sC=(h * Lq, Lq), **qk)
+                K.gemm(qbuf, k, out=P, ldc=ldS, act=6, rowvec=lse, sC=sP, **qk)
+            else:
+                K.gemm(qbuf, k, out=S, ldc=ldS, sC=sP, **qk)
+                state["P"] = K.softmax_fwd(S, Lk, ldS, nq=Lq, **mask)
+            K.gemm(state.get("P", P), v, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=d, out=o, ldc=Cn, batch=(B, h), sA=sP, sB=kv_s, sC=(Lq * Cn, d))
 
         def bwd():
-            P = state["P"]
-            K.gemm(P, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=Cn, out=dv, ldc=d, batch=(B, h), sA=sP,
+            Pm = state.get("P", P)
+            K.gemm(Pm, do, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=Cn, out=dv, ldc=d, batch=(B, h), sA=sP,
                    sB=(Lq * Cn, d), sC=kv_s)
-            K.gemm(do, v, M=Lq, N=Lk, K=d, lda=Cn, ldb=d, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * Cn, d), sB=kv_s, sC=sP)
-            dS = K.softmax_bwd(P, dP, Lk, d ** -0.5)
-            K.gemm(dS, k, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=d, out=dq, ldc=q_ld, batch=(B, h), sA=sP, sB=kv_s, sC=q_s)
-            K.gemm(dS, qbuf, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=q_ld, out=dk, ldc=d, batch=(B, h), sA=sP,
+            if fused:
+                K.gemm(do, v, M=Lq, N=Lk, K=d, lda=Cn, ldb=d, out=dS, ldc=ldS, alpha=scale, act=4, Z=Pm, batch=(B, h), sA=(Lq * Cn, d), sB=kv_s, sC=sP)
+                ds = dS
+            elif two_pass:
+                D = K.rowdot(do.view(B * Lq, Cn), o.view(B * Lq, Cn), B, Lq, h, d)
+                K.gemm(do, v, M=Lq, N=Lk, K=d, lda=Cn, ldb=d, out=dS, ldc=ldS, alpha=scale, act=7, Z=Pm, rowvec=D, batch=(B, h), sA=(Lq * Cn, d),
+                       sB=kv_s, sC=sP)
+                ds = dS
+            else:
+                K.gemm(do, v, M=Lq, N=Lk, K=d, lda=Cn, ldb=d, out=dP, ldc=ldS, batch=(B, h), sA=(Lq * Cn, d), sB=kv_s, sC=sP)
+                ds = K.softmax_bwd(Pm, dP, Lk, scale)
+            K.gemm(ds, k, M=Lq, N=d, K=Lk, lda=ldS, b_kmajor=False, ldb=d, out=dq, ldc=q_ld, batch=(B, h), sA=sP, sB=kv_s, sC=q_s)
+            K.gemm(ds, qbuf, M=Lk, N=d, K=Lq, a_kmajor=False, lda=ldS, b_kmajor=False, ldb=q_ld, out=dk, ldc=d, batch=(B, h), sA=sP,
                    sB=q_s, sC=kv_s)
 
         t_f = graph_time(fwd)
@@ -78,7 +103,9 @@ def main():
         fl = 4.0 * B * h * Lq * Lk * d
         print(json.dumps({"site": name, "heads": h, "d": d, "Lq": Lq, "Lk": Lk, "fwd_ms": round(t_f, 4), "bwd_ms": round(t_b, 4),
                           "fwd_tflops": round(fl / t_f / 1e9, 1), "bwd_tflops": round(2.0 * fl / t_b / 1e9, 1),
-                          "fwd_frac_of_bf16_peak": round(fl / t_f / 1e9 / peak, 3)}), flush=True)
+                          "fwd_frac_of_bf16_peak": round(fl / t_f / 1e9 / peak, 3), "bwd_frac_of_bf16_peak": round(2.0 * fl / t_b / 1e9 / peak, 3),
+                          "path": "fused-softmax epilogue" if fused else ("two-pass (lse + exp epilogue)" if two_pass else "f32 scores + masked softmax")}),
+              flush=True)
 
 
 if __name__ == "__main__":

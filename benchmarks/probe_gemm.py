@@ -3,7 +3,7 @@
 
     python benchmarks/probe_gemm.py [--reps 3] [--time] name[,name...]
 
-names: fc1_dec4 (262144x384x192 GELU), fc1_enc (8192x1536x384 GELU), dgelu_dec3 (131072x384x192 times-Z, MN-major B),
+names: fc1_dec4 (262144x384x192 GELU), fc1_enc (8192x1536x384 GELU), fc1_dec2 (32768x1536x768 GELU), qkv_s4 (8192x2304x768), dgelu_dec3 (131072x384x192 times-Z, MN-major B),
        fc2_enc (8192x384x1536 + residual f32), qkv_big (131072x576x192), wgrad_fc1 (1536x384 over 8192 tokens, split-K),
        qk_softmax (1024x256x96 x32 heads), pv (1024x96x256 x32)
 """
@@ -23,8 +23,8 @@ def rnd(*shape, dtype=torch.bfloat16, scale=1.0):
 
 
 def make(name):
-    if name in ("fc1_dec4", "fc1_enc", "fc1_dec3"):
-        M, N, Kd = {"fc1_dec4": (262144, 384, 192), "fc1_enc": (8192, 1536, 384), "fc1_dec3": (131072, 768, 384)}[name]
+    if name in ("fc1_dec4", "fc1_enc", "fc1_dec3", "fc1_dec2"):
+        M, N, Kd = {"fc1_dec4": (262144, 384, 192), "fc1_enc": (8192, 1536, 384), "fc1_dec3": (131072, 768, 384), "fc1_dec2": (32768, 1536, 768)}[name]
         A, B, bias = rnd(M, Kd), rnd(N, Kd, scale=0.05), torch.randn(N, device=dev)
         Z, out = torch.empty(M, N, dtype=torch.bfloat16, device=dev), torch.empty(M, N, dtype=torch.bfloat16, device=dev)
         return lambda **kw: K.gemm(A, B, M=M, N=N, K=Kd, bias=bias, act=1, Z=Z, out=out, **kw), 2.0 * M * N * Kd, 2.0 * (M * Kd + N * Kd + 2 * M * N)
@@ -38,8 +38,8 @@ def make(name):
         A, B, bias = rnd(M, Kd), rnd(N, Kd, scale=0.05), torch.randn(N, device=dev)
         res, out = torch.randn(M, N, device=dev), torch.empty(M, N, device=dev)
         return lambda **kw: K.gemm(A, B, M=M, N=N, K=Kd, bias=bias, residual=res, out=out, **kw), 2.0 * M * N * Kd, 2.0 * (M * Kd + N * Kd) + 8.0 * M * N
-    if name == "qkv_big":
-        M, N, Kd = 131072, 576, 192
+    if name in ("qkv_big", "qkv_s4"):
+        M, N, Kd = (131072, 576, 192) if name == "qkv_big" else (8192, 2304, 768)
         A, B, bias = rnd(M, Kd), rnd(N, Kd, scale=0.05), torch.randn(N, device=dev)
         out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
         return lambda **kw: K.gemm(A, B, M=M, N=N, K=Kd, bias=bias, out=out, **kw), 2.0 * M * N * Kd, 2.0 * (M * Kd + N * Kd + M * N)
