@@ -23,10 +23,12 @@ FAMILIES = [
     ("softmax_", "attention softmax fwd/bwd (blocks with > 256 keys, spatial fusion)"),
     ("mt_", "optimizer: grad norm + clip + AdamW + weight refresh"),
     ("cast_", "f32 -> 16-bit gradient casts"),
-    ("upsample_", "trilinear skip up-sampling fwd/bwd"),
+    ("upsample", "trilinear skip up-sampling fwd/bwd"),
     ("maxpool_", "MaxPool3d skip fwd/bwd"),
     ("im2col", "patch-embed im2col"),
-    ("classifier_", "classifier + stem skip fwd/bwd"),
+    ("classifier", "classifier + stem skip fwd/bwd"),
+    ("rowdot", "softmax-backward row term rowsum(dO o O)"),
+    ("f1_", "adaptive-F1 metric"),
     ("colsum", "column sums (residual bias gradients)"),
     ("permute_021", "frame-pool activation transposes"),
     ("kldiv|sim_matrix|egonce|reweight|token_mean|pos_embed|add_kernel|scale_kernel", "losses, fusion glue, stem glue"),
