@@ -1107,7 +1107,7 @@ bool csts_gemm_tc_supported(const csts_gemm_args& a) {
   // skinny problems go to the generic kernel — unless they stream a large operand (the (1,8,8) frame pools: 32 rows against
   // a 75 MB weight): those are bandwidth problems, and TMA + a deep ring move bytes faster than cp.async, whatever the tile's
   // fill (rows beyond M are zero-filled by the tensor map and clipped by the TMA store)
-  if (a.M < 64 && (int64_t)a.N * a.K < (1 << 24)) return false;
+  if (a.M < 64 && (int64_t)a.N * a.K * nb < (1 << 24)) return false;
   return true;
 }
 

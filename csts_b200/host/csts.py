@@ -145,7 +145,17 @@ class FramePoolFn(torch.autograd.Function):
         T = N // 64
         a = K.permute_021(tok.contiguous(), B * T, 64, Cn, wc.act)          # (B*T, hw, c) f32 -> (B*T, c, hw) 16-bit
         Kd = 64 * Cn
-        out = K.gemm(a.view(B * T, Kd), wc.w(weight), M=B * T, N=weight.shape[0], K=Kd, bias=bias, out_dtype=torch.float32, split_k=-1)
+        # Split over the 49152-deep contraction WITHOUT atomics: the splits are a batch dimension (operand batch stride = one
+        # k-range), every split writes its own (B*T, O) partial, and a column sum adds them — in a fixed order — onto the bias.
+        # The forward pass therefore holds no order-dependent f32 sum: two evaluations of one batch are bit-identical.
+        O = weight.shape[0]
+        S = 24 if Kd % (24 * 64) == 0 else 1
+        Kc = Kd // S
+        part = torch.empty((S, B * T, O), dtype=torch.float32, device=tok.device)
+        K.gemm(a.view(B * T, Kd), wc.w(weight), M=B * T, N=O, K=Kc, lda=Kd, ldb=Kd, out=part, ldc=O, batch=(S, 1), sA=(Kc, 0), sB=(Kc, 0),
+               sC=(B * T * O, 0))
+        out = bias.detach().repeat(B * T)
+        K.colsum(part.view(S, B * T * O), S, B * T * O, out=out)
         ctx.save_for_backward(a)
         ctx.wc, ctx.weight, ctx.dims = wc, weight, (B, N, Cn)
         return out.view(B, T, weight.shape[0])

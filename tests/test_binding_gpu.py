@@ -104,14 +104,13 @@ def test_reference_build_model_builds_the_b200_model_and_its_loop_trains_it(boun
     assert got[2][1] < got[0][1]                                          # and it trains: the KL term falls on a repeated batch
 
     # (3) with the loss lines bound as well (second snippet) the literal loop IS train_step's sequence:
-    #     the first step's loss agrees to f32 round-off (the forward pass holds one split-K product combined with f32
-    #     atomics — the frame pools — so two evaluations are not bit-reproducible)
+    #     the first step's loss is bit-identical (the forward pass holds no order-dependent sum)
     third = build_model(bcfg)
     third.load_state_dict(sd, strict=True)
     third.train()
     oopt = ref_optim.construct_optimizer(third, cfg)
     bound = _literal_steps(cfg, third, oopt, batches, b_losses, b_frame_softmax, b_sim_matrix)
-    assert abs(bound[0][0] - want[0]) <= 5e-5 * abs(want[0]), (bound[0], want[0])
+    assert bound[0][0] == want[0], (bound[0], want[0])
     for g, w in zip(bound[1:], want[1:]):
         assert abs(g[0] - w) <= 0.25 * abs(w)
 
