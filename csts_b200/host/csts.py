@@ -172,6 +172,13 @@ class FramePoolFn(torch.autograd.Function):
         dtok = K.permute_021(dtok_t, B * T, Cn, 64, torch.float32)                                                  # -> (B*T, hw, c)
         db = torch.zeros(O, dtype=torch.float32, device=dout.device)
         slot = grad_slot(ctx.wc, weight)          # 151 MB: written straight into the gradient arena
+        sync = getattr(ctx.wc, "grad_sync", None)
+        if sync is not None and slot is not None and id(weight) in sync.factored:
+            # data parallel: the ranks exchange the two thin factors of this gradient instead of the 151 MB product
+            # (host/distributed.py::OverlappedGradSync.factored_wgrad); the bias gradient takes the ordinary all-reduce
+            K.colsum(dout, B * T, O, out=db)
+            dw = sync.factored_wgrad(weight, g, a.view(B * T, Kd), slot.view(O, Kd))
+            return None, dtok.view(B, N, Cn), dw.view(weight.shape), db
         dw = K.gemm(g, a.view(B * T, Kd), M=O, N=Kd, K=B * T, a_kmajor=False, b_kmajor=False, lda=O, ldb=Kd, out_dtype=torch.float32,
                     out=None if slot is None else slot.view(O, Kd), rowsum=db)
         return None, dtok.view(B, N, Cn), dw.view(weight.shape), db
@@ -376,6 +383,11 @@ class CSTS(nn.Module):
         params = list(self.parameters())
         if wc.arena is None or not wc.arena.matches(params):
             wc.arena = GradArena(params) if os.environ.get("CSTS_GRAD_ARENA", "1") == "1" else None
+
+    def factored_grad_params(self):
+        """Parameters whose gradient is a thin product (B*T rows) that a data-parallel exchange can average from its
+        factors instead of all-reducing the product: the three frame-pool kernels (host/distributed.py)."""
+        return [self.vision_pool.weight, self.audio_pool.weight, self.audio_pool2.weight]
 
     def forward(self, x, y, return_embed=False, return_spatial_attn=False, return_temporal_attn=False):
         video = x[0] if isinstance(x, (list, tuple)) else x

@@ -113,9 +113,16 @@ class OverlappedGradSync:
     all-reduced IN PLACE: no packing copy, no re-pointing of ``p.grad``, and no buffer whose lifetime spans two
     streams (the arena is persistent).  A post-accumulate-grad hook counts down each bucket; when it is complete
     its slice is all-reduced (NCCL, AVG) on a side stream while backward keeps running on the main stream.
-    ``finish()`` joins the side stream before the clip / optimizer step.  Buckets are ~32 MB except that a large
-    tensor (the three 151 MB frame-pool kernels, ready after the decoder + fusion backward) closes its own, so only
-    the last small bucket of early-encoder gradients is exposed after backward ends.
+    ``finish()`` joins the side stream before the clip / optimizer step.  Buckets are ~32 MB, so only the last small
+    bucket of early-encoder gradients is exposed after backward ends.
+
+    Factored exchange.  Three parameters — the (768, 768, 1, 8, 8) frame-pool kernels — hold 453 MB of the 753 MB
+    gradient, yet each of those gradients is a product of two thin factors: dW = dY^T . X with dY (B*T, 768) and
+    X (B*T, 49152), B*T = 32 rows per rank.  Averaging dW over ranks equals ONE product over the concatenated rows,
+    mean_r dY_r^T X_r = (1/R) [dY_1; ..; dY_R]^T [X_1; ..; X_R], so for these parameters (``model.factored_grad_params()``)
+    the ranks all-gather the 16-bit factors (3.2 MB per rank and kernel) and every rank forms the averaged gradient
+    itself, straight into its arena slot (``factored_wgrad``): 60 % of the all-reduce volume never crosses NVLink, and
+    the sum over ranks is accumulated in f32 inside one tensor-core product instead of being rounded per rank.
     """
 
     def __init__(self, model, bucket_bytes=32 << 20):
@@ -128,6 +135,11 @@ class OverlappedGradSync:
         self.groups, self.ranges, self.group_of, self.pending = [], [], {}, []
         self.stream = None
         self.enabled = False
+        import os
+        factored = model.factored_grad_params() if hasattr(model, "factored_grad_params") and \
+            os.environ.get("CSTS_FACTORED_WGRAD", "1") == "1" else []
+        self.factored = {id(p) for p in factored}
+        self._factor_bufs = {}
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
@@ -135,6 +147,12 @@ class OverlappedGradSync:
         self.arena = arena
         self.groups, cur, size = [], [], 0
         for p in self.params:
+            if id(p) in self.factored:           # its own group, never all-reduced (factored_wgrad fills the slot)
+                if cur:
+                    self.groups.append(cur)
+                self.groups.append([p])
+                cur, size = [], 0
+                continue
             cur.append(p)
             size += p.numel() * 4
             if size >= self.bucket_bytes:
@@ -142,6 +160,7 @@ class OverlappedGradSync:
                 cur, size = [], 0
         if cur:
             self.groups.append(cur)
+        self.external = [len(g) == 1 and id(g[0]) in self.factored for g in self.groups]
         self.ranges = [arena.range_of(g) for g in self.groups]
         self.group_of = {id(p): g for g, ps in enumerate(self.groups) for p in ps}
 
@@ -157,6 +176,7 @@ class OverlappedGradSync:
             self.stream = torch.cuda.Stream()
         self.pending = [len(g) for g in self.groups]
         self.enabled = True
+        self.model._wc.grad_sync = self
 
     def _hook(self, param):
         if not self.enabled:
@@ -164,7 +184,7 @@ class OverlappedGradSync:
         self.arena.adopt(param)          # no-op for gradients written in place; a small copy for the others
         g = self.group_of[id(param)]
         self.pending[g] -= 1
-        if self.pending[g] == 0:
+        if self.pending[g] == 0 and not self.external[g]:
             lo, hi = self.ranges[g]
             self.stream.wait_stream(torch.cuda.current_stream())
             wc = getattr(self.model, "_wc", None)
@@ -181,8 +201,34 @@ class OverlappedGradSync:
         if not self.enabled:
             return
         self.enabled = False
+        if hasattr(self.model, "_wc"):
+            self.model._wc.grad_sync = None
         assert all(c == 0 for c in self.pending), "a parameter received no gradient"
         torch.cuda.current_stream().wait_stream(self.stream)
+
+    def factored_wgrad(self, weight, dy16, x16, out):
+        """Rank-averaged weight gradient of a factored parameter: all-gather the rows of [dY | X] (16-bit, this rank's
+        (rows, O) and (rows, Kd) factors), then out (O, Kd) f32 = (1/R) [dY_1;..;dY_R]^T [X_1;..;X_R] on the exchange
+        stream.  `out` is the parameter's arena slot.  The staging buffers are persistent (one pair per parameter), so no
+        allocation's lifetime spans two streams; they are free again once ``finish()`` has joined the exchange stream."""
+        from .. import kernels as K
+        world = get_world_size()
+        rows, O = dy16.shape
+        Kd = x16.shape[1]
+        bufs = self._factor_bufs.get(id(weight))
+        if bufs is None or bufs[0].dtype != dy16.dtype or bufs[0].shape != (rows, O + Kd) or bufs[1].shape[0] != world * rows:
+            bufs = (torch.empty((rows, O + Kd), dtype=dy16.dtype, device=dy16.device),
+                    torch.empty((world * rows, O + Kd), dtype=dy16.dtype, device=dy16.device))
+            self._factor_bufs[id(weight)] = bufs
+        packed, gathered = bufs
+        packed[:, :O].copy_(dy16)
+        packed[:, O:].copy_(x16)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(gathered, packed)
+            K.gemm(gathered, gathered, b_off=O, M=O, N=Kd, K=world * rows, a_kmajor=False, b_kmajor=False, lda=O + Kd, ldb=O + Kd,
+                   out=out, out_dtype=torch.float32, alpha=1.0 / world)
+        return out
 
 
 def broadcast_parameters(model, src=0):

@@ -47,6 +47,7 @@ class WeightCache:
         self._audio = None
         self._main = None
         self.sync_aware = False         # set by OverlappedGradSync: the gradient exchange waits for every stream of the model
+        self.grad_sync = None           # the active OverlappedGradSync between its start() and finish() (factored weight gradients)
         self._handoff = {}
         self.act_checkpoint = False     # MODEL.ACT_CHECKPOINT: encoder blocks keep their input only and recompute in backward
         self.defer_join = False

@@ -67,7 +67,11 @@ def _worker(rank, world, port, q):
         (kld + cfg.MODEL.LOSS_ALPHA * nce).backward()
         noise = (sum((first[n] - p.grad).pow(2).sum().item() for n, p in model.named_parameters()) / den) ** 0.5
         worst = max(((dp[n] - p.grad).norm() / p.grad.norm()).item() for n, p in model.named_parameters() if p.grad.norm() > 1e-5)
-        q.put(((num / den) ** 0.5, worst, in_arena, noise))
+        # the three frame-pool kernels are averaged from their all-gathered factors, not all-reduced
+        pools = {n: ((dp[n] - p.grad).norm() / p.grad.norm()).item() for n, p in model.named_parameters()
+                 if any(p is f for f in model.factored_grad_params())}
+        assert len(pools) == 3 and len(sync._factor_bufs) == 3 and sum(sync.external) == 3
+        q.put(((num / den) ** 0.5, worst, in_arena, noise, pools))
     dist.barrier()
     os._exit(0)
 
@@ -80,10 +84,11 @@ def test_two_gpu_gradients_match_global_batch():
     procs = [ctx.Process(target=_worker, args=(r, 2, 29641, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rel, worst, in_arena, noise = q.get(timeout=300)
+    rel, worst, in_arena, noise, pools = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
-    print("global-batch vs data-parallel gradient, relative L2:", rel, "worst tensor:", worst, "run-to-run noise of the global step:", noise)
+    print("global-batch vs data-parallel gradient, relative L2:", rel, "worst tensor:", worst, "run-to-run noise of the global step:", noise,
+          "frame-pool kernels (factored exchange):", pools)
     # Samples are independent through the network, so both sides evaluate the same per-sample arithmetic; what differs is
     # what differs between any two runs of ONE computation — f32 summation order (split-K reduce-adds, the cross-rank
     # reduction) and the 16-bit rounding flips it causes (tools/grad_noise.py: ~1e-2 in bf16 storage) — so the yardstick is
@@ -92,3 +97,4 @@ def test_two_gpu_gradients_match_global_batch():
     assert in_arena, "a gradient was not reduced inside the arena"
     assert rel < max(2.5 * noise, 5e-3), (rel, noise)       # measured: rel 8e-3 beside a run-to-run floor of 1e-2 (bf16 storage)
     assert worst < 0.3, worst
+    assert max(pools.values()) < max(5 * noise, 2e-2), pools

@@ -310,6 +310,39 @@ def test_grad_arena_layout_and_adoption():
     assert ar.owns(x.grad, x) and float(x.grad.sum()) == 30.0
 
 
+def test_overlapped_grad_sync_buckets_keep_factored_parameters_apart():
+    """host/distributed.py::OverlappedGradSync: buckets are contiguous arena slices in backward order; a parameter whose
+    gradient is exchanged through its factors (the frame-pool kernels) forms a group of its own that is never all-reduced,
+    and the groups on either side of it stay contiguous."""
+    from csts_b200.host import distributed as du
+    from csts_b200.host.grad_arena import GradArena
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.zeros(10))
+            self.pool = torch.nn.Parameter(torch.zeros(64, 8))
+            self.b = torch.nn.Parameter(torch.zeros(6))
+            self.c = torch.nn.Parameter(torch.zeros(30))
+
+        def factored_grad_params(self):
+            return [self.pool]
+    m = Model()
+    sync = du.OverlappedGradSync(m, bucket_bytes=100)
+    arena = GradArena(list(m.parameters()))
+    sync._bind(arena)
+    names = {id(p): n for n, p in m.named_parameters()}
+    assert [[names[id(p)] for p in g] for g in sync.groups] == [["c"], ["b"], ["pool"], ["a"]]
+    assert sync.external == [False, False, True, False]
+    for g, (lo, hi) in zip(sync.groups, sync.ranges):
+        assert (lo, hi) == arena.range_of(g) and hi - lo >= sum(p.numel() for p in g)
+    # the identity the factored exchange rests on: the rank-mean of thin products is one product over concatenated rows
+    gen = torch.Generator().manual_seed(3)
+    dys, xs = [torch.randn(4, 6, generator=gen) for _ in range(3)], [torch.randn(4, 9, generator=gen) for _ in range(3)]
+    mean = sum(dy.t() @ x for dy, x in zip(dys, xs)) / 3
+    torch.testing.assert_close(torch.cat(dys).t() @ torch.cat(xs) / 3, mean, rtol=1e-5, atol=1e-6)
+
+
 def _k400_like_checkpoint(model_state, tmp_path):
     """A pre-trained-MViT-like checkpoint: 224-pixel / 16-frame position embeddings, a DDP-style "module." prefix, one
     tensor of a different shape (the Kinetics classification head) and one unknown name."""
