@@ -157,7 +157,7 @@ class FramePoolFn(torch.autograd.Function):
         out = bias.detach().repeat(B * T)
         K.colsum(part.view(S, B * T * O), S, B * T * O, out=out)
         ctx.save_for_backward(a)
-        ctx.wc, ctx.weight, ctx.dims = wc, weight, (B, N, Cn)
+        ctx.wc, ctx.weight, ctx.bias, ctx.dims = wc, weight, bias, (B, N, Cn)
         return out.view(B, T, weight.shape[0])
 
     @staticmethod
@@ -170,15 +170,29 @@ class FramePoolFn(torch.autograd.Function):
         g = K.cast16(dout, ctx.wc.grad)
         dtok_t = K.gemm(g, ctx.wc.w(weight), M=B * T, N=Kd, K=O, b_kmajor=False, ldb=Kd, out_dtype=torch.float32)   # (B*T, c, hw)
         dtok = K.permute_021(dtok_t, B * T, Cn, 64, torch.float32)                                                  # -> (B*T, hw, c)
-        db = torch.zeros(O, dtype=torch.float32, device=dout.device)
         slot = grad_slot(ctx.wc, weight)          # 151 MB: written straight into the gradient arena
         sync = getattr(ctx.wc, "grad_sync", None)
         if sync is not None and slot is not None and id(weight) in sync.factored:
             # data parallel: the ranks exchange the two thin factors of this gradient instead of the 151 MB product
             # (host/distributed.py::OverlappedGradSync.factored_wgrad); the bias gradient takes the ordinary all-reduce
-            K.colsum(dout, B * T, O, out=db)
+            db = K.colsum(dout, B * T, O)
             dw = sync.factored_wgrad(weight, g, a.view(B * T, Kd), slot.view(O, Kd))
             return None, dtok.view(B, N, Cn), dw.view(weight.shape), db
+        bslot = grad_slot(ctx.wc, ctx.bias)
+        if slot is not None and bslot is not None:
+            # both gradients land in arena slots nobody reads before the optimizer: the 151 MB product (and the bias gradient
+            # fused into it) leaves the dX chain for the weight-gradient stream, like the blocks' weight gradients
+            fork = ctx.wc.backward_fork()
+
+            def wgrad():
+                bslot.zero_()
+                return K.gemm(g, a.view(B * T, Kd), M=O, N=Kd, K=B * T, a_kmajor=False, b_kmajor=False, lda=O, ldb=Kd,
+                              out_dtype=torch.float32, out=slot.view(O, Kd), rowsum=bslot)
+            dw = fork.run(wgrad, g, a)
+            if not getattr(ctx.wc, "defer_join", False):
+                fork.join()
+            return None, dtok.view(B, N, Cn), dw.view(weight.shape), bslot
+        db = torch.zeros(O, dtype=torch.float32, device=dout.device)
         dw = K.gemm(g, a.view(B * T, Kd), M=O, N=Kd, K=B * T, a_kmajor=False, b_kmajor=False, lda=O, ldb=Kd, out_dtype=torch.float32,
                     out=None if slot is None else slot.view(O, Kd), rowsum=db)
         return None, dtok.view(B, N, Cn), dw.view(weight.shape), db

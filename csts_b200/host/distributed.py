@@ -125,11 +125,11 @@ class OverlappedGradSync:
     the sum over ranks is accumulated in f32 inside one tensor-core product instead of being rounded per rank.
     """
 
-    def __init__(self, model, bucket_bytes=32 << 20):
+    def __init__(self, model, bucket_bytes=32 << 20, tail_bytes=40 << 20, tail_bucket_bytes=8 << 20):
         self.model = model
         if hasattr(model, "_wc"):
             model._wc.sync_aware = True           # this exchange waits for the model's audio and weight-gradient streams
-        self.bucket_bytes = bucket_bytes
+        self.bucket_bytes, self.tail_bytes, self.tail_bucket_bytes = bucket_bytes, tail_bytes, tail_bucket_bytes
         self.params = [p for p in model.parameters() if p.requires_grad][::-1]
         self.arena = None
         self.groups, self.ranges, self.group_of, self.pending = [], [], {}, []
@@ -146,6 +146,7 @@ class OverlappedGradSync:
     def _bind(self, arena):
         self.arena = arena
         self.groups, cur, size = [], [], 0
+        left = sum(p.numel() * 4 for p in self.params if id(p) not in self.factored)
         for p in self.params:
             if id(p) in self.factored:           # its own group, never all-reduced (factored_wgrad fills the slot)
                 if cur:
@@ -155,7 +156,10 @@ class OverlappedGradSync:
                 continue
             cur.append(p)
             size += p.numel() * 4
-            if size >= self.bucket_bytes:
+            left -= p.numel() * 4
+            # the last buckets (the first encoder blocks, whose gradients arrive when backward ends) are small: what is
+            # exposed after the last kernel of backward is one short all-reduce
+            if size >= (self.bucket_bytes if left > self.tail_bytes else self.tail_bucket_bytes):
                 self.groups.append(cur)
                 cur, size = [], 0
         if cur:
@@ -190,7 +194,9 @@ class OverlappedGradSync:
             wc = getattr(self.model, "_wc", None)
             if wc is not None:
                 # a bucket mixes gradients of the video encoder (this stream), of the audio encoder (its own stream) and
-                # weight gradients produced on the backward pass's second stream
+                # weight gradients produced on the backward pass's second stream.  (Waiting per bucket for exactly the
+                # points at which its gradients were produced — one event per stream — measured no faster: 21.98 vs
+                # 21.93 ms/step on 2 GPUs.)
                 for s in wc.branch_streams():
                     self.stream.wait_stream(s)
             with torch.cuda.stream(self.stream):

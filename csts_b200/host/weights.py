@@ -53,6 +53,7 @@ class WeightCache:
         self.defer_join = False
         self.parallel_audio = os.environ.get("CSTS_PARALLEL_AUDIO", "1") == "1"
         self.fork_backward = os.environ.get("CSTS_FORK_WGRAD", "1") == "1"
+        self.audio_wgrad_inline = os.environ.get("CSTS_AUDIO_WGRAD_INLINE", "1") == "1"
 
     def backward_fork(self):
         """The weight-gradient branch of the backward pass (block.py::_Fork): one second stream per model.  With
@@ -60,6 +61,11 @@ class WeightCache:
         join_backward(), instead of at the end of every block, so it keeps running under the next blocks' dX chain."""
         from .block import _Fork
         if not self.fork_backward:
+            return _Fork()
+        # The audio encoder's backward already runs on its own stream, next to the four times longer video chain: its
+        # weight gradients stay on that stream.  On the shared branch they would queue behind every video weight gradient
+        # (autograd enqueues the whole video backward first) and finish last, after both dX chains.
+        if self.audio_wgrad_inline and self._audio is not None and torch.cuda.current_stream() == self._audio:
             return _Fork()
         if self._fork is None or self._fork.side.device.index != torch.cuda.current_device():
             self._fork = _Fork(torch.cuda.Stream())

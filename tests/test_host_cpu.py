@@ -320,6 +320,9 @@ def test_overlapped_grad_sync_buckets_keep_factored_parameters_apart():
     class Model(torch.nn.Module):
         def __init__(self):
             super().__init__()
+            self.f = torch.nn.Parameter(torch.zeros(5))
+            self.e = torch.nn.Parameter(torch.zeros(5))
+            self.d = torch.nn.Parameter(torch.zeros(5))
             self.a = torch.nn.Parameter(torch.zeros(10))
             self.pool = torch.nn.Parameter(torch.zeros(64, 8))
             self.b = torch.nn.Parameter(torch.zeros(6))
@@ -328,12 +331,13 @@ def test_overlapped_grad_sync_buckets_keep_factored_parameters_apart():
         def factored_grad_params(self):
             return [self.pool]
     m = Model()
-    sync = du.OverlappedGradSync(m, bucket_bytes=100)
+    # 100-byte buckets in backward order; the last 90 bytes of gradient (what arrives when backward ends) go in 40-byte ones
+    sync = du.OverlappedGradSync(m, bucket_bytes=100, tail_bytes=90, tail_bucket_bytes=40)
     arena = GradArena(list(m.parameters()))
     sync._bind(arena)
     names = {id(p): n for n, p in m.named_parameters()}
-    assert [[names[id(p)] for p in g] for g in sync.groups] == [["c"], ["b"], ["pool"], ["a"]]
-    assert sync.external == [False, False, True, False]
+    assert [[names[id(p)] for p in g] for g in sync.groups] == [["c"], ["b"], ["pool"], ["a"], ["d", "e"], ["f"]]
+    assert sync.external == [False, False, True, False, False, False]
     for g, (lo, hi) in zip(sync.groups, sync.ranges):
         assert (lo, hi) == arena.range_of(g) and hi - lo >= sum(p.numel() for p in g)
     # the identity the factored exchange rests on: the rank-mean of thin products is one product over concatenated rows
