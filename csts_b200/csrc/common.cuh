@@ -225,3 +225,21 @@ template <> __device__ __forceinline__ float2 unpack2<bf16>(uint32_t w) {
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 template <> __device__ __forceinline__ float2 unpack2<f16>(uint32_t w) { return __half22float2(*reinterpret_cast<f162*>(&w)); }
+
+// Mixed-precision FMA of sm_100 (PTX fma.rn.f32.{f16,bf16} = SASS FHFMA): a0 += x.lo * w.lo, a1 += x.hi * w.hi with x, w packed
+// 16-bit pairs and f32 accumulators.  The 16-bit operands are read straight from the halves of a 32-bit register (R.H0 / R.H1),
+// so a kernel that multiplies two 16-bit tensors needs no unpack instructions at all; the product of two 11-bit (8-bit)
+// significands is exact in f32, so the result is bit-identical to converting both operands first.
+template <typename T> __device__ __forceinline__ void fhfma2(float& a0, float& a1, uint32_t x, uint32_t w);
+template <> __device__ __forceinline__ void fhfma2<bf16>(float& a0, float& a1, uint32_t x, uint32_t w) {
+  asm("{\n.reg .b16 x0, x1, w0, w1;\nmov.b32 {x0, x1}, %2;\nmov.b32 {w0, w1}, %3;\n"
+      "fma.rn.f32.bf16 %0, x0, w0, %0;\nfma.rn.f32.bf16 %1, x1, w1, %1;\n}\n"
+      : "+f"(a0), "+f"(a1)
+      : "r"(x), "r"(w));
+}
+template <> __device__ __forceinline__ void fhfma2<f16>(float& a0, float& a1, uint32_t x, uint32_t w) {
+  asm("{\n.reg .b16 x0, x1, w0, w1;\nmov.b32 {x0, x1}, %2;\nmov.b32 {w0, w1}, %3;\n"
+      "fma.rn.f32.f16 %0, x0, w0, %0;\nfma.rn.f32.f16 %1, x1, w1, %1;\n}\n"
+      : "+f"(a0), "+f"(a1)
+      : "r"(x), "r"(w));
+}

@@ -477,6 +477,9 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
   unsigned char* cg = reinterpret_cast<unsigned char*>(p.C) + (coff + (int64_t)m0 * p.ldc) * 2;
   const unsigned char* pg = reinterpret_cast<const unsigned char*>(p.Z) + (coff + (int64_t)m0 * p.ldz) * 2;
   float m = -INFINITY, l = 0.f, dot = 0.f;
+  // the softmax runs in the base-2 domain: t = acc * alpha * log2(e), p = 2^(t - max) — one FMUL/FFMA and one
+  // single-instruction ex2.approx.ftz per element (expf's default form wraps the MUFU in a denormal-scaling sequence)
+  const float a2 = p.alpha * 1.4426950408889634f;
 #pragma unroll 1
   for (int c = 0; c < ncols; c += 32) {
     uint32_t r[32];
@@ -487,15 +490,15 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
       float mloc = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        float v = (c + i < ncols) ? __uint_as_float(r[i]) * p.alpha : -INFINITY;
+        float v = (c + i < ncols) ? __uint_as_float(r[i]) * a2 : -INFINITY;
         r[i] = __float_as_uint(v);
         mloc = fmaxf(mloc, v);
       }
       const float mnew = fmaxf(m, mloc);
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sum += __expf(__uint_as_float(r[i]) - mnew);
-      l = l * __expf(m - mnew) + sum;
+      for (int i = 0; i < 32; ++i) sum += ex2_ftz(__uint_as_float(r[i]) - mnew);
+      l = l * ex2_ftz(m - mnew) + sum;
       m = mnew;
     } else {
       __syncwarp();
@@ -517,7 +520,7 @@ __device__ __forceinline__ void softmax_rows(const TcParams& p, int64_t coff, ui
     tmem_ld_wait();
     if (EPI == EPI_SOFTMAX) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (c + i < ncols) ? __expf(__uint_as_float(r[i]) * p.alpha - m) * inv : 0.f;
+      for (int i = 0; i < 32; ++i) v[i] = (c + i < ncols) ? ex2_ftz(fmaf(__uint_as_float(r[i]), a2, -m)) * inv : 0.f;
     } else {
       __syncwarp();
       float pf[32];

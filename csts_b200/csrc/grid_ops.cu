@@ -210,10 +210,12 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
     p.in = p.in2; p.out = p.out2; p.w = p.w2; p.gamma = p.gamma2; p.beta = p.beta2; p.pre = p.pre2; p.mean = p.mean2; p.rstd = p.rstd2;
   }
   constexpr int NJ = (D + 127) / 128;
-  __shared__ float s_w[27 * D];
+  // the kernel in the activations' 16-bit type (what conv3d computes with under the reference's autocast): products
+  // of two 16-bit values then go through the mixed-precision FMA with no unpack instruction (common.cuh::fhfma2)
+  __shared__ __align__(16) T s_w[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
     int tap = i / D, c = i - tap * D;
-    s_w[i] = p.w[c * 27 + tap];               // parameter layout (d,1,3,3,3) -> [tap][c]
+    st_f(&s_w[i], p.w[c * 27 + tap]);         // parameter layout (d,1,3,3,3) -> [tap][c]
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -260,11 +262,11 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           if (4 * lane + 128 * j < D) {
-            float v[TI][4], w3[3][4];
+            uint2 v[TI], w3[3];
 #pragma unroll
-            for (int ti = 0; ti < TI; ++ti) ld4(src + ti * sT + 128 * j, v[ti]);
+            for (int ti = 0; ti < TI; ++ti) v[ti] = *reinterpret_cast<const uint2*>(src + ti * sT + 128 * j);
 #pragma unroll
-            for (int kt = 0; kt < 3; ++kt) ld4(s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane + 128 * j, w3[kt]);
+            for (int kt = 0; kt < 3; ++kt) w3[kt] = *reinterpret_cast<const uint2*>(s_w + ((kt * 3 + kh) * 3 + kw) * D + 4 * lane + 128 * j);
             // (plane, kt) -> output pairing, resolved at compile time
 #pragma unroll
             for (int a = 0; a < (TRANSPOSED ? TI : TO); ++a)
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
                 const int other = a * ST + kt - 1;                 // transposed: a = ti, other = to;  regular: a = to, other = ti
                 if (other < 0 || other >= (TRANSPOSED ? TO : TI)) continue;
                 const int ti = TRANSPOSED ? a : other, to = TRANSPOSED ? other : a;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[to][j][i] = fmaf(v[ti][i], w3[kt][i], acc[to][j][i]);
+                fhfma2<T>(acc[to][j][0], acc[to][j][1], v[ti].x, w3[kt].x);
+                fhfma2<T>(acc[to][j][2], acc[to][j][3], v[ti].y, w3[kt].y);
               }
           }
         }
@@ -481,30 +483,19 @@ __global__ void __launch_bounds__(192) dwconv_wgrad_tcol_kernel(csts_wgrad_args 
 #pragma unroll
         for (int t = 0; t < TBG; ++t) braw[kw][t] = ok ? __ldg(reinterpret_cast<const uint2*>(bp + wb * bsP + t * bsT)) : make_uint2(0u, 0u);
       }
-      float sv[TSM][4];
+      // both factors are 16-bit and of one type (the launcher guarantees it): mixed-precision FMAs on the packed pairs
+      static_assert(sizeof(TS) == 2 && sizeof(TB) == 2, "16-bit operands");
 #pragma unroll
-      for (int t = 0; t < TSM; ++t) {
-        float2 lo = unpack2<TS>(sraw[t].x), hi = unpack2<TS>(sraw[t].y);
-        sv[t][0] = lo.x; sv[t][1] = lo.y; sv[t][2] = hi.x; sv[t][3] = hi.y;
-      }
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        float bv[TBG][4];
-#pragma unroll
-        for (int t = 0; t < TBG; ++t) {
-          float2 lo = unpack2<TB>(braw[kw][t].x), hi = unpack2<TB>(braw[kw][t].y);
-          bv[t][0] = lo.x; bv[t][1] = lo.y; bv[t][2] = hi.x; bv[t][3] = hi.y;
-        }
+      for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt)
 #pragma unroll
           for (int ts = 0; ts < TSM; ++ts) {
             const int tb = ts * ST + kt - 1;
             if (tb < 0 || tb >= TBG) continue;                          // resolved at compile time
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[kt][kw][i] = fmaf(sv[ts][i], bv[tb][i], acc[kt][kw][i]);
+            fhfma2<TS>(acc[kt][kw][0], acc[kt][kw][1], sraw[ts].x, braw[kw][tb].x);
+            fhfma2<TS>(acc[kt][kw][2], acc[kt][kw][3], sraw[ts].y, braw[kw][tb].y);
           }
-      }
     }
     if (++ws == p.Ws) { ws = 0; if (++hs == p.Hs) { hs = 0; if (++hd == p.heads) { hd = 0; ++b; } } }
   }
