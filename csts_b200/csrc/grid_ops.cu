@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) dwconv_tcol_kernel(csts_pool_args p, int 
         for (int j = 0; j < NJ; ++j) {
           int c = 4 * lane + 128 * j;
           if (c < D) {
-            float g[4], be[4], y[4];
+            float g[4], be[4], y[4];           // (re-loaded per output: keeping them in registers costs occupancy — measured slower)
             ld4(p.gamma + c, g);
             ld4(p.beta + c, be);
 #pragma unroll
@@ -438,16 +438,21 @@ __global__ void __launch_bounds__(288) dwconv_wgrad_kernel(csts_wgrad_args p, in
 template <typename TS, typename TB, int TSM, int TBG, int ST>
 __global__ void __launch_bounds__(192) dwconv_wgrad_tcol_kernel(csts_wgrad_args p, int lh, int lw, int cols_per_slot) {
   pdl_wait();
-  if (blockIdx.y == 1) { p.small = p.small2; p.big = p.big2; p.dw = p.dw2; }   // second problem of the launch
+  // blockIdx.y = (problem of the launch) * groups + (96-channel group of the head): depthwise channels are independent, so a
+  // 192-channel head is two 96-channel problems whose operands start 96 elements further on
+  const int groups = gridDim.y / (p.small2 ? 2 : 1);
+  if ((int)blockIdx.y >= groups) { p.small = p.small2; p.big = p.big2; p.dw = p.dw2; }
   constexpr int D = 96;
+  const int cg = blockIdx.y % groups;
   __shared__ float s_dw[27 * D];
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) s_dw[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kh = warp % 3, slot = warp / 3, slots = (blockDim.x >> 5) / 3;
   const bool active = 4 * lane < D;
-  const TS* small = reinterpret_cast<const TS*>(p.small);
-  const TB* big = reinterpret_cast<const TB*>(p.big);
+  const TS* small = reinterpret_cast<const TS*>(p.small) + cg * D;
+  const TB* big = reinterpret_cast<const TB*>(p.big) + cg * D;
+  float* dw = p.dw + cg * D * 27;
   const int HWs = p.Hs * p.Ws;
   const int64_t total = (int64_t)p.B * p.heads * HWs;
   const int ssP = (int)p.small_sP, bsP = (int)p.big_sP;
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(192) dwconv_wgrad_tcol_kernel(csts_wgrad_args 
   __syncthreads();
   for (int i = threadIdx.x; i < 27 * D; i += blockDim.x) {
     int tap = i / D, c = i - tap * D;
-    atomicAdd(p.dw + c * 27 + tap, s_dw[i]);
+    atomicAdd(dw + c * 27 + tap, s_dw[i]);
   }
 }
 
@@ -943,7 +948,7 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
                "dwconv_wgrad: operand dtypes must be 1 (bf16) or 2 (f16)");
   cudaStream_t st = (cudaStream_t)stream;
   static const bool no_tcol = getenv("CSTS_NO_TCOL") != nullptr;       // A/B tuning runs only
-  if (p->d == 96 && p->small_dtype == p->big_dtype && !no_tcol &&
+  if ((p->d == 96 || p->d == 192) && p->small_dtype == p->big_dtype && !no_tcol &&
       ((p->st == 1 && p->Ts == 4 && p->Tb == 4) || (p->st == 2 && p->Ts == 4 && p->Tb == 8))) {
     // T-column kernel: 2 column slots x 3 kernel rows per block; every block ends with 27*d global atomics, so at
     // most 3 blocks per SM
@@ -952,10 +957,11 @@ int csts_dwconv_wgrad(const csts_wgrad_args* p, void* stream) {
     int64_t nslots = cols < (int64_t)csts_num_sms() * slot_mult ? cols : (int64_t)csts_num_sms() * slot_mult;
     int cols_per_warp = (int)((cols + nslots - 1) / nslots);
     int cgrid = (int)((cols + (int64_t)cols_per_warp * 2 - 1) / ((int64_t)cols_per_warp * 2));
+    const int ny = (p->small2 ? 2 : 1) * (p->d / 96);               // grid.y: [problem][96-channel group of the head]
 #define WGRAD_TCOL(TS_, TB_)                                                                                          \
   do {                                                                                                                \
-    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid, p->small2 ? 2 : 1), dim3(192), 0, st, *p, lh, lw, cols_per_warp); \
-    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid, p->small2 ? 2 : 1), dim3(192), 0, st, *p, lh, lw, cols_per_warp);            \
+    if (p->st == 1) launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 4, 1>, dim3(cgrid, ny), dim3(192), 0, st, *p, lh, lw, cols_per_warp); \
+    else launch_pdl(dwconv_wgrad_tcol_kernel<TS_, TB_, 4, 8, 2>, dim3(cgrid, ny), dim3(192), 0, st, *p, lh, lw, cols_per_warp);            \
   } while (0)
     if (p->small_dtype == CSTS_F16) WGRAD_TCOL(f16, f16);
     else WGRAD_TCOL(bf16, bf16);

@@ -701,12 +701,13 @@ def test_rowwise_and_pool_kernels_f16_storage():
     assert rel_err(dqkv[:, :, 0].permute(0, 2, 3, 1).reshape(B * h, d, *thw), xr.grad) < 8e-4
 
 
-@pytest.mark.parametrize("thw,stride", [((4, 16, 16), (1, 2, 2)), ((2, 8, 8), (1, 1, 1))])
-def test_paired_pool_launch_equals_two_single_launches(thw, stride):
+@pytest.mark.parametrize("thw,stride,d", [((4, 16, 16), (1, 2, 2), 96), ((2, 8, 8), (1, 1, 1), 96), ((4, 8, 8), (1, 4, 4), 192)])
+def test_paired_pool_launch_equals_two_single_launches(thw, stride, d):
     """The k and v pools of a block run as one launch (grid.y = 2): forward (+LayerNorm), adjoint gather and weight
-    gradient must equal the single-problem launches bit for bit."""
+    gradient must equal the single-problem launches bit for bit.  (192-channel heads: the weight gradient runs as two
+    96-channel groups per problem, grid.y = 4.)"""
     k = K()
-    B, h, d = 2, 2, 96
+    B, h = 2, 2
     N = thw[0] * thw[1] * thw[2]
     Cn = h * d
     g = torch.Generator(device="cpu").manual_seed(31)
