@@ -225,6 +225,8 @@ def pool_tokens(t, thw, w, stride, ln_w, ln_b, transposed=False):
     """
     B, h, L, d = t.shape
     g = _to_grid(t, thw)
+    w = rnd_f(w, "poolw")       # storage emulation: the kernel in the activations' 16-bit type (conv3d under autocast; the CUDA
+                                # path's mixed-precision FMAs take both factors in 16 bits); its gradient stays f32
     if transposed:
         op = tuple(0 if s == 1 else s - 1 for s in stride)
         g = F.conv_transpose3d(g, w, None, stride=stride, padding=1, output_padding=op, groups=d)
