@@ -11,6 +11,8 @@ the world size so that â€” after DDP's mean all-reduce of parameter gradients â€
 the gradient of the single-process global-batch loss (each rank evaluates the full-batch NCE loss
 but can only differentiate through its own rows).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -135,7 +137,6 @@ class OverlappedGradSync:
         self.groups, self.ranges, self.group_of, self.pending = [], [], {}, []
         self.stream = None
         self.enabled = False
-        import os
         factored = model.factored_grad_params() if hasattr(model, "factored_grad_params") and \
             os.environ.get("CSTS_FACTORED_WGRAD", "1") == "1" else []
         self.factored = {id(p) for p in factored}
